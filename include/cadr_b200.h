@@ -1,0 +1,277 @@
+/* cadr_b200.h — C ABI of libcadr_b200.so, the B200 (sm_100a) backend for CADR's per-frame
+ * drawable processing and data upload.
+ *
+ * The reference (Rendering-FIT/CADR) has no FFI/plugin seam of its own: CadR is a C++ class library
+ * whose GPU work is recorded into Vulkan command buffers.  The two places where control crosses from
+ * scene bookkeeping to GPU work are
+ *     CadR::Renderer::recordDrawableProcessing   src/CadR/Renderer.cpp:598-720
+ *     CadR::Renderer::executeCopyOperations      src/CadR/Renderer.cpp:946-999
+ * and everything the GPU needs there is (a) the 32-byte push-constant block
+ * {handleTableRoot, drawableListPtr, indirectDataPtr, drawablePointersBufferPtr}
+ * (src/CadR/shaders/processDrawables.comp:68-74, Renderer.cpp:677-682) and (b) the copy-region
+ * triples {srcOffset, dstOffset, size} (src/CadR/DataMemory.cpp:417-425).  This ABI is cut exactly
+ * there.  Every entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in signatures; a stream is an opaque `void*` holding a
+ *     cudaStream_t (NULL = the context's own stream);
+ *   - device addresses are raw 64-bit CUDA device pointers and play the role of VkDeviceAddress;
+ *   - every call returns CADR_OK (0) or a negative error; the message is kept per thread and read with
+ *     cadr_b200_last_error().  Error taxonomy mirrors src/CadR/Exceptions.h:13-40
+ *     (LogicError / OutOfResources / Timeout) plus CADR_E_CUDA for driver/runtime failures;
+ *   - a context is bound to one GPU; calls on one context must be externally serialised (the reference
+ *     is single-threaded: no mutex/atomic anywhere in src/CadR); all device work is stream-ordered and
+ *     asynchronous, cadr_b200_sync() is the fence wait;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry fails with CADR_E_NO_DEVICE.
+ */
+#ifndef CADR_B200_H
+#define CADR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+# define CADR_API
+#else
+# define CADR_API __attribute__((visibility("default")))
+#endif
+
+#define CADR_B200_ABI_VERSION 1
+
+/* ---- error codes (src/CadR/Exceptions.h:13-40) ------------------------------------------------- */
+enum {
+	CADR_OK                  =  0,
+	CADR_E_LOGIC             = -1,  /* CadR::LogicError: bad argument / API misuse                 */
+	CADR_E_OUT_OF_RESOURCES  = -2,  /* CadR::OutOfResources: device/host allocation failed          */
+	CADR_E_TIMEOUT           = -3,  /* CadR::Timeout: fence wait expired (Renderer.cpp:989-993)      */
+	CADR_E_CUDA              = -4,  /* vk::Error analogue: CUDA runtime/driver error                 */
+	CADR_E_NO_DEVICE         = -5,  /* no CUDA device: compute entry called on an address-only ctx   */
+	CADR_E_OVERFLOW          = -6   /* an output region given to cadr_b200_cull_compact was too small */
+};
+
+typedef struct cadr_ctx cadr_ctx;
+typedef void* cadr_stream;  /* cudaStream_t */
+
+/* ---- device layouts (little-endian, std430) ---------------------------------- */
+
+/* DrawableGpuData, 48 B — src/CadR/Drawable.h:32-43, processDrawables.comp:17-27 */
+typedef struct cadr_drawable_gpu_data {
+	uint64_t vertexDataHandle;
+	uint64_t indexDataHandle;
+	uint64_t matrixListHandle;
+	uint64_t drawableDataHandle;   /* 0 = none (looked up like any other: slot 0 is zero)          */
+	uint64_t primitiveSetHandle;
+	uint32_t primitiveSetOffset;   /* BYTES into the PrimitiveSet array                            */
+	uint32_t padding;
+} cadr_drawable_gpu_data;
+
+/* PrimitiveSet, 8 B — src/CadR/PrimitiveSet.h:12-15, processDrawables.comp:29-33 */
+typedef struct cadr_primitive_set { uint32_t count, first; } cadr_primitive_set;
+
+/* IndirectData == VkDrawIndirectCommand, 16 B — processDrawables.comp:43-50, Renderer.cpp:467 */
+typedef struct cadr_indirect_data {
+	uint32_t vertexCount, instanceCount, firstVertex, baseInstance;
+} cadr_indirect_data;
+
+/* DrawablePointers, 32 B — processDrawables.comp:52-59, Renderer.h:201 */
+typedef struct cadr_drawable_pointers {
+	uint64_t vertexDataPtr, indexDataPtr, matrixListPtr, drawableDataPtr;
+} cadr_drawable_pointers;
+
+/* MatrixList block: 64-B header {u32 numMatrices, u32 capacity, 56 B zero} + N x mat4 (column-major
+ * f32) — src/CadR/MatrixList.h:54-59, processDrawables.comp:35-41 */
+#define CADR_MATRIX_LIST_HEADER_BYTES 64u
+#define CADR_MATRIX_BYTES             64u
+
+/* Handle table node: 2048 x u64 — src/CadR/HandleTable.h:33-35 */
+#define CADR_HANDLES_PER_TABLE   2048u
+#define CADR_HANDLE_LEVEL_SHIFT  11u
+#define CADR_HANDLE_LEVEL_MASK   0x7ffu
+
+/* ---- Tier X (north-star extension; NOT present in the reference: parity unpinned) --------------- */
+
+/* VkDrawIndexedIndirectCommand, 20 B */
+typedef struct cadr_draw_indexed_indirect {
+	uint32_t indexCount, instanceCount, firstIndex;
+	int32_t  vertexOffset;
+	uint32_t firstInstance;     /* index of the first entry of this run in the instance-index buffer */
+} cadr_draw_indexed_indirect;
+
+/* Per-drawable culling record, 48 B, array parallel to the drawable list.
+ * sphere = CadR::BoundingSphere {vec3 center, float radius} in model space
+ * (src/CadR/BoundingSphere.h:18-21); radius < 0 means empty => never visible (:39-43). */
+typedef struct cadr_drawable_cull_data {
+	float    sphere[4];
+	uint32_t lodCount;                   /* 1..3                                                    */
+	uint32_t lodPrimitiveSetOffset[3];   /* bytes into the PrimitiveSet array, like primitiveSetOffset */
+	float    lodThreshold[2];            /* ascending eye distances; lod = #(threshold <= dist)      */
+	uint32_t stateSetIndex;              /* index into cadr_cull_params::stateSetRegions             */
+	uint32_t reserved;
+} cadr_drawable_cull_data;
+
+/* Output region of one StateSet (element indices into cmdOut/ptrOut/tagOut resp. instOut). */
+typedef struct cadr_stateset_region {
+	uint32_t cmdBase, cmdCapacity, instBase, instCapacity;
+} cadr_stateset_region;
+
+/* {drawableIndex, lod} of an emitted command — used for canonical sorting and by the consumer. */
+typedef struct cadr_command_tag { uint32_t drawableIndex, lod; } cadr_command_tag;
+
+/* Head of the counters buffer; followed by numStateSets packed u64:
+ *   low 32 bits  = number of commands emitted for the StateSet (usable directly as the count buffer
+ *                  of vkCmdDrawIndexedIndirectCount),
+ *   high 32 bits = number of instance indices emitted for the StateSet. */
+typedef struct cadr_cull_header {
+	uint32_t status;          /* bit 0: a region overflowed, bit 1: chunk workspace overflowed       */
+	uint32_t nearBandCount;   /* instances within 1e-5 of a frustum plane or LOD threshold           */
+	uint32_t chunkCount;      /* internal: work items queued for the large-list kernel               */
+	uint32_t chunkCursor;     /* internal: work items taken                                          */
+	uint32_t visibleInstances;
+	uint32_t reserved[11];
+} cadr_cull_header;           /* 64 B */
+#define CADR_CULL_STATUS_REGION_OVERFLOW 1u
+#define CADR_CULL_STATUS_CHUNK_OVERFLOW  2u
+
+typedef struct cadr_cull_params {
+	/* Tier R inputs, same meaning as the push constants (processDrawables.comp:68-74) */
+	uint64_t handleTableRoot;
+	uint32_t handleLevel;        /* 1..3                                                            */
+	uint32_t numDrawables;
+	uint64_t drawableList;       /* cadr_drawable_gpu_data[numDrawables]                            */
+	/* Tier R outputs of this frame, consumed here (numMatrices, matrixListPtr, pointers to forward) */
+	uint64_t indirectData;       /* cadr_indirect_data[numDrawables]                                */
+	uint64_t drawablePointers;   /* cadr_drawable_pointers[numDrawables]                            */
+	/* Tier X inputs */
+	uint64_t cullData;           /* cadr_drawable_cull_data[numDrawables]                           */
+	float    planes[6][4];       /* world-space (nx,ny,nz,d), inward-facing, unit normals           */
+	float    eye[4];             /* camera position xyz, w unused                                   */
+	uint32_t numStateSets;
+	uint32_t reserved0;
+	uint64_t stateSetRegions;    /* cadr_stateset_region[numStateSets]                              */
+	/* outputs */
+	uint64_t cmdOut;             /* cadr_draw_indexed_indirect[], 20-B stride                       */
+	uint64_t ptrOut;             /* cadr_drawable_pointers[], parallel to cmdOut                    */
+	uint64_t tagOut;             /* cadr_command_tag[], parallel to cmdOut                          */
+	uint64_t instOut;            /* uint32_t instance indices                                       */
+	uint64_t counters;           /* cadr_cull_header + uint64_t[numStateSets]; zeroed by the call    */
+	/* scratch */
+	uint64_t chunkWorkspace;     /* 8 B per work item of the large-list kernel                      */
+	uint32_t chunkCapacity;      /* >= sum over drawables with > 32 matrices of ceil(n/1024)         */
+	uint32_t reserved1;
+} cadr_cull_params;
+
+/* ---- upload ------------------------------------------------------------------ */
+
+/* One copy region == one vk::BufferCopy recorded by DataMemory::recordUploads
+ * (src/CadR/DataMemory.cpp:417-425): src is an offset into the staging block, dst a device address. */
+typedef struct cadr_copy_region {
+	uint64_t dstAddr;
+	uint64_t srcOffset;
+	uint64_t bytes;
+} cadr_copy_region;
+
+/* One handle-table update == HandleTable::set(handle, addr) (src/CadR/HandleTable.cpp:348-378). */
+typedef struct cadr_handle_patch { uint64_t handle, addr; } cadr_handle_patch;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+
+CADR_API int         cadr_b200_abi_version(void);
+CADR_API const char* cadr_b200_last_error(void);
+
+/* Replaces VulkanLibrary::load + VulkanInstance::chooseDevice + VulkanDevice::create + Renderer::init
+ * (src/CadR/Renderer.cpp:97-313): binds the context to CUDA device `device`, creates its stream and
+ * scratch buffers.  Fails with CADR_E_NO_DEVICE when no usable GPU exists. */
+CADR_API int  cadr_b200_create(int device, cadr_ctx** out);
+
+/* Address-space-only context for host-logic tests on machines without a GPU: arena_alloc hands out
+ * addresses from a fake range, host_alloc uses plain memory, and every entry that would touch a device
+ * returns CADR_E_NO_DEVICE.  It computes nothing. */
+CADR_API int  cadr_b200_create_address_space_only(cadr_ctx** out);
+
+CADR_API void cadr_b200_destroy(cadr_ctx* ctx);
+CADR_API int  cadr_b200_device(const cadr_ctx* ctx);            /* CUDA device index, -1 = address-only */
+CADR_API int  cadr_b200_sm_count(const cadr_ctx* ctx);
+CADR_API cadr_stream cadr_b200_stream(const cadr_ctx* ctx);     /* the context's own stream             */
+
+/* Fence wait — vkWaitForFences in Renderer::executeCopyOperations (Renderer.cpp:982-993).
+ * timeout_ns == 0 waits forever; on expiry returns CADR_E_TIMEOUT (CadR::Timeout). */
+CADR_API int  cadr_b200_sync(cadr_ctx* ctx, cadr_stream stream, uint64_t timeout_ns);
+
+/* ---- memory ------------------------------------------------------------------------------------- */
+
+/* Device buffer with an address — stands in for vkCreateBuffer + allocatePointerAccessMemory +
+ * getBufferDeviceAddress (src/CadR/DataMemory.cpp:36-94, Renderer.cpp:489-591).  256-B aligned. */
+CADR_API int  cadr_b200_arena_alloc(cadr_ctx* ctx, size_t bytes, uint64_t* devAddr);
+CADR_API int  cadr_b200_arena_free(cadr_ctx* ctx, uint64_t devAddr);
+
+/* Host-visible, host-cached, mapped staging block — StagingMemory::StagingMemory
+ * (src/CadR/StagingMemory.cpp:29-76).  Pinned so that uploads are true DMA. */
+CADR_API int  cadr_b200_host_alloc(cadr_ctx* ctx, size_t bytes, void** hostPtr);
+CADR_API int  cadr_b200_host_free(cadr_ctx* ctx, void* hostPtr);
+
+CADR_API int  cadr_b200_memcpy_h2d(cadr_ctx* ctx, uint64_t dstAddr, const void* src, size_t bytes, cadr_stream stream);
+CADR_API int  cadr_b200_memcpy_d2h(cadr_ctx* ctx, void* dst, uint64_t srcAddr, size_t bytes, cadr_stream stream);
+CADR_API int  cadr_b200_memset(cadr_ctx* ctx, uint64_t dstAddr, int value, size_t bytes, cadr_stream stream);
+
+/* ---- upload path -------------------------------------------------------------------------------- */
+
+/* DataMemory::recordUploads (src/CadR/DataMemory.cpp:400-446): copy `n` regions from the host staging
+ * block `stagingBase` to device addresses.  Regions at or above CADR_UPLOAD_DMA_THRESHOLD bytes go out
+ * as individual async DMA copies (what vkCmdCopyBuffer does); smaller ones are packed into one DMA to
+ * a device mirror followed by ONE scatter-copy kernel launch. */
+CADR_API int  cadr_b200_upload(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n,
+                               const void* stagingBase, cadr_stream stream);
+
+/* Device-side scatter only: staging already resident in HBM at `stagingDevAddr` (srcOffset relative to
+ * it).  This is the kernel the HBM roofline is quoted on for the upload path. */
+CADR_API int  cadr_b200_scatter_copy(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n,
+                                     uint64_t stagingDevAddr, cadr_stream stream);
+
+/* HandleTable::set without the 16 KiB whole-leaf re-upload (src/CadR/HandleTable.cpp:58-68,348-378):
+ * walks root -> [mid ->] leaf on the device and stores the 8-byte entry in place. */
+CADR_API int  cadr_b200_patch_handles(cadr_ctx* ctx, uint64_t handleTableRoot, uint32_t handleLevel,
+                                      const cadr_handle_patch* patches, uint32_t n, cadr_stream stream);
+
+/* ---- drawable processing (Tier R: what processDrawables.comp computes) -------------------------- */
+
+/* vkCmdPushConstants + vkCmdDispatch[Base] of processDrawables.comp
+ * (src/CadR/Renderer.cpp:669-692; shader main() :92-113).  Same four addresses, same order.
+ * numDrawables must be < 2^30 (Renderer.cpp:687).  numDrawables == 0 is a no-op (Renderer.cpp:600-620). */
+CADR_API int  cadr_b200_process_drawables(cadr_ctx* ctx, uint64_t handleTableRoot, uint32_t handleLevel,
+                                          uint64_t drawableList, uint64_t indirectOut, uint64_t pointersOut,
+                                          uint64_t numDrawables, cadr_stream stream);
+
+/* The whole of Renderer::recordDrawableProcessing (Renderer.cpp:598-720): DMA numDrawables*48 bytes
+ * from the host staging list to `drawableList` (:635-644), then process them. */
+CADR_API int  cadr_b200_record_drawable_processing(cadr_ctx* ctx, const cadr_drawable_gpu_data* hostDrawableList,
+                                                   uint64_t handleTableRoot, uint32_t handleLevel,
+                                                   uint64_t drawableList, uint64_t indirectOut, uint64_t pointersOut,
+                                                   uint64_t numDrawables, cadr_stream stream);
+
+/* ---- Tier X: frustum culling + LOD selection + stream compaction -------------------------------- */
+
+/* No reference counterpart.  Specification: DESIGN.md "Tier X". */
+CADR_API int  cadr_b200_cull_compact(cadr_ctx* ctx, const cadr_cull_params* params, cadr_stream stream);
+
+/* Size of the counters buffer for `numStateSets` StateSets. */
+CADR_API size_t cadr_b200_cull_counters_bytes(uint32_t numStateSets);
+
+/* ---- timing (FrameInfo timestamps, src/CadR/Renderer.cpp:436,660,696,778) ----------------------- */
+
+/* When enabled, process_drawables / cull_compact / upload bracket each kernel with CUDA events.
+ * cadr_b200_kernel_times returns, after a sync, the milliseconds of the most recent call:
+ * [0] process_drawables, [1] cull small-list kernel, [2] cull large-list kernel,
+ * [3] scatter copy, [4] handle patch.  Unused slots are 0. */
+CADR_API int  cadr_b200_set_profiling(cadr_ctx* ctx, int enabled);
+CADR_API int  cadr_b200_kernel_times(cadr_ctx* ctx, float* ms, uint32_t n);
+/* How many kernels of this library the context has launched since creation. */
+CADR_API uint64_t cadr_b200_launch_count(const cadr_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

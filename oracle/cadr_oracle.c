@@ -1,0 +1,347 @@
+/* cadr_oracle.c — CPU restatement of CADR's drawable-processing path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
+ * library; the product (libcadr_b200.so, cadr_b200/) never does and has no CPU fallback.
+ *
+ * Tier R  (oracle_process_drawables): line-by-line restatement of the reference compute shader
+ *         /root/reference/src/CadR/shaders/processDrawables.comp  main() :92-113, lookupHandle() :77-89,
+ *         layouts :17-64.  Integer only, order-deterministic: output slot i <-> drawable i.
+ *         PINNING: the reference's own tests hold no vector for this shader and no Vulkan ICD
+ *         exists in this environment, so the shader cannot be executed natively.  It is pinned instead by
+ *         tests/golden/process_drawables_*.json, produced by running the reference's OWN SPIR-V (compiled
+ *         from the unmodified .comp by the reference's vendored glslangValidator) through
+ *         oracle/spirv_run.py — see oracle/make_golden.py.
+ * Tier X  (oracle_cull_compact): frustum culling + LOD + compaction.  The reference has NO implementation
+ *          => PARITY UNPINNED BY THE REFERENCE.  The sphere transform restates
+ *         /root/reference/src/CadR/BoundingSphere.h:70-87 (operator*), the rest follows DESIGN.md "Tier X".
+ * Upload  (oracle_upload): the copy regions recorded by DataMemory::recordUploads,
+ *         /root/reference/src/CadR/DataMemory.cpp:400-446 (one vkCmdCopyBuffer region per marker).
+ *
+ * Device memory is modelled as a list of segments {device base address, size, host mirror}; emitted
+ * pointers are therefore numerically identical to what the GPU writes for the same arena contents.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fopenmp -fPIC -shared   (FMA contraction MUST stay off: Tier X is
+ * compared bit-for-bit with CUDA code that uses __fmul_rn/__fadd_rn).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+# include <omp.h>
+#endif
+
+typedef struct oracle_segment {
+	uint64_t base;
+	uint64_t bytes;
+	uint8_t* host;
+} oracle_segment;
+
+typedef struct oracle_mem {
+	const oracle_segment* seg;
+	uint32_t numSegs;
+} oracle_mem;
+
+/* Address translation.  A null or out-of-arena address is a fault in the reference (it would be UB on
+ * the GPU); the oracle reports it instead of emulating it. */
+static inline const uint8_t* xlate(const oracle_mem* m, uint64_t a, uint64_t n, int* fault)
+{
+	for(uint32_t i = 0; i < m->numSegs; i++) {
+		const oracle_segment* s = &m->seg[i];
+		if(a >= s->base && a + n <= s->base + s->bytes)
+			return s->host + (a - s->base);
+	}
+	*fault = 1;
+	return NULL;
+}
+static inline uint64_t load64(const oracle_mem* m, uint64_t a, int* fault)
+{
+	const uint8_t* p = xlate(m, a, 8, fault);
+	uint64_t v = 0;
+	if(p) memcpy(&v, p, 8);
+	return v;
+}
+static inline uint32_t load32(const oracle_mem* m, uint64_t a, int* fault)
+{
+	const uint8_t* p = xlate(m, a, 4, fault);
+	uint32_t v = 0;
+	if(p) memcpy(&v, p, 4);
+	return v;
+}
+
+/* lookupHandle(), processDrawables.comp:77-89.  uint(handle) truncations exactly as written there. */
+static inline uint64_t lookup_handle(const oracle_mem* m, uint64_t root, int level, uint64_t handle, int* fault)
+{
+	if(level == 1)                                                      /* :79-80 */
+		return load64(m, root + 8ull * (uint32_t)handle, fault);
+	if(level == 2) {                                                    /* :81-83 */
+		uint64_t table2 = load64(m, root + 8ull * (uint32_t)(handle >> 11), fault);
+		return load64(m, table2 + 8ull * ((uint32_t)handle & 0x7ffu), fault);
+	}
+	/* level 3 */                                                       /* :84-87 */
+	uint64_t table2 = load64(m, root + 8ull * (uint32_t)(handle >> 22), fault);
+	uint64_t table3 = load64(m, table2 + 8ull * ((uint32_t)(handle >> 11) & 0x7ffu), fault);
+	return load64(m, table3 + 8ull * ((uint32_t)handle & 0x7ffu), fault);
+}
+
+/* DrawableGpuData offsets, processDrawables.comp:17-27 / src/CadR/Drawable.h:32-43 */
+enum { D_VERTEX = 0, D_INDEX = 8, D_MATRIX = 16, D_DATA = 24, D_PRIMSET = 32, D_PSOFFSET = 40, D_SIZE = 48 };
+
+/* main(), processDrawables.comp:92-113, for drawable i.  Returns 1 on a memory fault. */
+static inline int process_one(const oracle_mem* m, uint64_t root, int level, uint64_t drawableList, uint64_t i,
+                              uint8_t* indirectOut, uint8_t* pointersOut)
+{
+	int fault = 0;
+	uint64_t d = drawableList + i * D_SIZE;                                               /* :95-96 */
+	uint64_t ps = lookup_handle(m, root, level, load64(m, d + D_PRIMSET, &fault), &fault)
+	              + load32(m, d + D_PSOFFSET, &fault);                                    /* :97 */
+	uint64_t ml = lookup_handle(m, root, level, load64(m, d + D_MATRIX, &fault), &fault); /* :98 */
+
+	uint32_t ind[4];                                                                      /* :101-105 */
+	ind[0] = load32(m, ps + 0, &fault);      /* vertexCount   = ps.count       */
+	ind[1] = load32(m, ml + 0, &fault);      /* instanceCount = ml.numMatrices */
+	ind[2] = load32(m, ps + 4, &fault);      /* firstVertex   = ps.first       */
+	ind[3] = 0;                              /* baseInstance  = 0              */
+	memcpy(indirectOut + i * 16, ind, 16);
+
+	uint64_t ptr[4];                                                                      /* :108-112 */
+	ptr[0] = lookup_handle(m, root, level, load64(m, d + D_VERTEX, &fault), &fault);
+	ptr[1] = lookup_handle(m, root, level, load64(m, d + D_INDEX, &fault), &fault);
+	ptr[2] = ml;
+	ptr[3] = lookup_handle(m, root, level, load64(m, d + D_DATA, &fault), &fault);
+	memcpy(pointersOut + i * 32, ptr, 32);
+	return fault;
+}
+
+/* Returns the number of drawables that faulted (0 = clean run). */
+uint64_t oracle_process_drawables(const oracle_segment* segs, uint32_t numSegs, uint64_t root, int level,
+                                  uint64_t drawableList, uint64_t n, uint8_t* indirectOut, uint8_t* pointersOut,
+                                  int numThreads)
+{
+	oracle_mem m = { segs, numSegs };
+	uint64_t faults = 0;
+	(void)numThreads;
+#pragma omp parallel for schedule(static) reduction(+:faults) num_threads(numThreads > 0 ? numThreads : 1)
+	for(int64_t i = 0; i < (int64_t)n; i++)
+		faults += (uint64_t)process_one(&m, root, level, drawableList, (uint64_t)i, indirectOut, pointersOut);
+	return faults;
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * Tier X
+ * ---------------------------------------------------------------------------------------------------- */
+
+typedef struct oracle_cull_result {
+	uint64_t numCommands;      /* total over all StateSets */
+	uint64_t numInstances;     /* total survivors */
+	uint64_t nearBand;
+	uint64_t faults;
+	uint32_t overflow;         /* a StateSet region was too small */
+} oracle_cull_result;
+
+/* per-instance evaluation; operation order is normative (DESIGN.md "Tier X") */
+static inline int eval_instance(const float* M /* 16 floats, column-major */, const float* bs /* xyz r */,
+                                uint32_t lodCount, float thr0, float thr1,
+                                const float planes[6][4], const float eye[3], int* nearBand)
+{
+	/* centre = mat3(M)*c + M[3].xyz                       BoundingSphere.h:73 */
+	float cx = ((M[0] * bs[0] + M[4] * bs[1]) + M[8]  * bs[2]) + M[12];
+	float cy = ((M[1] * bs[0] + M[5] * bs[1]) + M[9]  * bs[2]) + M[13];
+	float cz = ((M[2] * bs[0] + M[6] * bs[1]) + M[10] * bs[2]) + M[14];
+	/* radius = sqrt(max squared column length) * r        BoundingSphere.h:76-85 */
+	float s0 = (M[0] * M[0] + M[1] * M[1]) + M[2]  * M[2];
+	float s1 = (M[4] * M[4] + M[5] * M[5]) + M[6]  * M[6];
+	float s2 = (M[8] * M[8] + M[9] * M[9]) + M[10] * M[10];
+	float s01 = (s0 < s1) ? s1 : s0;       /* std::max */
+	float s = (s01 < s2) ? s2 : s01;
+	float r = sqrtf(s) * bs[3];
+
+	int nonEmpty = bs[3] >= 0.f;           /* BoundingSphere.h:39-43: radius -inf (or < 0) == empty */
+	int visible = nonEmpty;
+	int nearP = 0;
+	for(int k = 0; k < 6; k++) {
+		float dot = ((planes[k][0] * cx + planes[k][1] * cy) + planes[k][2] * cz) + planes[k][3];
+		visible = visible && (dot >= -r);
+		nearP = nearP || (fabsf(dot + r) < 1e-5f);
+	}
+	float dx = cx - eye[0], dy = cy - eye[1], dz = cz - eye[2];
+	float dist = sqrtf((dx * dx + dy * dy) + dz * dz);
+	int lod = 0, nearT = 0;
+	if(lodCount > 1) { lod += (thr0 <= dist) ? 1 : 0; nearT = nearT || (fabsf(dist - thr0) < 1e-5f); }
+	if(lodCount > 2) { lod += (thr1 <= dist) ? 1 : 0; nearT = nearT || (fabsf(dist - thr1) < 1e-5f); }
+	*nearBand = nonEmpty && (nearP || (visible && nearT));
+	return visible ? lod : -1;
+}
+
+/* Sequential, deterministic emission: drawables in list order, LODs ascending, instance indices ascending.
+ * Output buffers have the layouts of include/cadr_b200.h (cmd 20 B, ptr 32 B, tag 8 B, inst 4 B, counts =
+ * packed u64 per StateSet: low = commands, high = instances).  One command per non-empty (drawable, lod):
+ * the oracle does not split long lists into work items; comparisons merge the GPU's per-item commands. */
+void oracle_cull_compact(const oracle_segment* segs, uint32_t numSegs, uint64_t root, int level,
+                         uint64_t drawableList, uint32_t n,
+                         const uint8_t* indirect, const uint8_t* pointers,   /* Tier R outputs (host copies) */
+                         const uint8_t* cullData,                              /* 48 B per drawable */
+                         const float planes[6][4], const float eye[3],
+                         const uint32_t* regions, uint32_t numStateSets,       /* 4 x u32 per StateSet */
+                         uint8_t* cmdOut, uint8_t* ptrOut, uint8_t* tagOut, uint32_t* instOut, uint64_t* counts,
+                         oracle_cull_result* res)
+{
+	oracle_mem m = { segs, numSegs };
+	memset(res, 0, sizeof(*res));
+	memset(counts, 0, (size_t)numStateSets * 8);
+	uint32_t* tmp[3] = { NULL, NULL, NULL };
+	size_t tmpCap = 0;
+	for(uint32_t d = 0; d < n; d++) {
+		int fault = 0;
+		uint32_t N;            memcpy(&N, indirect + (size_t)d * 16 + 4, 4);
+		uint64_t ml;           memcpy(&ml, pointers + (size_t)d * 32 + 16, 8);
+		const uint8_t* cd = cullData + (size_t)d * 48;
+		float bs[4];           memcpy(bs, cd, 16);
+		uint32_t lodCount;     memcpy(&lodCount, cd + 16, 4);
+		uint32_t psOff[3];     memcpy(psOff, cd + 20, 12);
+		float thr[2];          memcpy(thr, cd + 32, 8);
+		uint32_t ss;           memcpy(&ss, cd + 40, 4);
+		if(lodCount < 1) lodCount = 1;
+		if(lodCount > 3) lodCount = 3;
+		if(N == 0) continue;
+		if(N > tmpCap) {
+			for(int l = 0; l < 3; l++) { free(tmp[l]); tmp[l] = (uint32_t*)malloc((size_t)N * 4); }
+			tmpCap = N;
+		}
+		const uint8_t* mats = xlate(&m, ml + 64, (uint64_t)N * 64, &fault);
+		if(!mats) { res->faults++; continue; }
+		uint32_t k[3] = { 0, 0, 0 };
+		for(uint32_t j = 0; j < N; j++) {
+			float M[16];
+			memcpy(M, mats + (size_t)j * 64, 64);
+			int nb;
+			int lod = eval_instance(M, bs, lodCount, thr[0], thr[1], planes, eye, &nb);
+			res->nearBand += (uint64_t)nb;
+			if(lod >= 0) tmp[lod][k[lod]++] = j;
+		}
+		uint32_t nCmd = (k[0] ? 1u : 0u) + (k[1] ? 1u : 0u) + (k[2] ? 1u : 0u), nInst = k[0] + k[1] + k[2];
+		if(nInst == 0) continue;
+		if(ss >= numStateSets) { res->faults++; continue; }
+		const uint32_t* reg = regions + (size_t)ss * 4;   /* cmdBase, cmdCap, instBase, instCap */
+		uint32_t cmdOff = (uint32_t)counts[ss], instOff = (uint32_t)(counts[ss] >> 32);
+		counts[ss] += (uint64_t)nCmd | ((uint64_t)nInst << 32);
+		if(cmdOff + nCmd > reg[1] || instOff + nInst > reg[3]) { res->overflow = 1; continue; }
+		uint64_t psBase = lookup_handle(&m, root, level, load64(&m, drawableList + (uint64_t)d * D_SIZE + D_PRIMSET, &fault), &fault);
+		uint32_t ci = reg[0] + cmdOff, ii = reg[2] + instOff;
+		for(uint32_t l = 0; l < 3; l++) {
+			if(k[l] == 0) continue;
+			uint32_t cmd[5];
+			cmd[0] = load32(&m, psBase + psOff[l] + 0, &fault);   /* indexCount    */
+			cmd[1] = k[l];                                        /* instanceCount */
+			cmd[2] = load32(&m, psBase + psOff[l] + 4, &fault);   /* firstIndex    */
+			cmd[3] = 0;                                           /* vertexOffset  */
+			cmd[4] = ii;                                          /* firstInstance */
+			memcpy(cmdOut + (size_t)ci * 20, cmd, 20);
+			memcpy(ptrOut + (size_t)ci * 32, pointers + (size_t)d * 32, 32);
+			uint32_t tag[2] = { d, l };
+			memcpy(tagOut + (size_t)ci * 8, tag, 8);
+			memcpy(instOut + ii, tmp[l], (size_t)k[l] * 4);
+			ci++; ii += k[l];
+			res->numCommands++;
+		}
+		res->numInstances += nInst;
+		res->faults += (uint64_t)fault;
+	}
+	for(int l = 0; l < 3; l++) free(tmp[l]);
+}
+
+/* Throughput variant for the CPU baseline: evaluates every instance of drawables [first, first+count) on
+ * numThreads threads and returns the number of survivors (no emission; emission is O(survivors) and
+ * sequential by construction).  Used only for timing. */
+uint64_t oracle_cull_count(const oracle_segment* segs, uint32_t numSegs, uint32_t first, uint32_t count,
+                           const uint8_t* indirect, const uint8_t* pointers, const uint8_t* cullData,
+                           const float planes[6][4], const float eye[3], uint64_t* instancesVisited, int numThreads)
+{
+	oracle_mem m = { segs, numSegs };
+	uint64_t survivors = 0, visited = 0;
+	(void)numThreads;
+#pragma omp parallel for schedule(dynamic, 16) reduction(+:survivors, visited) num_threads(numThreads > 0 ? numThreads : 1)
+	for(int64_t dd = 0; dd < (int64_t)count; dd++) {
+		uint32_t d = first + (uint32_t)dd;
+		int fault = 0;
+		uint32_t N;            memcpy(&N, indirect + (size_t)d * 16 + 4, 4);
+		uint64_t ml;           memcpy(&ml, pointers + (size_t)d * 32 + 16, 8);
+		const uint8_t* cd = cullData + (size_t)d * 48;
+		float bs[4];           memcpy(bs, cd, 16);
+		uint32_t lodCount;     memcpy(&lodCount, cd + 16, 4);
+		float thr[2];          memcpy(thr, cd + 32, 8);
+		if(lodCount < 1) lodCount = 1;
+		if(lodCount > 3) lodCount = 3;
+		if(N == 0) continue;
+		const uint8_t* mats = xlate(&m, ml + 64, (uint64_t)N * 64, &fault);
+		if(!mats) continue;
+		for(uint32_t j = 0; j < N; j++) {
+			float M[16];
+			memcpy(M, mats + (size_t)j * 64, 64);
+			int nb;
+			survivors += eval_instance(M, bs, lodCount, thr[0], thr[1], planes, eye, &nb) >= 0;
+		}
+		visited += N;
+	}
+	if(instancesVisited) *instancesVisited = visited;
+	return survivors;
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * Upload: DataMemory::recordUploads, DataMemory.cpp:400-446 — one copy per marker:
+ *   src = stagingStart - stagingBufferStart, dst = marker.deviceAddress, size = stagingEnd - stagingStart.
+ * Regions are {dstAddr, srcOffset, bytes} triples (24 B each). Returns the number of faulting regions.
+ * ---------------------------------------------------------------------------------------------------- */
+uint64_t oracle_upload(const oracle_segment* segs, uint32_t numSegs, const uint64_t* regions, uint32_t n,
+                       const uint8_t* staging)
+{
+	oracle_mem m = { segs, numSegs };
+	uint64_t faults = 0;
+	for(uint32_t i = 0; i < n; i++) {
+		uint64_t dst = regions[3 * i], src = regions[3 * i + 1], bytes = regions[3 * i + 2];
+		if(bytes == 0) continue;
+		int fault = 0;
+		uint8_t* p = (uint8_t*)xlate(&m, dst, bytes, &fault);
+		if(!p) { faults++; continue; }
+		memcpy(p, staging + src, bytes);
+	}
+	return faults;
+}
+
+/* HandleTable::set as seen by the device after the upload: the 8-byte slot of `handle` holds `addr`
+ * (HandleTable.cpp:348-378; table walk as lookupHandle). */
+uint64_t oracle_patch_handles(const oracle_segment* segs, uint32_t numSegs, uint64_t root, int level,
+                              const uint64_t* patches /* handle, addr pairs */, uint32_t n)
+{
+	oracle_mem m = { segs, numSegs };
+	uint64_t faults = 0;
+	for(uint32_t i = 0; i < n; i++) {
+		uint64_t h = patches[2 * i], addr = patches[2 * i + 1], table = root;
+		int fault = 0;
+		uint32_t idx;
+		if(level == 3) {
+			table = load64(&m, table + 8ull * (uint32_t)(h >> 22), &fault);
+			table = load64(&m, table + 8ull * ((uint32_t)(h >> 11) & 0x7ffu), &fault);
+			idx = (uint32_t)h & 0x7ffu;
+		}
+		else if(level == 2) {
+			table = load64(&m, table + 8ull * (uint32_t)(h >> 11), &fault);
+			idx = (uint32_t)h & 0x7ffu;
+		}
+		else
+			idx = (uint32_t)h;
+		uint8_t* p = (uint8_t*)xlate(&m, table + 8ull * idx, 8, &fault);
+		if(p) memcpy(p, &addr, 8);
+		faults += (uint64_t)fault;
+	}
+	return faults;
+}
+
+int oracle_max_threads(void)
+{
+#ifdef _OPENMP
+	return omp_get_max_threads();
+#else
+	return 1;
+#endif
+}

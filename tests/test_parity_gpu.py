@@ -1,0 +1,208 @@
+"""GPU parity tests proper: the CUDA path through the C ABI against the CPU oracle on identical seeded inputs.
+Bit-exact for everything: Tier R is integer; Tier X is compared after canonical sorting within each StateSet
+(emission order depends on atomic arrival), including the near-band instances, because oracle and kernel
+perform the same fp32 operations in the same order without FMA contraction."""
+import numpy as np
+import pytest
+
+import cadr_b200
+from cadr_b200 import synth
+from cadr_b200.frame import DeviceScene, canonicalise
+from oracle import binding as ob
+from helpers import assert_tier_x_equal, gpu_frame, oracle_tier_r, oracle_tier_x
+
+pytestmark = pytest.mark.gpu
+
+R_CASES = [
+    dict(seed=1), dict(seed=2, first_handle=1990), dict(seed=3, first_handle=3000, force_level=3),
+    dict(seed=4, first_handle=4_194_250, big_lists=2), dict(seed=5, n=1, num_lists=3),
+    dict(seed=6, n=257, with_drawable_data=False), dict(seed=7, n=4099, num_lists=900, num_geometries=40),
+]
+
+
+def _oracle_r(ds: DeviceScene):
+    sc = ds.scene
+    return oracle_tier_r(sc, arena_base=ds.arena, list_base=ds.drawable_list)
+
+
+@pytest.mark.parametrize("kw", R_CASES, ids=lambda k: f"seed{k['seed']}")
+def test_tier_r_random_scenes(ctx, kw):
+    sc = synth.random_scene(**kw)
+    ds, ind, ptr, _ = gpu_frame(ctx, sc)
+    try:
+        _, e_ind, e_ptr = _oracle_r(ds)
+        assert np.array_equal(ind, e_ind)
+        assert np.array_equal(ptr, e_ptr)
+    finally:
+        ds.close()
+
+
+@pytest.mark.parametrize("builder", [lambda: synth.config1(12), lambda: synth.config2(70_001),
+                                     lambda: synth.config3(300, 100, state_sets=7)], ids=["C1", "C2", "C3"])
+def test_tier_r_baseline_shapes(ctx, builder):
+    sc = builder()
+    ds, ind, ptr, _ = gpu_frame(ctx, sc)
+    try:
+        _, e_ind, e_ptr = _oracle_r(ds)
+        assert np.array_equal(ind, e_ind) and np.array_equal(ptr, e_ptr)
+    finally:
+        ds.close()
+
+
+def test_zero_drawables_is_a_no_op(ctx):
+    """Renderer.cpp:600-620: nothing is dispatched for an empty scene."""
+    before = ctx.launch_count
+    ctx.process_drawables(0, 1, 0, 0, 0, 0)
+    assert ctx.launch_count == before
+
+
+def test_api_misuse_is_a_logic_error(ctx):
+    a = ctx.arena_alloc(4096)
+    try:
+        with pytest.raises(cadr_b200.LogicError):
+            ctx.process_drawables(a, 4, a, a, a, 10)           # no such handle level
+        with pytest.raises(cadr_b200.LogicError):
+            ctx.process_drawables(a, 1, a, a, a, 1 << 30)      # Renderer.cpp:687 limit
+        with pytest.raises(cadr_b200.LogicError):
+            ctx.process_drawables(a, 1, a + 8, a, a, 10)       # misaligned list
+        with pytest.raises(cadr_b200.LogicError):
+            ctx.patch_handles(a, 1, [(5000, 1)])               # handle outside a level-1 table
+    finally:
+        ctx.arena_free(a)
+
+
+X_CASES = [
+    (dict(seed=11), 0), (dict(seed=12, big_lists=3), 40), (dict(seed=13, first_handle=4_194_250, big_lists=1), 200),
+    (dict(seed=14, n=2000, num_lists=400, max_count=40, state_sets=17), 120),
+    (dict(seed=15, n=700, num_lists=60, max_count=300, state_sets=3, big_lists=5), 300),
+    (dict(seed=16, n=1, num_lists=2), 0),
+]
+
+
+@pytest.mark.parametrize("kw,frame", X_CASES, ids=lambda v: f"seed{v['seed']}" if isinstance(v, dict) else f"f{v}")
+def test_tier_x_random_scenes(ctx, kw, frame):
+    sc = synth.random_scene(**kw)
+    planes, eye = synth.orbit_camera(frame, 250.0, far=500.0)
+    ds, ind, ptr, got = gpu_frame(ctx, sc, planes, eye)
+    try:
+        _, _, ref = oracle_tier_x(sc, planes, eye, arena_base=ds.arena, list_base=ds.drawable_list)
+        assert_tier_x_equal(got, ref)
+    finally:
+        ds.close()
+
+
+@pytest.mark.parametrize("builder,radius,far", [(lambda: synth.config2(200_003), 1500.0, 1500.0),
+                                                (lambda: synth.config3(600, 1000, state_sets=64), 1500.0, 3000.0),
+                                                (lambda: synth.config3(64, 2500, state_sets=5), 1500.0, 3000.0)],
+                         ids=["C2", "C3", "C3-multi-item"])
+def test_tier_x_baseline_shapes(ctx, builder, radius, far):
+    sc = builder()
+    ds = DeviceScene(ctx, sc)
+    try:
+        for frame in (0, 77):
+            planes, eye = synth.orbit_camera(frame, radius, far=far)
+            ds.record_drawable_processing()
+            ds.cull(planes, eye)
+            ctx.sync(ds.stream)
+            got = ds.read_tier_x()
+            _, _, ref = oracle_tier_x(sc, planes, eye, arena_base=ds.arena, list_base=ds.drawable_list)
+            assert_tier_x_equal(got, ref)
+            p = got["inst_count"].sum() / sc.total_instances
+            assert 0.02 < p < 0.9, f"survivor fraction {p}"
+    finally:
+        ds.close()
+
+
+def test_tier_x_all_visible_none_visible_and_idempotent(ctx):
+    sc = synth.random_scene(21, big_lists=2, n=900, num_lists=80)
+    big = 1e9
+    all_in = np.array([[1, 0, 0, big], [-1, 0, 0, big], [0, 1, 0, big], [0, -1, 0, big], [0, 0, 1, big], [0, 0, -1, big]], np.float32)
+    none = all_in.copy(); none[0, 3] = -big
+    eye = np.zeros(3, np.float32)
+    ds = DeviceScene(ctx, sc)
+    try:
+        ds.record_drawable_processing()
+        ds.cull(all_in, eye); ctx.sync(ds.stream)
+        a1 = ds.read_tier_x()
+        ds.cull(all_in, eye); ctx.sync(ds.stream)
+        a2 = ds.read_tier_x()
+        cnt = sc.ml_count[sc.drawable_ml].astype(np.int64)
+        nonempty = sc.cull[:, 3].view(np.float32) >= 0
+        assert a1["inst_count"].sum() == int(cnt[nonempty].sum())
+        assert_tier_x_equal(a1, a2)                        # same frame twice: same canonical result
+        ds.cull(none, eye); ctx.sync(ds.stream)
+        z = ds.read_tier_x()
+        assert z["inst_count"].sum() == 0 and z["cmd_count"].sum() == 0 and z["status"] == 0
+    finally:
+        ds.close()
+
+
+def test_tier_x_region_overflow_is_reported(ctx):
+    sc = synth.random_scene(22, n=500, num_lists=40)
+    sc.regions = sc.regions.copy()
+    sc.regions[:, 3] = np.minimum(sc.regions[:, 3], 3)     # instance regions far too small
+    big = 1e9
+    all_in = np.array([[1, 0, 0, big], [-1, 0, 0, big], [0, 1, 0, big], [0, -1, 0, big], [0, 0, 1, big], [0, 0, -1, big]], np.float32)
+    ds = DeviceScene(ctx, sc)
+    try:
+        ds.record_drawable_processing()
+        ds.cull(all_in, np.zeros(3, np.float32)); ctx.sync(ds.stream)
+        assert ds.read_counters()["status"] & 1
+    finally:
+        ds.close()
+
+
+def test_upload_scatter_and_patch(ctx):
+    rng = np.random.default_rng(9)
+    size = 3 << 20
+    arena = ctx.arena_alloc(size)
+    host = np.zeros(size, np.uint8)
+    staging = rng.integers(0, 256, 2 << 20, dtype=np.uint8)
+    try:
+        ctx.memset(arena, 0, size)
+        # ragged regions: 16-B aligned starts (allocator guarantee), arbitrary sizes, one > 256 KiB (own DMA),
+        # one misaligned pair (generic path), one empty
+        regs, dst, src = [], 64, 0
+        for b in [1, 15, 16, 17, 100, 4096, 33000, 70001, 300_000, 0, 5]:
+            regs.append((arena + dst, src, b))
+            dst = (dst + b + 15) & ~15
+            src = (src + b + 15) & ~15
+        regs.append((arena + dst + 3, src + 5, 1000))
+        regions = np.array(regs, np.uint64)
+        ctx.upload(regions, staging)
+        ctx.sync()
+        got = np.empty(size, np.uint8)
+        ctx.memcpy_d2h(got, arena); ctx.sync()
+        ob.upload(ob.Memory([(arena, host)]), regions, staging)
+        assert np.array_equal(got, host)
+        # device-resident staging: the scatter kernel alone
+        stage_dev = ctx.arena_alloc(staging.nbytes)
+        ctx.memcpy_h2d(stage_dev, staging[::-1].copy())
+        ctx.scatter_copy(regions, stage_dev)
+        ctx.memcpy_d2h(got, arena); ctx.sync()
+        host2 = host.copy()
+        ob.upload(ob.Memory([(arena, host2)]), regions, staging[::-1].copy())
+        assert np.array_equal(got, host2)
+        ctx.arena_free(stage_dev)
+    finally:
+        ctx.arena_free(arena)
+
+
+@pytest.mark.parametrize("kw", [dict(seed=31), dict(seed=32, first_handle=1990), dict(seed=33, first_handle=4_194_250)],
+                         ids=["L1", "L2", "L3"])
+def test_patch_handles_matches_oracle(ctx, kw):
+    sc = synth.random_scene(**kw)
+    ds = DeviceScene(ctx, sc)
+    try:
+        img = sc.image(ds.arena)
+        hs = np.unique(sc.drawables[:, 2])[:5]
+        patches = np.stack([hs, np.uint64(ds.arena) + sc.ml_off[::-1][:len(hs)]], axis=1).astype(np.uint64)
+        ctx.patch_handles(ds.root, sc.handle_level, [(int(h), int(a)) for h, a in patches])
+        ds.record_drawable_processing(); ctx.sync(ds.stream)
+        ind, ptr = ds.read_tier_r()
+        mem = ob.Memory([(ds.arena, img), (ds.drawable_list, np.ascontiguousarray(sc.drawables))])
+        ob.patch_handles(mem, ds.root, sc.handle_level, patches)
+        e_ind, e_ptr = ob.process_drawables(mem, ds.root, sc.handle_level, ds.drawable_list, sc.n)
+        assert np.array_equal(ind, e_ind) and np.array_equal(ptr, e_ptr)
+    finally:
+        ds.close()
