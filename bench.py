@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py — culled+emitted instances/s of CADR's per-frame drawable processing on B200.
+
+A "step" is one frame of the hot path over one synthetic scene: processDrawables (Tier R: handle resolve +
+indirect/pointer records) followed by culling + LOD selection + stream compaction into per-StateSet
+VkDrawIndexedIndirectCommand lists (Tier X), through the C ABI of libcadr_b200.so.
+
+  value     device-resident: drawable list, matrices, tables already in HBM; CUDA events on the launching
+            stream around exactly K steps; max over ranks.
+  e2e       the same frame through the host-buffer entry point (cadr_b200_record_drawable_processing: DMA of the
+            48 B/drawable list from pinned host memory every frame, as Renderer::recordDrawableProcessing does)
+            plus a device->host read of the per-StateSet counters every frame.
+  roofline  dominant kernel (cullLargeKernel for C3, cullSmallKernel for C2): algorithmic bytes per launch
+            ((64 + 4p) B per instance, SURVEY §8d / DESIGN.md) / mean launch duration from CUDA events
+            recorded around that kernel inside the library, against MEASURED_PEAKS.json:hbm_gbs.
+  cpu_baseline / --impl reference
+            the CPU restatement of the path (oracle/, OpenMP over all host cores) on a bounded sample of the same
+            workload.  The reference's own GPU path cannot run here (no Vulkan ICD) and it has no CPU path other
+            than running the GLSL on a CPU ICD, so the port is the baseline ("kind": "port").
+
+Workloads (BASELINE.json configs): c3 = 100k geometries x 1000-instance MatrixLists (100 M instances), 64
+StateSets, 3 LODs — the configuration north_star's target is quoted on; c2 = 10 M drawables x 1 matrix.
+Multi-GPU (torchrun): every rank culls its own c3-shaped shard (weak scaling, config 5 = 8 x 125 M), then the
+compacted command lists + per-StateSet counters are all-gathered over NCCL into one buffer on every rank.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from cadr_b200 import synth  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2"])
+    ap.add_argument("--drawables", type=int, default=0, help="override the drawable count (debug)")
+    ap.add_argument("--instances", type=int, default=1000, help="matrices per list for c3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="drawables in the CPU sample (0: auto)")
+    return ap.parse_args()
+
+
+def make_scene(args, rank: int, host_matrices: bool, drawables: int | None = None) -> synth.Scene:
+    if args.workload == "c3":
+        n = drawables or args.drawables or 100_000
+        return synth.config3(n, args.instances, state_sets=64, seed=0xC0FFEE03 + rank, host_matrices=host_matrices)
+    n = drawables or args.drawables or 10_000_000
+    return synth.config2(n, seed=0xC0FFEE02 + rank, host_matrices=host_matrices)
+
+
+def camera(args, frame: int):
+    far = 3000.0 if args.workload == "c3" else 1500.0
+    return synth.orbit_camera(frame, 1500.0, far=far)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# -----------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on a bounded sample
+# -----------------------------------------------------------------------------------------------------
+def cpu_sample_run(args, steps: int, warmup: int, sample_drawables: int | None = None):
+    """Time the oracle (Tier R + Tier X evaluation, OpenMP) on the first `sample` drawables of the workload.
+    -> (instances/s, description, threads, seconds per step)"""
+    from oracle import binding as ob
+    threads = ob.max_threads()
+    if sample_drawables is None:
+        sample_drawables = args.cpu_sample or (2000 if args.workload == "c3" else 2_000_000)
+    sc = make_scene(args, 0, host_matrices=True, drawables=sample_drawables)
+    base, lst = 0x7F1200000000, 0x7F2000000000
+    img = sc.image(base)
+    mem = ob.Memory([(base, img), (lst, np.ascontiguousarray(sc.drawables))])
+    times = []
+    inst = sc.total_instances
+    for k in range(warmup + steps):
+        planes, eye = camera(args, k)
+        t0 = time.perf_counter()
+        ind, ptr = ob.process_drawables(mem, base + sc.root_off, sc.handle_level, lst, sc.n, threads)
+        surv, visited = ob.cull_count(mem, 0, sc.n, ind, ptr, sc.cull, planes, eye, threads)
+        dt = time.perf_counter() - t0
+        assert visited == inst
+        if k >= warmup:
+            times.append(dt)
+    sec = statistics.median(times)
+    desc = (f"{sc.n} of the workload's drawables ({inst} instances): oracle processDrawables + per-instance "
+            f"cull/LOD evaluation, OpenMP {threads} threads, median of {steps} frames")
+    return inst / sec, desc, threads, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
+    value, desc, threads, sec = cpu_sample_run(args, steps, warmup)
+    total = 100_000_000 if args.workload == "c3" else 10_000_000
+    line = {
+        "impl": "reference", "metric": "culled+emitted instances/sec", "value": round(value / 1e6, 3), "unit": "M instances/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(sec * 1e3 * total / max(1, int(value * sec)), 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": round(value / 1e6, 3), "unit": "M instances/s", "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": round(value / 1e6, 3), "unit": "M instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference GLSL needs a Vulkan ICD (none on this image, SURVEY F7); this is the CPU restatement (oracle/) of the same path",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, n_gpus: int) -> dict:
+    if args.workload == "c3":
+        n = args.drawables or 100_000
+        return {"workload": f"BASELINE configs[2]: synthetic CAD assembly, {n} geometries x {args.instances}-instance MatrixLists "
+                            f"({n * args.instances / 1e6:.0f} M instances) per GPU, 64 StateSets, 3-level LOD, orbiting camera 1 deg/frame",
+                "per_gpu_instances": n * args.instances, "gpus": n_gpus,
+                "l2": "inputs (6.4 GB of matrices per GPU) are far larger than the 126 MB L2; no flush needed",
+                "multi_gpu": "each rank culls its own shard; command lists + counters all-gathered over NCCL" if n_gpus > 1 else "single GPU"}
+    n = args.drawables or 10_000_000
+    return {"workload": f"BASELINE configs[1]: {n} drawables x 1 matrix, single StateSet, orbiting camera", "per_gpu_instances": n,
+            "gpus": n_gpus, "l2": "inputs (1.3 GB matrix lists + 0.5 GB drawable list per GPU) are far larger than the 126 MB L2"}
+
+
+# -----------------------------------------------------------------------------------------------------
+# GPU arm
+# -----------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import cadr_b200
+    from cadr_b200.frame import DeviceScene
+    from cadr_b200.synth_torch import TorchArena, fill_matrix_lists
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; cadr_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    ctx = cadr_b200.Context(local)
+    stream_t = torch.cuda.Stream(device=dev)
+    stream = stream_t.cuda_stream
+    scene = make_scene(args, rank, host_matrices=False)
+    arena = TorchArena(dev)
+    with torch.cuda.stream(stream_t):
+        ds = DeviceScene(ctx, scene, alloc=arena.alloc, free=arena.free, upload=False, stream=stream)
+        ds.upload_static(with_matrices=False)
+        fill_matrix_lists(scene, arena.tensor(ds.arena))
+    torch.cuda.synchronize()
+    inst = scene.total_instances
+    cams = [camera(args, k) for k in range(360)]
+
+    # multi-GPU exchange buffers: every rank ends up with all ranks' command lists and counters
+    gathered = None
+    if world > 1:
+        parts = [arena.tensor(ds.cmd_out), arena.tensor(ds.ptr_out), arena.tensor(ds.tag_out), arena.tensor(ds.counters)]
+        gathered = [torch.empty(world * p.numel(), dtype=torch.uint8, device=dev) for p in parts]
+
+    def exchange():
+        for g, p in zip(gathered, parts):
+            dist.all_gather_into_tensor(g, p)
+
+    def step_device(k, with_exchange=True):
+        planes, eye = cams[k % 360]
+        ds.process_drawables()
+        ds.cull(planes, eye)
+        if world > 1 and with_exchange:
+            exchange()
+
+    counters_host = torch.empty(ds.counters_bytes, dtype=torch.uint8).pin_memory()
+    counters_dev = arena.tensor(ds.counters)
+
+    def step_e2e(k):
+        planes, eye = cams[k % 360]
+        ds.record_drawable_processing()           # pinned host list -> device (48 B/drawable), then the kernel
+        ds.cull(planes, eye)
+        if world > 1:
+            exchange()
+        counters_host.copy_(counters_dev, non_blocking=True)
+        stream_t.synchronize()                    # the host consumes the counts every frame
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream_t)
+        for k in range(steps):
+            fn(args.warmup + k)
+        e1.record(stream_t)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    with torch.cuda.stream(stream_t):
+        # warm-up (>= 3), including the first record_drawable_processing that makes the list resident
+        ds.record_drawable_processing()
+        for k in range(max(args.warmup, 3)):
+            step_device(k)
+        torch.cuda.synchronize()
+        status = ds.read_counters()["status"]
+        if status:
+            raise SystemExit(f"bench.py: cull_compact reported overflow status {status}")
+
+        sampler = ClockSampler(local) if rank == 0 else None
+        l0 = ctx.launch_count
+        ms_total = timed(step_device, args.steps)
+        launches = ctx.launch_count - l0
+        clocks = sampler.stop() if sampler else None
+
+        ms_cull_only = timed(lambda k: step_device(k, with_exchange=False), args.steps) if world > 1 else ms_total
+
+        for k in range(3):
+            step_e2e(k)
+        ms_e2e = timed(step_e2e, args.steps)
+
+        # per-kernel durations (CUDA events recorded by the library around each of its kernels)
+        ctx.set_profiling(True)
+        ktimes, surv = [], []
+        for k in range(min(args.steps, 20)):
+            step_device(args.warmup + k, with_exchange=False)
+            stream_t.synchronize()
+            ktimes.append(ctx.kernel_times())
+            surv.append(int(ds.read_counters()["inst_count"].sum()))
+        ctx.set_profiling(False)
+
+    kt = np.array(ktimes)
+    k_process, k_small, k_large = (float(kt[:, i].mean()) for i in range(3))
+    p = float(np.mean(surv)) / inst
+    if args.workload == "c3":
+        dom_name, dom_ms = "cullLargeKernel", k_large
+    else:
+        dom_name, dom_ms = "cullSmallKernel", k_small
+    alg_bytes = (64.0 + 4.0 * p) * inst
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    total_inst = inst * world
+    value = total_inst * args.steps / (ms_total * 1e-3)
+    e2e_value = total_inst * args.steps / (ms_e2e * 1e-3)
+
+    line = {
+        "metric": "culled+emitted instances/sec", "value": round(value / 1e6, 1), "unit": "M instances/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "survivor_fraction": round(p, 4),
+        "e2e": {"value": round(e2e_value / 1e6, 1), "unit": "M instances/s", "h2d_bytes_per_step": scene.n * 48 + 232,
+                "d2h_bytes_per_step": ds.counters_bytes, "ms_per_step": round(ms_e2e / args.steps, 4)},
+        "gpu_launches": int(launches),
+        "kernels_ms": {"processDrawablesKernel": round(k_process, 4), "cullSmallKernel": round(k_small, 4), "cullLargeKernel": round(k_large, 4)},
+        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": recorded_traffic(dom_name), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": int(alg_bytes), "launch_ms": round(dom_ms, 4)},
+        "clocks": clocks,
+    }
+    if world > 1:
+        line["cull_only"] = {"value": round(total_inst * args.steps / (ms_cull_only * 1e-3) / 1e6, 1), "unit": "M instances/s",
+                             "ms_per_step": round(ms_cull_only / args.steps, 4)}
+        line["exchange_bytes_per_rank"] = int(sum(p.numel() for p in parts))
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, desc, threads, _ = cpu_sample_run(args, 5, 1)
+        line["cpu_baseline"] = {"value": round(v / 1e6, 3), "unit": "M instances/s", "cores": threads, "kind": "port", "sample": desc}
+    if rank == 0:
+        print(json.dumps(line))
+    ds.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
