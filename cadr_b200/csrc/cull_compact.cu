@@ -7,32 +7,59 @@
 // Two kernels per frame, both HBM-bound (no tensor-core work: gather + compaction):
 //
 //   cullSmallKernel   one THREAD per drawable.  Lists of <= 32 matrices are evaluated by the drawable's own
-//                     thread (config C2: 10 M drawables x 1 matrix).  Longer lists are cut into work items
-//                     of <= 1024 instances and queued (one block-aggregated atomic per CTA).
-//   cullLargeKernel   persistent, one CTA per SM slot, pulls work items from the queue.  Each of the 8 warps
-//                     takes 128 consecutive matrices of the item, four batches of 32: lane l reads matrix l of
-//                     the batch as two 256-bit loads (full 32-B sectors), evaluates it, and the warp compacts
-//                     survivors per LOD with __ballot_sync + __popc.  Per item: ONE 64-bit atomicAdd on the
-//                     StateSet's packed {commands, instances} counter reserves both output ranges.
+//                     thread (config C2: 10 M drawables x 1 matrix).  Longer lists are cut into work items of
+//                     <= 1024 consecutive matrices; the thread writes one self-contained 128-byte descriptor
+//                     per item (matrix address, count, sphere, LOD table, resolved PrimitiveSets, pointers to
+//                     forward) into a queue reserved with ONE block-aggregated atomic per CTA.
+//   cullLargeKernel   persistent, one CTA per SM, warp-specialised:
+//                       producer warp   pulls item indices from the queue cursor and streams each item's
+//                                       descriptor + up to 64 KiB of matrices into a 3-stage shared-memory ring
+//                                       with TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx::bytes);
+//                       16 consumer warps wait on the stage's mbarrier, read "their" 64 matrices conflict-free
+//                                       from shared memory, evaluate them, compact survivors per LOD with
+//                                       __ballot_sync/__popc into a per-stage stash (rank reserved by one
+//                                       shared-memory atomic per warp and LOD) and release the stage.  The warp
+//                                       that finishes an item last reserves the item's output ranges with ONE
+//                                       64-bit global atomicAdd on the StateSet's packed {commands, instances}
+//                                       counter, writes the <= 3 commands and copies the stash out coalesced.
+//                     No CTA-wide barrier inside the loop: loads of items i+1, i+2 are in flight while item i is
+//                     evaluated, and warps never wait for each other.
+//   cullLargeLdgKernel  the first version of the same stage (direct 256-bit global loads, CTA barriers); kept
+//                     selectable (CADR_B200_CULL_VARIANT=0) for A/B measurements.
 //
-// No per-instance global atomics anywhere.  Emission order of commands inside a StateSet depends on atomic
-// arrival order, so comparisons canonicalise by (drawableIndex, lod); instance runs are written in ascending
-// instance order within each (drawable, lod, work item).
+// No per-instance global atomics anywhere.  Emission order of commands inside a StateSet and of instance
+// indices inside a run depends on arrival order, so comparisons canonicalise: merge by (drawableIndex, lod),
+// sort instance indices.
 //
 // Algorithmic bytes per instance: 64 R (mat4) + 4*p W (u32 index of a survivor) + per-drawable
 // overhead / N.
 
 #include "common.cuh"
+#include <cstdlib>
 
 namespace cadr {
 
 constexpr uint32_t SMALL_MAX  = 32;    // lists up to this many matrices are handled by one thread
 constexpr uint32_t CHUNK      = 1024;  // instances per work item of the large-list kernel
 constexpr int      CS_THREADS = 256;
-constexpr int      CL_THREADS = 256;
-constexpr int      CL_WARPS   = CL_THREADS / 32;
-constexpr uint32_t CL_PER_WARP = CHUNK / CL_WARPS;   // 128 instances per warp per item
-constexpr int      CL_BATCHES = CL_PER_WARP / 32;    // 4 batches of 32
+
+// Self-contained work item of the large-list kernel: 128 bytes, written by cullSmallKernel.
+struct __align__(16) WorkItem {
+	uint64_t matrices;        // device address of the item's first matrix
+	uint32_t count;           // 1..CHUNK matrices (0xffffffff in shared memory: end of work)
+	uint32_t firstInstance;   // index of the first matrix inside its MatrixList
+	uint32_t drawable;
+	uint32_t stateSet;
+	uint32_t lodCount;        // 1..3
+	uint32_t pad0;
+	float    sphere[4];
+	float    thr0, thr1;
+	uint32_t pad1[2];
+	uint32_t ps[3][2];        // {indexCount, firstIndex} of each LOD's PrimitiveSet
+	uint32_t pad2[2];
+	uint4    ptr0, ptr1;      // DrawablePointers to forward
+};
+static_assert(sizeof(WorkItem) == 128, "WorkItem must be 128 bytes");
 
 struct CullArgs {
 	uint64_t root;
@@ -47,7 +74,7 @@ struct CullArgs {
 	uint32_t* instOut;
 	cadr_cull_header* hdr;
 	unsigned long long* counts;
-	uint2*    chunkWs;
+	WorkItem* items;
 	uint32_t  chunkCapacity;
 	uint32_t  n;
 	float4 plane[6];
@@ -131,17 +158,6 @@ __device__ __forceinline__ uint64_t primitiveSetBase(const CullArgs& A, uint32_t
 	return lookupHandle<LEVEL>(A.root, h);
 }
 
-__device__ __forceinline__ void writeCommand(const CullArgs& A, uint32_t ci, uint64_t psAddr, uint32_t instanceCount,
-                                             uint32_t firstInstance, uint32_t d, uint32_t lod, uint4 p0, uint4 p1)
-{
-	uint32_t count = ldg_u32(psAddr), first = ldg_u32(psAddr + 4);
-	uint32_t* c = reinterpret_cast<uint32_t*>(A.cmdOut + 20ull * ci);
-	c[0] = count; c[1] = instanceCount; c[2] = first; c[3] = 0u; c[4] = firstInstance;
-	A.ptrOut[2ull * ci] = p0;
-	A.ptrOut[2ull * ci + 1] = p1;
-	A.tagOut[ci] = make_uint2(d, lod);
-}
-
 __device__ __forceinline__ uint32_t warpInclusiveScan(uint32_t v, int lane)
 {
 #pragma unroll
@@ -150,6 +166,18 @@ __device__ __forceinline__ uint32_t warpInclusiveScan(uint32_t v, int lane)
 		if(lane >= o) v += t;
 	}
 	return v;
+}
+
+// command + forwarded pointers + tag of one (drawable, lod[, item])
+__device__ __forceinline__ void writeCommandRecord(const CullArgs& A, uint32_t ci, uint32_t indexCount, uint32_t instanceCount,
+                                                   uint32_t firstIndex, uint32_t firstInstance, uint32_t d, uint32_t lod,
+                                                   uint4 p0, uint4 p1)
+{
+	uint32_t* c = reinterpret_cast<uint32_t*>(A.cmdOut + 20ull * ci);
+	c[0] = indexCount; c[1] = instanceCount; c[2] = firstIndex; c[3] = 0u; c[4] = firstInstance;
+	A.ptrOut[2ull * ci] = p0;
+	A.ptrOut[2ull * ci + 1] = p1;
+	A.tagOut[ci] = make_uint2(d, lod);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -172,23 +200,31 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 	uint32_t N = 0;
 	if(valid) N = ldg_stream_u4(A.indirect + d).y;  // IndirectData.instanceCount == ml.numMatrices
 
-	// ---- queue work items for long lists -----------------------------------------------------------
+	// ---- number of work items this drawable needs in the large-list queue --------------------------
 	uint32_t nChunks = (N > SMALL_MAX) ? (N + CHUNK - 1) / CHUNK : 0;
 	uint32_t chunkIncl = warpInclusiveScan(nChunks, lane);
 	if(lane == 31) sChunkTot[warp] = chunkIncl;
 
-	// ---- evaluate short lists ----------------------------------------------------------------------
-	const bool small = valid && N > 0 && N <= SMALL_MAX;
-	uint32_t mask0 = 0, mask1 = 0, mask2 = 0, nearCount = 0, stateSet = 0xffffffffu;
+	// ---- per-drawable records (needed by both paths) -------------------------------------------------
 	uint32_t psOff[3] = {0, 0, 0};
+	uint32_t stateSet = 0xffffffffu;
 	uint4 p0 = make_uint4(0, 0, 0, 0), p1 = p0;
-	if(small) {
+	LodInfo L;
+	L.sphere = make_float4(0.f, 0.f, 0.f, -1.f); L.lodCount = 1; L.thr0 = L.thr1 = 0.f;
+	if(valid && N > 0) {
 		uint4 ca = ldg_stream_u4(A.cullData + 3ull * d), cb = ldg_stream_u4(A.cullData + 3ull * d + 1),
 		      cc = ldg_stream_u4(A.cullData + 3ull * d + 2);
 		p0 = ldg_stream_u4(A.pointers + 2ull * d);
 		p1 = ldg_stream_u4(A.pointers + 2ull * d + 1);
-		LodInfo L = unpackLod(ca, cb, cc, psOff, stateSet);
-		const uint8_t* mats = reinterpret_cast<const uint8_t*>(uint64_t(p1.x) | (uint64_t(p1.y) << 32)) + CADR_MATRIX_LIST_HEADER_BYTES;
+		L = unpackLod(ca, cb, cc, psOff, stateSet);
+	}
+	const uint64_t matrixList = uint64_t(p1.x) | (uint64_t(p1.y) << 32);
+
+	// ---- evaluate short lists ------------------------------------------------------------------------
+	const bool small = valid && N > 0 && N <= SMALL_MAX;
+	uint32_t mask0 = 0, mask1 = 0, mask2 = 0, nearCount = 0;
+	if(small) {
+		const uint8_t* mats = reinterpret_cast<const uint8_t*>(matrixList) + CADR_MATRIX_LIST_HEADER_BYTES;
 		for(uint32_t j = 0; j < N; j++) {
 			Mat m = loadMat(mats + 64ull * j);
 			bool nb;
@@ -212,7 +248,7 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 	__syncthreads();
 	const uint32_t domSet = sDomSet;
 
-	// chunk queue: one atomic per CTA
+	// work-item queue: one atomic per CTA
 	if(tid == 0) {
 		uint32_t tot = 0;
 #pragma unroll
@@ -220,7 +256,7 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 		sChunkBase = tot ? atomicAdd(&A.hdr->chunkCount, tot) : 0u;
 	}
 
-	// dominant group: block-aggregated reservation
+	// dominant group: block-aggregated reservation of the output ranges
 	const bool inDom = has && stateSet == domSet;
 	uint32_t domIncl = warpInclusiveScan(inDom ? packed : 0u, lane);
 	if(lane == 31) sGroupTot[warp] = domIncl;
@@ -233,12 +269,11 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 		sDomBase = tot ? atomicAdd(A.counts + domSet, add) : 0ull;
 	}
 
-	// write queued work items (needs sChunkBase: published by the barrier above? no - thread 0 wrote it after
-	// the first barrier, so it is read after the next one)
 	uint32_t cmdOff = 0, instOff = 0;
 	bool reserved = false;
 
-	// stragglers: drawables of a different StateSet than the dominant one (CTA spans a range boundary)
+	// stragglers: drawables of a different StateSet than the dominant one (CTA spans a range boundary):
+	// warp-aggregated, one atomic per (warp, StateSet)
 	unsigned pend = __ballot_sync(0xffffffffu, has && !inDom);
 	while(pend) {
 		int leader = __ffs(pend) - 1;
@@ -259,15 +294,30 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 		}
 		pend &= ~grp;
 	}
-	__syncthreads();
+	__syncthreads();  // publishes sChunkBase and sDomBase
 
-	// queue entries {drawable, chunk}
+	// ---- write the work items of a long list ---------------------------------------------------------
 	if(nChunks) {
 		uint32_t base = sChunkBase + (chunkIncl - nChunks);
 		for(int w = 0; w < warp; w++) base += sChunkTot[w];
+		const uint64_t psBase = primitiveSetBase<LEVEL>(A, d);
+		uint32_t ps[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+#pragma unroll
+		for(int l = 0; l < 3; l++)
+			if(uint32_t(l) < L.lodCount) { ps[l][0] = ldg_u32(psBase + psOff[l]); ps[l][1] = ldg_u32(psBase + psOff[l] + 4); }
 		for(uint32_t c = 0; c < nChunks; c++) {
-			if(base + c < A.chunkCapacity) A.chunkWs[base + c] = make_uint2(d, c);
-			else { atomicOr(&A.hdr->status, CADR_CULL_STATUS_CHUNK_OVERFLOW); break; }
+			if(base + c >= A.chunkCapacity) { atomicOr(&A.hdr->status, CADR_CULL_STATUS_CHUNK_OVERFLOW); break; }
+			const uint32_t j0 = c * CHUNK;
+			const uint64_t mats = matrixList + CADR_MATRIX_LIST_HEADER_BYTES + 64ull * j0;
+			uint4* w = reinterpret_cast<uint4*>(A.items + (base + c));
+			w[0] = make_uint4(uint32_t(mats), uint32_t(mats >> 32), min(CHUNK, N - j0), j0);
+			w[1] = make_uint4(d, stateSet, L.lodCount, 0u);
+			w[2] = make_uint4(__float_as_uint(L.sphere.x), __float_as_uint(L.sphere.y), __float_as_uint(L.sphere.z), __float_as_uint(L.sphere.w));
+			w[3] = make_uint4(__float_as_uint(L.thr0), __float_as_uint(L.thr1), 0u, 0u);
+			w[4] = make_uint4(ps[0][0], ps[0][1], ps[1][0], ps[1][1]);
+			w[5] = make_uint4(ps[2][0], ps[2][1], 0u, 0u);
+			w[6] = p0;
+			w[7] = p1;
 		}
 	}
 
@@ -288,14 +338,13 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 			atomicOr(&A.hdr->status, CADR_CULL_STATUS_REGION_OVERFLOW);
 		}
 		else {
-			uint64_t psBase = primitiveSetBase<LEVEL>(A, d);
+			const uint64_t psBase = primitiveSetBase<LEVEL>(A, d);
 			uint32_t ci = reg.x + cmdOff, ii = reg.z + instOff;
-			uint32_t masks[3] = {mask0, mask1, mask2};
 #pragma unroll
 			for(int l = 0; l < 3; l++) {
-				uint32_t mk = masks[l];
+				uint32_t mk = (l == 0) ? mask0 : (l == 1) ? mask1 : mask2;
 				if(mk == 0) continue;
-				writeCommand(A, ci, psBase + psOff[l], __popc(mk), ii, d, l, p0, p1);
+				writeCommandRecord(A, ci, ldg_u32(psBase + psOff[l]), __popc(mk), ldg_u32(psBase + psOff[l] + 4), ii, d, l, p0, p1);
 				ci++;
 				while(mk) {
 					int j = __ffs(mk) - 1;
@@ -308,21 +357,253 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// long lists: persistent CTAs, one work item (<= 1024 consecutive matrices of one list) at a time
+// long lists, TMA pipeline: persistent CTAs, producer warp + 16 consumer warps, 3-stage smem ring
 // ---------------------------------------------------------------------------------------------------
-template<int LEVEL>
-__global__ void __launch_bounds__(CL_THREADS, 2)
+constexpr int TP_STAGES         = 3;
+constexpr int TP_CONSUMER_WARPS = 16;
+constexpr int TP_THREADS        = (TP_CONSUMER_WARPS + 1) * 32;     // 544
+constexpr int TP_PER_WARP       = CHUNK / TP_CONSUMER_WARPS;        // 64 instances per warp per item
+constexpr int TP_BATCHES        = TP_PER_WARP / 32;                 // 2
+
+struct __align__(128) TpStage {
+	uint8_t  mats[CHUNK * 64];       // 64 KiB, filled by TMA
+	WorkItem item;                   // 128 B, filled by TMA
+	uint16_t stash[3][CHUNK];        // survivors' local indices per LOD
+	uint32_t cnt[3];                 // survivors per LOD so far (smem atomics)
+	uint32_t done;                   // consumer warps finished with this item
+	uint32_t nearBand;
+	uint32_t pad[27];
+};
+static_assert(sizeof(TpStage) % 128 == 0, "stage alignment");
+constexpr size_t TP_SMEM_BYTES = TP_STAGES * sizeof(TpStage) + 2 * TP_STAGES * sizeof(uint64_t);
+
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarArrive(uint64_t* bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbarArriveExpectTx(uint64_t* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"MBAR_WAIT_%=:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+		"@p bra MBAR_DONE_%=;\n\t"
+		"bra MBAR_WAIT_%=;\n\t"
+		"MBAR_DONE_%=:\n\t}"
+		:: "r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tmaLoad(void* dstSmem, uint64_t srcGlobal, uint32_t bytes, uint64_t* bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(smemAddr(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+}
+
+// Read matrix `jj` of the stage.  A lane's matrix is 64 contiguous bytes, so lanes l and l+2 of a quarter-warp
+// would hit the same banks; each lane therefore reads its four 16-byte columns in a rotated order (column
+// (k + rot) & 3 in step k, rot = (lane >> 1) & 3), which makes every LDS.128 cover all 32 banks exactly once,
+// and un-rotates in registers with two select levels.
+__device__ __forceinline__ Mat loadMatSmem(const uint8_t* mats, uint32_t jj, int lane)
+{
+	const uint8_t* mp = mats + 64u * jj;
+	const uint32_t rot = (uint32_t(lane) >> 1) & 3u;
+	float4 q0 = *reinterpret_cast<const float4*>(mp + (((0u + rot) & 3u) << 4));
+	float4 q1 = *reinterpret_cast<const float4*>(mp + (((1u + rot) & 3u) << 4));
+	float4 q2 = *reinterpret_cast<const float4*>(mp + (((2u + rot) & 3u) << 4));
+	float4 q3 = *reinterpret_cast<const float4*>(mp + (((3u + rot) & 3u) << 4));
+	// q[k] = column (k + rot) & 3  =>  column c = q[(c - rot) & 3] = q[(c + back) & 3], back = (4 - rot) & 3
+	const uint32_t back = (4u - rot) & 3u;
+	const bool b2 = back & 2u, b1 = back & 1u;
+	auto sel = [](bool c, const float4& a, const float4& b) { return make_float4(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z, c ? a.w : b.w); };
+	float4 t0 = sel(b2, q2, q0), t1 = sel(b2, q3, q1), t2 = sel(b2, q0, q2), t3 = sel(b2, q1, q3);  // t[c] = q[(c + (back&2)) & 3]
+	Mat m;
+	m.c0 = sel(b1, t1, t0); m.c1 = sel(b1, t2, t1); m.c2 = sel(b1, t3, t2); m.c3 = sel(b1, t0, t3);
+	return m;
+}
+
+__global__ void __launch_bounds__(TP_THREADS, 1)
 cullLargeKernel(const __grid_constant__ CullArgs A)
 {
-	__shared__ uint32_t sItem[2];
-	__shared__ uint32_t sWarpCnt[CL_WARPS][4];   // [warp][lod], 4th = near-band count
-	__shared__ uint32_t sLodStart[3];            // absolute index into instOut of each LOD's run, or 0xffffffff
-	__shared__ uint32_t sCmdBase;                // absolute index into cmdOut of the item's first command
+	extern __shared__ __align__(128) uint8_t smem[];
+	TpStage* stages = reinterpret_cast<TpStage*>(smem);
+	uint64_t* full = reinterpret_cast<uint64_t*>(smem + TP_STAGES * sizeof(TpStage));
+	uint64_t* empty = full + TP_STAGES;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+	if(tid == 0) {
+#pragma unroll
+		for(int s = 0; s < TP_STAGES; s++) { mbarInit(&full[s], 1); mbarInit(&empty[s], TP_CONSUMER_WARPS); }
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
 
 	uint32_t total = A.hdr->chunkCount;
 	if(total > A.chunkCapacity) total = A.chunkCapacity;
 
+	if(warp == TP_CONSUMER_WARPS) {
+		// ===== producer: one elected lane =====
+		if(lane == 0) {
+			uint32_t next = atomicAdd(&A.hdr->chunkCursor, 1u);
+			for(uint32_t it = 0;; it++) {
+				const uint32_t s = it % TP_STAGES, ph = (it / TP_STAGES) & 1u;
+				const uint32_t item = next;
+				const bool end = item >= total;
+				uint4 head = make_uint4(0, 0, 0, 0);
+				if(!end) {
+					head = *reinterpret_cast<const uint4*>(A.items + item);   // {matrices lo, hi, count, firstInstance}
+					next = atomicAdd(&A.hdr->chunkCursor, 1u);                // prefetch the next item index
+				}
+				TpStage& st = stages[s];
+				mbarWait(&empty[s], ph ^ 1u);                                 // all consumers released the stage
+				st.cnt[0] = 0; st.cnt[1] = 0; st.cnt[2] = 0; st.done = 0; st.nearBand = 0;
+				if(end) {
+					st.item.count = 0xffffffffu;
+					mbarArrive(&full[s]);
+					break;
+				}
+				const uint32_t bytes = head.z * 64u;
+				mbarArriveExpectTx(&full[s], bytes + uint32_t(sizeof(WorkItem)));
+				tmaLoad(&st.item, reinterpret_cast<uint64_t>(A.items + item), uint32_t(sizeof(WorkItem)), &full[s]);
+				tmaLoad(st.mats, uint64_t(head.x) | (uint64_t(head.y) << 32), bytes, &full[s]);
+			}
+		}
+		return;
+	}
+
+	// ===== consumers =====
+	const uint32_t lt = (1u << lane) - 1u;
+	for(uint32_t it = 0;; it++) {
+		const uint32_t s = it % TP_STAGES, ph = (it / TP_STAGES) & 1u;
+		TpStage& st = stages[s];
+		mbarWait(&full[s], ph);
+		const uint32_t cnt = st.item.count;
+		if(cnt == 0xffffffffu) break;
+
+		LodInfo L;
+		L.sphere = make_float4(st.item.sphere[0], st.item.sphere[1], st.item.sphere[2], st.item.sphere[3]);
+		L.lodCount = st.item.lodCount; L.thr0 = st.item.thr0; L.thr1 = st.item.thr1;
+
+		int lod[TP_BATCHES];
+		uint32_t bal[TP_BATCHES][3];
+		uint32_t wc[3] = {0, 0, 0}, nearCnt = 0;
+		const uint32_t jw = warp * TP_PER_WARP + lane;
+#pragma unroll
+		for(int b = 0; b < TP_BATCHES; b++) {
+			const uint32_t jj = jw + b * 32;
+			bool nb = false;
+			lod[b] = -1;
+			if(jj < cnt) {
+				Mat m = loadMatSmem(st.mats, jj, lane);
+				lod[b] = evalInstance(m, L, A.plane, A.eye, nb);
+			}
+			bal[b][0] = __ballot_sync(0xffffffffu, lod[b] == 0);
+			bal[b][1] = __ballot_sync(0xffffffffu, lod[b] == 1);
+			bal[b][2] = __ballot_sync(0xffffffffu, lod[b] == 2);
+			nearCnt += __popc(__ballot_sync(0xffffffffu, nb));
+			wc[0] += __popc(bal[b][0]); wc[1] += __popc(bal[b][1]); wc[2] += __popc(bal[b][2]);
+		}
+		// rank of this warp's survivors inside the item's per-LOD stash: one smem atomic per (warp, LOD)
+		uint32_t rank = 0;
+		if(lane < 3) {
+			uint32_t mine = (lane == 0) ? wc[0] : (lane == 1) ? wc[1] : wc[2];
+			if(mine) rank = atomicAdd(&st.cnt[lane], mine);
+		}
+		else if(lane == 3 && nearCnt) atomicAdd(&st.nearBand, nearCnt);
+		uint32_t r0 = __shfl_sync(0xffffffffu, rank, 0), r1 = __shfl_sync(0xffffffffu, rank, 1), r2 = __shfl_sync(0xffffffffu, rank, 2);
+#pragma unroll
+		for(int b = 0; b < TP_BATCHES; b++) {
+			const uint32_t jj = jw + b * 32;
+			if(lod[b] == 0) st.stash[0][r0 + __popc(bal[b][0] & lt)] = uint16_t(jj);
+			if(lod[b] == 1) st.stash[1][r1 + __popc(bal[b][1] & lt)] = uint16_t(jj);
+			if(lod[b] == 2) st.stash[2][r2 + __popc(bal[b][2] & lt)] = uint16_t(jj);
+			r0 += __popc(bal[b][0]); r1 += __popc(bal[b][1]); r2 += __popc(bal[b][2]);
+		}
+		__syncwarp();
+		uint32_t arrived = 0;
+		if(lane == 0) {
+			__threadfence_block();                         // stash writes before the arrival count
+			arrived = atomicAdd(&st.done, 1u);
+		}
+		arrived = __shfl_sync(0xffffffffu, arrived, 0);
+		if(arrived == TP_CONSUMER_WARPS - 1) {
+			// ---- last warp of the item: reserve, emit commands, copy the stash out -------------------
+			__threadfence_block();
+			const uint32_t t0 = *reinterpret_cast<volatile uint32_t*>(&st.cnt[0]);
+			const uint32_t t1 = *reinterpret_cast<volatile uint32_t*>(&st.cnt[1]);
+			const uint32_t t2 = *reinterpret_cast<volatile uint32_t*>(&st.cnt[2]);
+			const uint32_t nInst = t0 + t1 + t2;
+			if(nInst) {
+				const uint32_t nCmd = (t0 ? 1u : 0u) + (t1 ? 1u : 0u) + (t2 ? 1u : 0u);
+				const uint32_t stateSet = st.item.stateSet;
+				unsigned long long base = 0;
+				uint4 reg = make_uint4(0, 0, 0, 0);
+				if(lane == 0) {
+					base = atomicAdd(A.counts + stateSet, (unsigned long long)nCmd | ((unsigned long long)nInst << 32));
+					reg = ldg_u4(reinterpret_cast<uint64_t>(A.regions + stateSet));
+					uint32_t nbTot = *reinterpret_cast<volatile uint32_t*>(&st.nearBand);
+					if(nbTot) atomicAdd(&A.hdr->nearBandCount, nbTot);
+				}
+				base = __shfl_sync(0xffffffffu, base, 0);
+				reg.x = __shfl_sync(0xffffffffu, reg.x, 0); reg.y = __shfl_sync(0xffffffffu, reg.y, 0);
+				reg.z = __shfl_sync(0xffffffffu, reg.z, 0); reg.w = __shfl_sync(0xffffffffu, reg.w, 0);
+				const uint32_t cmdOff = uint32_t(base), instOff = uint32_t(base >> 32);
+				if(cmdOff + nCmd > reg.y || instOff + nInst > reg.w) {
+					if(lane == 0) atomicOr(&A.hdr->status, CADR_CULL_STATUS_REGION_OVERFLOW);
+				}
+				else {
+					const uint32_t i0 = reg.z + instOff, i1 = i0 + t0, i2 = i1 + t1;
+					const uint32_t j0 = st.item.firstInstance, d = st.item.drawable;
+					if(lane < 3) {
+						const uint32_t tl = (lane == 0) ? t0 : (lane == 1) ? t1 : t2;
+						if(tl) {
+							uint32_t ci = reg.x + cmdOff + ((lane > 0 && t0) ? 1u : 0u) + ((lane > 1 && t1) ? 1u : 0u);
+							writeCommandRecord(A, ci, st.item.ps[lane][0], tl, st.item.ps[lane][1],
+							                   (lane == 0) ? i0 : (lane == 1) ? i1 : i2, d, uint32_t(lane), st.item.ptr0, st.item.ptr1);
+						}
+					}
+					for(uint32_t i = lane; i < t0; i += 32) A.instOut[i0 + i] = j0 + st.stash[0][i];
+					for(uint32_t i = lane; i < t1; i += 32) A.instOut[i1 + i] = j0 + st.stash[1][i];
+					for(uint32_t i = lane; i < t2; i += 32) A.instOut[i2 + i] = j0 + st.stash[2][i];
+				}
+			}
+			else if(lane == 0) {
+				uint32_t nbTot = *reinterpret_cast<volatile uint32_t*>(&st.nearBand);
+				if(nbTot) atomicAdd(&A.hdr->nearBandCount, nbTot);
+			}
+		}
+		__syncwarp();
+		if(lane == 0) mbarArrive(&empty[s]);   // this warp no longer touches the stage
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// long lists, first version: direct 256-bit global loads, CTA barriers (kept for A/B measurements)
+// ---------------------------------------------------------------------------------------------------
+constexpr int      CL_THREADS  = 256;
+constexpr int      CL_WARPS    = CL_THREADS / 32;
+constexpr uint32_t CL_PER_WARP = CHUNK / CL_WARPS;   // 128 instances per warp per item
+constexpr int      CL_BATCHES  = CL_PER_WARP / 32;   // 4 batches of 32
+
+__global__ void __launch_bounds__(CL_THREADS, 2)
+cullLargeLdgKernel(const __grid_constant__ CullArgs A)
+{
+	__shared__ uint32_t sItem[2];
+	__shared__ uint32_t sWarpCnt[CL_WARPS][4];   // [warp][lod], 4th = near-band count
+	__shared__ uint32_t sLodStart[3];            // absolute index into instOut of each LOD's run, or 0xffffffff
+	__shared__ uint32_t sCmdBase;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+	uint32_t total = A.hdr->chunkCount;
+	if(total > A.chunkCapacity) total = A.chunkCapacity;
 	if(tid == 0) sItem[0] = atomicAdd(&A.hdr->chunkCursor, 1u);
 	__syncthreads();
 
@@ -330,33 +611,23 @@ cullLargeKernel(const __grid_constant__ CullArgs A)
 		const uint32_t item = sItem[it & 1];
 		if(item >= total) break;
 		uint32_t nextItem = 0;
-		if(tid == 0) nextItem = atomicAdd(&A.hdr->chunkCursor, 1u);  // prefetch; latency hidden behind the loads below
+		if(tid == 0) nextItem = atomicAdd(&A.hdr->chunkCursor, 1u);
 
-		const uint2 wi = A.chunkWs[item];
-		const uint32_t d = wi.x, j0 = wi.y * CHUNK;
-		const uint32_t N = ldg_u4(reinterpret_cast<uint64_t>(A.indirect + d)).y;
-		const uint4 p0 = ldg_u4(reinterpret_cast<uint64_t>(A.pointers + 2ull * d));
-		const uint4 p1 = ldg_u4(reinterpret_cast<uint64_t>(A.pointers + 2ull * d + 1));
-		const uint8_t* mats = reinterpret_cast<const uint8_t*>(uint64_t(p1.x) | (uint64_t(p1.y) << 32)) + CADR_MATRIX_LIST_HEADER_BYTES;
-		const uint32_t cnt = min(CHUNK, N - j0);
+		const uint4* w = reinterpret_cast<const uint4*>(A.items + item);
+		const uint4 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+		const uint8_t* mats = reinterpret_cast<const uint8_t*>(uint64_t(w0.x) | (uint64_t(w0.y) << 32));
+		const uint32_t cnt = w0.z, j0 = w0.w, d = w1.x, stateSet = w1.y;
+		LodInfo L;
+		L.sphere = make_float4(__uint_as_float(w2.x), __uint_as_float(w2.y), __uint_as_float(w2.z), __uint_as_float(w2.w));
+		L.lodCount = w1.z; L.thr0 = __uint_as_float(w3.x); L.thr1 = __uint_as_float(w3.y);
 
-		// issue all matrix loads of this warp's four batches first (16 x 32 B per lane in flight)
 		Mat m[CL_BATCHES];
-		const uint32_t jw = warp * CL_PER_WARP + lane;  // offset inside the item
+		const uint32_t jw = warp * CL_PER_WARP + lane;
 #pragma unroll
 		for(int k = 0; k < CL_BATCHES; k++) {
 			uint32_t jj = jw + k * 32;
-			if(jj < cnt) m[k] = loadMat(mats + 64ull * (j0 + jj));
+			if(jj < cnt) m[k] = loadMat(mats + 64ull * jj);
 		}
-
-		uint32_t psOff[3], stateSet;
-		const uint4 ca = ldg_u4(reinterpret_cast<uint64_t>(A.cullData + 3ull * d));
-		const uint4 cb = ldg_u4(reinterpret_cast<uint64_t>(A.cullData + 3ull * d + 1));
-		const uint4 cc = ldg_u4(reinterpret_cast<uint64_t>(A.cullData + 3ull * d + 2));
-		const LodInfo L = unpackLod(ca, cb, cc, psOff, stateSet);
-		uint64_t psAddr = 0;
-		if(tid < 3) psAddr = primitiveSetBase<LEVEL>(A, d) + psOff[tid];
-
 		int lod[CL_BATCHES];
 		uint32_t bal[CL_BATCHES][3];
 		uint32_t wc0 = 0, wc1 = 0, wc2 = 0, nearCnt = 0;
@@ -376,11 +647,10 @@ cullLargeKernel(const __grid_constant__ CullArgs A)
 		if(tid == 0) sItem[(it + 1) & 1] = nextItem;
 		__syncthreads();
 
-		// one thread reserves both output ranges of the item with a single packed atomic
 		if(tid == 0) {
 			uint32_t t0 = 0, t1 = 0, t2 = 0, nb = 0;
 #pragma unroll
-			for(int w = 0; w < CL_WARPS; w++) { t0 += sWarpCnt[w][0]; t1 += sWarpCnt[w][1]; t2 += sWarpCnt[w][2]; nb += sWarpCnt[w][3]; }
+			for(int q = 0; q < CL_WARPS; q++) { t0 += sWarpCnt[q][0]; t1 += sWarpCnt[q][1]; t2 += sWarpCnt[q][2]; nb += sWarpCnt[q][3]; }
 			uint32_t nCmd = (t0 ? 1u : 0u) + (t1 ? 1u : 0u) + (t2 ? 1u : 0u), nInst = t0 + t1 + t2;
 			uint32_t s0 = 0xffffffffu, s1 = 0xffffffffu, s2 = 0xffffffffu;
 			if(nb) atomicAdd(&A.hdr->nearBandCount, nb);
@@ -392,7 +662,7 @@ cullLargeKernel(const __grid_constant__ CullArgs A)
 					atomicOr(&A.hdr->status, CADR_CULL_STATUS_REGION_OVERFLOW);
 				else {
 					s0 = reg.z + instOff; s1 = s0 + t0; s2 = s1 + t1;
-					sCmdBase = reg.x + cmdOff;  // command slot of LOD l = sCmdBase + (number of non-empty lower LODs)
+					sCmdBase = reg.x + cmdOff;
 				}
 			}
 			sLodStart[0] = s0; sLodStart[1] = s1; sLodStart[2] = s2;
@@ -400,20 +670,21 @@ cullLargeKernel(const __grid_constant__ CullArgs A)
 		__syncthreads();
 
 		if(sLodStart[0] != 0xffffffffu) {
-			// per-LOD totals again (cheap: 8 smem reads) for command emission by threads 0..2
-			if(tid < 3) {
-				uint32_t t[3] = {0, 0, 0};
+			uint32_t t0 = 0, t1 = 0, t2 = 0;
 #pragma unroll
-				for(int w = 0; w < CL_WARPS; w++) { t[0] += sWarpCnt[w][0]; t[1] += sWarpCnt[w][1]; t[2] += sWarpCnt[w][2]; }
-				if(t[tid]) {
-					uint32_t ci = sCmdBase;
-					for(int l = 0; l < tid; l++) ci += t[l] ? 1u : 0u;
-					writeCommand(A, ci, psAddr, t[tid], sLodStart[tid], d, uint32_t(tid), p0, p1);
+			for(int q = 0; q < CL_WARPS; q++) { t0 += sWarpCnt[q][0]; t1 += sWarpCnt[q][1]; t2 += sWarpCnt[q][2]; }
+			if(tid < 3) {
+				const uint32_t tl = (tid == 0) ? t0 : (tid == 1) ? t1 : t2;
+				if(tl) {
+					uint32_t ci = sCmdBase + ((tid > 0 && t0) ? 1u : 0u) + ((tid > 1 && t1) ? 1u : 0u);
+					const uint4 w4 = w[4], w5 = w[5];
+					const uint32_t ic = (tid == 0) ? w4.x : (tid == 1) ? w4.z : w5.x;
+					const uint32_t fi = (tid == 0) ? w4.y : (tid == 1) ? w4.w : w5.y;
+					writeCommandRecord(A, ci, ic, tl, fi, sLodStart[tid], d, uint32_t(tid), w[6], w[7]);
 				}
 			}
-			// instance indices: ascending j inside each LOD run
 			uint32_t pre0 = sLodStart[0], pre1 = sLodStart[1], pre2 = sLodStart[2];
-			for(int w = 0; w < warp; w++) { pre0 += sWarpCnt[w][0]; pre1 += sWarpCnt[w][1]; pre2 += sWarpCnt[w][2]; }
+			for(int q = 0; q < warp; q++) { pre0 += sWarpCnt[q][0]; pre1 += sWarpCnt[q][1]; pre2 += sWarpCnt[q][2]; }
 			const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
 			for(int k = 0; k < CL_BATCHES; k++) {
@@ -424,8 +695,14 @@ cullLargeKernel(const __grid_constant__ CullArgs A)
 				pre0 += __popc(bal[k][0]); pre1 += __popc(bal[k][1]); pre2 += __popc(bal[k][2]);
 			}
 		}
-		__syncthreads();  // smem (sWarpCnt, sLodStart, sCmdBase) is rewritten by the next iteration
+		__syncthreads();
 	}
+}
+
+static int cullVariant()
+{
+	const char* v = std::getenv("CADR_B200_CULL_VARIANT");
+	return v ? std::atoi(v) : 1;   // 1 = TMA pipeline (default), 0 = direct-load version
 }
 
 int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s)
@@ -442,9 +719,9 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s)
 	if(!p.handleTableRoot || !p.drawableList || !p.indirectData || !p.drawablePointers || !p.cullData ||
 	   !p.stateSetRegions || !p.cmdOut || !p.ptrOut || !p.tagOut || !p.instOut)
 		return setError(CADR_E_LOGIC, "cull_compact: null device address");
-	if((p.drawableList | p.indirectData | p.drawablePointers | p.cullData | p.stateSetRegions | p.ptrOut) & 15)
+	if((p.drawableList | p.indirectData | p.drawablePointers | p.cullData | p.stateSetRegions | p.ptrOut | p.chunkWorkspace) & 15)
 		return setError(CADR_E_LOGIC, "cull_compact: record buffers must be 16-byte aligned");
-	if((p.cmdOut & 3) || (p.tagOut & 7) || (p.instOut & 3) || (p.chunkWorkspace & 7))
+	if((p.cmdOut & 3) || (p.tagOut & 7) || (p.instOut & 3))
 		return setError(CADR_E_LOGIC, "cull_compact: output buffers misaligned");
 	if(p.numStateSets == 0)
 		return setError(CADR_E_LOGIC, "cull_compact: numStateSets must be > 0");
@@ -464,7 +741,7 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s)
 	A.instOut = reinterpret_cast<uint32_t*>(p.instOut);
 	A.hdr = reinterpret_cast<cadr_cull_header*>(p.counters);
 	A.counts = reinterpret_cast<unsigned long long*>(p.counters + sizeof(cadr_cull_header));
-	A.chunkWs = reinterpret_cast<uint2*>(p.chunkWorkspace);
+	A.items = reinterpret_cast<WorkItem*>(p.chunkWorkspace);
 	A.chunkCapacity = p.chunkCapacity;
 	A.n = p.numDrawables;
 	for(int k = 0; k < 6; k++) A.plane[k] = make_float4(p.planes[k][0], p.planes[k][1], p.planes[k][2], p.planes[k][3]);
@@ -482,14 +759,22 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s)
 	CADR_CUDA(cudaGetLastError());
 
 	if(p.chunkCapacity) {
-		// persistent grid: two CTAs per SM (launch bounds), never more CTAs than work items could exist
-		uint32_t gridL = uint32_t(ctx->smCount) * 2u;
-		if(gridL > p.chunkCapacity) gridL = p.chunkCapacity;
+		const int variant = cullVariant();
 		ctx->timeBegin(KS_CULL_LARGE, s);
-		switch(p.handleLevel) {
-		case 1: cullLargeKernel<1><<<gridL, CL_THREADS, 0, s>>>(A); break;
-		case 2: cullLargeKernel<2><<<gridL, CL_THREADS, 0, s>>>(A); break;
-		default: cullLargeKernel<3><<<gridL, CL_THREADS, 0, s>>>(A); break;
+		if(variant == 0) {
+			uint32_t gridL = uint32_t(ctx->smCount) * 2u;   // two CTAs per SM (launch bounds)
+			if(gridL > p.chunkCapacity) gridL = p.chunkCapacity;
+			cullLargeLdgKernel<<<gridL, CL_THREADS, 0, s>>>(A);
+		}
+		else {
+			static bool attrSet = false;
+			if(!attrSet) {
+				CADR_CUDA(cudaFuncSetAttribute(cullLargeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TP_SMEM_BYTES)));
+				attrSet = true;
+			}
+			uint32_t gridL = uint32_t(ctx->smCount);       // persistent: one CTA per SM (215 KB of shared memory each)
+			if(gridL > p.chunkCapacity) gridL = p.chunkCapacity;
+			cullLargeKernel<<<gridL, TP_THREADS, TP_SMEM_BYTES, s>>>(A);
 		}
 		ctx->timeEnd(KS_CULL_LARGE, s);
 		ctx->launches++;

@@ -50,7 +50,7 @@ class DeviceScene:
         self.counters_bytes = ctx.cull_counters_bytes(S)
         self.counters = self._new(self.counters_bytes)
         self.chunk_cap = scene.chunk_capacity
-        self.chunk_ws = self._new(max(self.chunk_cap, 1) * 8)
+        self.chunk_ws = self._new(max(self.chunk_cap, 1) * 128)   # CADR_CULL_WORK_ITEM_BYTES
         self.root = self.arena + scene.root_off
         # host staging for the drawable list (the reference keeps it in a mapped HOST_CACHED buffer,
         # Renderer.cpp:513-535) — pinned here so the per-frame copy is a true DMA

@@ -135,6 +135,9 @@ typedef struct cadr_cull_header {
 } cadr_cull_header;           /* 64 B */
 #define CADR_CULL_STATUS_REGION_OVERFLOW 1u
 #define CADR_CULL_STATUS_CHUNK_OVERFLOW  2u
+#define CADR_CULL_WORK_ITEM_BYTES        128u   /* one self-contained descriptor per <= 1024 matrices */
+#define CADR_CULL_SMALL_LIST_MAX         32u    /* lists up to this size are evaluated by one thread  */
+#define CADR_CULL_WORK_ITEM_INSTANCES    1024u
 
 typedef struct cadr_cull_params {
 	/* Tier R inputs, same meaning as the push constants (processDrawables.comp:68-74) */
@@ -159,8 +162,8 @@ typedef struct cadr_cull_params {
 	uint64_t instOut;            /* uint32_t instance indices                                       */
 	uint64_t counters;           /* cadr_cull_header + uint64_t[numStateSets]; zeroed by the call    */
 	/* scratch */
-	uint64_t chunkWorkspace;     /* 8 B per work item of the large-list kernel                      */
-	uint32_t chunkCapacity;      /* >= sum over drawables with > 32 matrices of ceil(n/1024)         */
+	uint64_t chunkWorkspace;     /* CADR_CULL_WORK_ITEM_BYTES per work item of the large-list kernel, 16-B aligned */
+	uint32_t chunkCapacity;      /* >= sum over drawables with > 32 matrices of ceil(numMatrices/1024) */
 	uint32_t reserved1;
 } cadr_cull_params;
 
