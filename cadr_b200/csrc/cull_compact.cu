@@ -98,9 +98,9 @@ __device__ __forceinline__ Mat loadMat(const uint8_t* p)
 
 struct LodInfo { float4 sphere; uint32_t lodCount; float thr0, thr1; };
 
-// Per-instance evaluation.  Operation order is normative (DESIGN.md "Tier X"); every product and sum is a
-// separately rounded fp32 operation (__fmul_rn/__fadd_rn are never contracted into FMA), sqrt is IEEE
-// round-to-nearest, so the result is bit-identical to the C oracle built with -ffp-contract=off.
+// Per-instance evaluation.  Operation order is normative (DESIGN.md "Tier X"): every multiply-add below is ONE
+// IEEE-754 fusedMultiplyAdd (__fmaf_rn == C fmaf), every other product/sum/sqrt a separately rounded fp32
+// operation, so the result is bit-identical to the C oracle (built with -ffp-contract=off, explicit fmaf).
 // Returns the LOD (0..2) of a visible instance or -1; `nearBand` reports a sphere within 1e-5 of a plane or
 // of an LOD threshold.
 __device__ __forceinline__ int evalInstance(const Mat& m, const LodInfo& L, const float4 (&plane)[6],
@@ -108,13 +108,13 @@ __device__ __forceinline__ int evalInstance(const Mat& m, const LodInfo& L, cons
 {
 	const float4 b = L.sphere;
 	// centre = mat3(M)*c + M[3].xyz                                   BoundingSphere.h:73
-	float cx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m.c0.x, b.x), __fmul_rn(m.c1.x, b.y)), __fmul_rn(m.c2.x, b.z)), m.c3.x);
-	float cy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m.c0.y, b.x), __fmul_rn(m.c1.y, b.y)), __fmul_rn(m.c2.y, b.z)), m.c3.y);
-	float cz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m.c0.z, b.x), __fmul_rn(m.c1.z, b.y)), __fmul_rn(m.c2.z, b.z)), m.c3.z);
+	float cx = __fmaf_rn(m.c2.x, b.z, __fmaf_rn(m.c1.x, b.y, __fmaf_rn(m.c0.x, b.x, m.c3.x)));
+	float cy = __fmaf_rn(m.c2.y, b.z, __fmaf_rn(m.c1.y, b.y, __fmaf_rn(m.c0.y, b.x, m.c3.y)));
+	float cz = __fmaf_rn(m.c2.z, b.z, __fmaf_rn(m.c1.z, b.y, __fmaf_rn(m.c0.z, b.x, m.c3.z)));
 	// radius = sqrt(max squared column length) * r                    BoundingSphere.h:76-85
-	float s0 = __fadd_rn(__fadd_rn(__fmul_rn(m.c0.x, m.c0.x), __fmul_rn(m.c0.y, m.c0.y)), __fmul_rn(m.c0.z, m.c0.z));
-	float s1 = __fadd_rn(__fadd_rn(__fmul_rn(m.c1.x, m.c1.x), __fmul_rn(m.c1.y, m.c1.y)), __fmul_rn(m.c1.z, m.c1.z));
-	float s2 = __fadd_rn(__fadd_rn(__fmul_rn(m.c2.x, m.c2.x), __fmul_rn(m.c2.y, m.c2.y)), __fmul_rn(m.c2.z, m.c2.z));
+	float s0 = __fmaf_rn(m.c0.z, m.c0.z, __fmaf_rn(m.c0.y, m.c0.y, __fmul_rn(m.c0.x, m.c0.x)));
+	float s1 = __fmaf_rn(m.c1.z, m.c1.z, __fmaf_rn(m.c1.y, m.c1.y, __fmul_rn(m.c1.x, m.c1.x)));
+	float s2 = __fmaf_rn(m.c2.z, m.c2.z, __fmaf_rn(m.c2.y, m.c2.y, __fmul_rn(m.c2.x, m.c2.x)));
 	float s01 = (s0 < s1) ? s1 : s0;        // std::max
 	float s = (s01 < s2) ? s2 : s01;
 	float r = __fmul_rn(__fsqrt_rn(s), b.w);
@@ -124,13 +124,12 @@ __device__ __forceinline__ int evalInstance(const Mat& m, const LodInfo& L, cons
 	bool nearP = false;
 #pragma unroll
 	for(int k = 0; k < 6; k++) {
-		float dot = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(plane[k].x, cx), __fmul_rn(plane[k].y, cy)),
-		                                __fmul_rn(plane[k].z, cz)), plane[k].w);
+		float dot = __fmaf_rn(plane[k].z, cz, __fmaf_rn(plane[k].y, cy, __fmaf_rn(plane[k].x, cx, plane[k].w)));
 		visible = visible && (dot >= -r);
 		nearP = nearP || (fabsf(__fadd_rn(dot, r)) < 1e-5f);
 	}
 	float dx = __fadd_rn(cx, -eye.x), dy = __fadd_rn(cy, -eye.y), dz = __fadd_rn(cz, -eye.z);
-	float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+	float dist = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
 	int lod = 0;
 	bool nearT = false;
 	if(L.lodCount > 1) { lod += (L.thr0 <= dist) ? 1 : 0; nearT = nearT || (fabsf(__fadd_rn(dist, -L.thr0)) < 1e-5f); }
@@ -376,6 +375,7 @@ struct __align__(128) TpStage {
 };
 static_assert(sizeof(TpStage) % 128 == 0, "stage alignment");
 constexpr size_t TP_SMEM_BYTES = TP_STAGES * sizeof(TpStage) + 2 * TP_STAGES * sizeof(uint64_t);
+static_assert(TP_SMEM_BYTES <= 227 * 1024, "shared memory budget of one CTA");
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count)
@@ -493,18 +493,24 @@ cullLargeKernel(const __grid_constant__ CullArgs A)
 		L.lodCount = st.item.lodCount; L.thr0 = st.item.thr0; L.thr1 = st.item.thr1;
 
 		int lod[TP_BATCHES];
+		bool nbv[TP_BATCHES];
 		uint32_t bal[TP_BATCHES][3];
 		uint32_t wc[3] = {0, 0, 0}, nearCnt = 0;
 		const uint32_t jw = warp * TP_PER_WARP + lane;
+		// branch-free evaluation of both batches (index clamped, result masked) so that the two independent
+		// instruction streams interleave; a tail item re-evaluates its last matrix in the idle lanes
 #pragma unroll
 		for(int b = 0; b < TP_BATCHES; b++) {
 			const uint32_t jj = jw + b * 32;
-			bool nb = false;
-			lod[b] = -1;
-			if(jj < cnt) {
-				Mat m = loadMatSmem(st.mats, jj, lane);
-				lod[b] = evalInstance(m, L, A.plane, A.eye, nb);
-			}
+			Mat m = loadMatSmem(st.mats, min(jj, cnt - 1u), lane);
+			bool nb;
+			int l = evalInstance(m, L, A.plane, A.eye, nb);
+			lod[b] = (jj < cnt) ? l : -1;
+			nbv[b] = nb && (jj < cnt);
+		}
+#pragma unroll
+		for(int b = 0; b < TP_BATCHES; b++) {
+			const bool nb = nbv[b];
 			bal[b][0] = __ballot_sync(0xffffffffu, lod[b] == 0);
 			bal[b][1] = __ballot_sync(0xffffffffu, lod[b] == 1);
 			bal[b][2] = __ballot_sync(0xffffffffu, lod[b] == 2);

@@ -20,8 +20,9 @@
  * Device memory is modelled as a list of segments {device base address, size, host mirror}; emitted
  * pointers are therefore numerically identical to what the GPU writes for the same arena contents.
  *
- * Build: gcc -O2 -ffp-contract=off -fopenmp -fPIC -shared   (FMA contraction MUST stay off: Tier X is
- * compared bit-for-bit with CUDA code that uses __fmul_rn/__fadd_rn).
+ * Build: gcc -O2 -ffp-contract=off -fopenmp -fPIC -shared   (implicit FMA contraction MUST stay off: Tier X is
+ * compared bit-for-bit with CUDA code whose every operation is an explicit __fmaf_rn/__fmul_rn/__fadd_rn; the
+ * fused operations of the specification are written as fmaf(), which is exact on any host).
  */
 #include <math.h>
 #include <stdint.h>
@@ -139,19 +140,21 @@ typedef struct oracle_cull_result {
 	uint32_t overflow;         /* a StateSet region was too small */
 } oracle_cull_result;
 
-/* per-instance evaluation; operation order is normative (DESIGN.md "Tier X") */
+/* per-instance evaluation; operation order is normative (DESIGN.md "Tier X"): every fmaf() is ONE IEEE-754
+ * fusedMultiplyAdd, everything else a separately rounded fp32 operation (-ffp-contract=off keeps the
+ * compiler from fusing or un-fusing anything). */
 static inline int eval_instance(const float* M /* 16 floats, column-major */, const float* bs /* xyz r */,
                                 uint32_t lodCount, float thr0, float thr1,
                                 const float planes[6][4], const float eye[3], int* nearBand)
 {
 	/* centre = mat3(M)*c + M[3].xyz                       BoundingSphere.h:73 */
-	float cx = ((M[0] * bs[0] + M[4] * bs[1]) + M[8]  * bs[2]) + M[12];
-	float cy = ((M[1] * bs[0] + M[5] * bs[1]) + M[9]  * bs[2]) + M[13];
-	float cz = ((M[2] * bs[0] + M[6] * bs[1]) + M[10] * bs[2]) + M[14];
+	float cx = fmaf(M[8],  bs[2], fmaf(M[4], bs[1], fmaf(M[0], bs[0], M[12])));
+	float cy = fmaf(M[9],  bs[2], fmaf(M[5], bs[1], fmaf(M[1], bs[0], M[13])));
+	float cz = fmaf(M[10], bs[2], fmaf(M[6], bs[1], fmaf(M[2], bs[0], M[14])));
 	/* radius = sqrt(max squared column length) * r        BoundingSphere.h:76-85 */
-	float s0 = (M[0] * M[0] + M[1] * M[1]) + M[2]  * M[2];
-	float s1 = (M[4] * M[4] + M[5] * M[5]) + M[6]  * M[6];
-	float s2 = (M[8] * M[8] + M[9] * M[9]) + M[10] * M[10];
+	float s0 = fmaf(M[2],  M[2],  fmaf(M[1], M[1], M[0] * M[0]));
+	float s1 = fmaf(M[6],  M[6],  fmaf(M[5], M[5], M[4] * M[4]));
+	float s2 = fmaf(M[10], M[10], fmaf(M[9], M[9], M[8] * M[8]));
 	float s01 = (s0 < s1) ? s1 : s0;       /* std::max */
 	float s = (s01 < s2) ? s2 : s01;
 	float r = sqrtf(s) * bs[3];
@@ -160,12 +163,12 @@ static inline int eval_instance(const float* M /* 16 floats, column-major */, co
 	int visible = nonEmpty;
 	int nearP = 0;
 	for(int k = 0; k < 6; k++) {
-		float dot = ((planes[k][0] * cx + planes[k][1] * cy) + planes[k][2] * cz) + planes[k][3];
+		float dot = fmaf(planes[k][2], cz, fmaf(planes[k][1], cy, fmaf(planes[k][0], cx, planes[k][3])));
 		visible = visible && (dot >= -r);
 		nearP = nearP || (fabsf(dot + r) < 1e-5f);
 	}
 	float dx = cx - eye[0], dy = cy - eye[1], dz = cz - eye[2];
-	float dist = sqrtf((dx * dx + dy * dy) + dz * dz);
+	float dist = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
 	int lod = 0, nearT = 0;
 	if(lodCount > 1) { lod += (thr0 <= dist) ? 1 : 0; nearT = nearT || (fabsf(dist - thr0) < 1e-5f); }
 	if(lodCount > 2) { lod += (thr1 <= dist) ? 1 : 0; nearT = nearT || (fabsf(dist - thr1) < 1e-5f); }

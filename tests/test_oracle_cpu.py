@@ -80,8 +80,15 @@ def test_oracle_reports_faults_instead_of_emulating_ub():
         ob.process_drawables(mem, FAKE_BASE + sc.root_off, sc.handle_level, FAKE_LIST, sc.n)
 
 
+def _fma(a, b, c):
+    """fusedMultiplyAdd in numpy: the float32 x float32 product is exact in float64; the sum is rounded to 53 bits
+    and then to 24 (a double rounding that can differ from a true fma only on exact float32 midpoints)."""
+    return (a.astype(np.float64) * np.float64(b) + np.asarray(c, dtype=np.float64)).astype(np.float32) if np.isscalar(b) or np.ndim(b) == 0 \
+        else (a.astype(np.float64) * b.astype(np.float64) + np.asarray(c, dtype=np.float64)).astype(np.float32)
+
+
 def numpy_lod(sc: synth.Scene, planes, eye):
-    """Independent float32 evaluation of the Tier X spec (vectorised numpy; numpy never contracts to FMA).
+    """Independent evaluation of the Tier X spec (vectorised numpy, fused multiply-adds emulated in float64).
     -> per-drawable list of int8 arrays: lod per instance or -1."""
     starts = np.concatenate([[0], np.cumsum(sc.ml_count.astype(np.int64))])
     f = np.float32
@@ -93,17 +100,17 @@ def numpy_lod(sc: synth.Scene, planes, eye):
         bs = cd[0:4].view(np.float32)
         lodc = min(max(int(cd[4]), 1), 3)
         thr = cd[8:10].view(np.float32)
-        c = [((M[:, 0 + a] * bs[0] + M[:, 4 + a] * bs[1]) + M[:, 8 + a] * bs[2]) + M[:, 12 + a] for a in range(3)]
-        s = [(M[:, 4 * q] * M[:, 4 * q] + M[:, 4 * q + 1] * M[:, 4 * q + 1]) + M[:, 4 * q + 2] * M[:, 4 * q + 2] for q in range(3)]
+        c = [_fma(M[:, 8 + a], bs[2], _fma(M[:, 4 + a], bs[1], _fma(M[:, 0 + a], bs[0], M[:, 12 + a]))) for a in range(3)]
+        s = [_fma(M[:, 4 * q + 2], M[:, 4 * q + 2], _fma(M[:, 4 * q + 1], M[:, 4 * q + 1], M[:, 4 * q] * M[:, 4 * q])) for q in range(3)]
         smax = np.maximum(np.maximum(s[0], s[1]), s[2])
         with np.errstate(invalid="ignore"):
             r = np.sqrt(smax) * bs[3]
             vis = np.full(M.shape[0], bs[3] >= 0)
             for p in planes:
-                dot = ((p[0] * c[0] + p[1] * c[1]) + p[2] * c[2]) + p[3]
+                dot = _fma(c[2], p[2], _fma(c[1], p[1], _fma(c[0], p[0], np.full(M.shape[0], p[3], np.float32))))
                 vis &= dot >= -r
         dx, dy, dz = c[0] - f(eye[0]), c[1] - f(eye[1]), c[2] - f(eye[2])
-        dist = np.sqrt((dx * dx + dy * dy) + dz * dz)
+        dist = np.sqrt(_fma(dz, dz, _fma(dy, dy, dx * dx)))
         lod = np.zeros(M.shape[0], np.int8)
         if lodc > 1:
             lod += thr[0] <= dist
