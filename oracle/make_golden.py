@@ -1,0 +1,149 @@
+#!/usr/bin/env python
+"""Generate tests/golden/ from the REFERENCE ITSELF (run in the build container only; needs /root/reference).
+
+  process_drawables_*.npz   inputs (arena image, drawable list) and the outputs obtained by executing the
+                            reference's own compute shader: processDrawables.comp compiled unmodified by the
+                            reference's vendored glslangValidator (oracle/Makefile) and interpreted by
+                            oracle/spirv_run.py, dispatched as Renderer::recordDrawableProcessing does
+                            (Renderer.cpp:684-692, incl. the DispatchBase tail above 32768 drawables).
+  allocator_kat.json.gz     command streams and the placements chosen by the reference's own
+                            CircularAllocationMemory.h (oracle/ref_alloc_probe.cpp): the scenarios of
+                            tests/DataAllocationTest.cpp:62-323 plus random alloc/free sequences.
+
+The committed vectors pin oracle/cadr_oracle.c (Tier R) and cadr_b200/host's allocator; the tests never need
+/root/reference.
+"""
+from __future__ import annotations
+
+import gzip
+import json
+import os
+import struct
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from cadr_b200 import synth  # noqa: E402
+from oracle import spirv_run as sr  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+REF = os.path.join(ROOT, "oracle", "_ref")
+BASE, LIST, IND, PTR = 0x7F1200000000, 0x7F2000000000, 0x7F3000000000, 0x7F4000000000
+
+SCENES = {
+    "L1_ragged": dict(seed=101, n=300),
+    "L2_transition_2048": dict(seed=102, n=300, first_handle=1990),
+    "L3_forced": dict(seed=103, n=200, first_handle=3000, force_level=3),
+    "L3_transition_4194304": dict(seed=104, n=300, first_handle=4_194_250, big_lists=2),
+    "dispatch_base_tail": dict(seed=105, n=32768 + 77, num_geometries=9, num_lists=64, max_count=5, state_sets=3),
+}
+
+
+def reloc_words(sc: synth.Scene) -> np.ndarray:
+    w = [(node_off // 8 + idx.astype(np.int64))[target != 0] for node_off, idx, target in sc.tables]
+    return np.unique(np.concatenate(w)).astype(np.uint32)
+
+
+def golden_process_drawables():
+    for name, kw in SCENES.items():
+        sc = synth.random_scene(**kw)
+        img = sc.image(BASE)
+        dl = np.ascontiguousarray(sc.drawables).copy()
+        ind = np.zeros((sc.n, 4), np.uint32)
+        ptr = np.zeros((sc.n, 4), np.uint64)
+        mem = sr.Memory([(BASE, img), (LIST, dl), (IND, ind), (PTR, ptr)])
+        mod = sr.load_module(os.path.join(REF, f"processDrawables_L{sc.handle_level}.spv"))
+        push = struct.pack("<4Q", BASE + sc.root_off, LIST, IND, PTR)   # Renderer.cpp:677-682
+        sr.dispatch(mod, mem, push, sc.n)
+        out = os.path.join(GOLD, f"process_drawables_{name}.npz")
+        np.savez_compressed(out, level=sc.handle_level, root_off=sc.root_off, base=BASE, image=img,
+                            reloc=reloc_words(sc), drawables=dl, indirect=ind, pointers=ptr,
+                            generator=json.dumps(dict(scene="cadr_b200.synth.random_scene", kwargs=kw)))
+        print(f"{out}: {sc.n} drawables, level {sc.handle_level}, {os.path.getsize(out) / 1024:.0f} KiB")
+
+
+def probe(buffer_bytes: int, cmds: list[tuple]) -> list[list[int]]:
+    text = f"{buffer_bytes}\n" + "\n".join(" ".join(str(x) for x in c) for c in cmds) + "\n"
+    r = subprocess.run([os.path.join(REF, "alloc_probe")], input=text, capture_output=True, text=True, check=True)
+    out = []
+    for line in r.stdout.strip().splitlines():
+        f = line.split()
+        out.append([int(x) for x in f[1:]])
+    assert len(out) == len(cmds)
+    return out
+
+
+def golden_allocator():
+    cases = []
+
+    def add(name, buffer_bytes, cmds):
+        cases.append(dict(name=name, buffer=buffer_bytes, cmds=[list(c) for c in cmds], expect=probe(buffer_bytes, cmds)))
+
+    # DataAllocationTest.cpp:87-128: two allocations of size s, both release orders
+    for s in list(range(1, 260)):
+        add(f"two_of_{s}_fifo", 65536, [("a", 1, s), ("a", 2, s), ("f", 1), ("f", 2)])
+        add(f"two_of_{s}_lifo", 65536, [("a", 1, s), ("a", 2, s), ("f", 2), ("f", 1)])
+    # DataAllocationTest.cpp:196-323: n allocations of size s within 64 KiB, six release orders + block-2 wrap
+    rng = np.random.default_rng(7)
+    for s in (1, 16, 17, 48, 64, 65, 100, 128, 129, 259):
+        off = 16 if s <= 16 else 32 if s <= 32 else 48 if s <= 48 else 64 if s <= 64 else 128 if s <= 128 else (s + 63) & ~63
+        for n in (1, 2, 3, 199, 200, 201, 202, 401, 1029):
+            if off * n >= 65536:
+                continue
+            alloc = [("a", i, s) for i in range(n)]
+            orders = {
+                "fifo": list(range(n)), "lifo": list(range(n))[::-1],
+                "even_odd": list(range(0, n, 2)) + list(range(1, n, 2)),
+                "odd_even": list(range(1, n, 2)) + list(range(0, n, 2)),
+                "rev_a": list(range(n - 2, -1, -2)) + list(range(n - 1, -1, -2)),
+                "rev_b": list(range(n - 1, -1, -2)) + list(range(n - 2, -1, -2)),
+            }
+            for oname, order in orders.items():
+                add(f"grid_{s}x{n}_{oname}", 65536, alloc + [("f", i) for i in order])
+            # block-2 scenario (:283-321): a big block pushes the first small one to the buffer end, then wraps
+            wrap = [("a", 10_000, 65536 - off), ("a", 0, s), ("f", 10_000)] + [("a", i, s) for i in range(1, n)]
+            add(f"wrap_{s}x{n}_fifo", 65536, wrap + [("f", i) for i in range(n)])
+            add(f"wrap_{s}x{n}_lifo", 65536, wrap + [("f", i) for i in range(n - 1, -1, -1)])
+    # random churn: mixed sizes, interleaved frees, buffers that fill up and wrap
+    for k in range(40):
+        buf = int(rng.choice([4096, 65536, 1 << 20]))
+        live, cmds, nid = [], [], 0
+        for _ in range(int(rng.integers(50, 600))):
+            if live and rng.random() < 0.45:
+                i = live.pop(int(rng.integers(0, len(live))) if rng.random() < 0.5 else 0)
+                cmds.append(("f", i))
+            else:
+                sz = int(rng.choice([1, 8, 16, 40, 64, 100, 128, 1000, 4000, 16384, 60000])) if rng.random() < 0.7 else int(rng.integers(1, buf // 8))
+                cmds.append(("a", nid, sz))
+                live.append(nid)
+                nid += 1
+        # frees of allocations that failed (-1) are not issued: filter with a dry run
+        res = probe(buf, [c for c in cmds if c[0] == "a"])
+        failed = {c[1] for c, r in zip([c for c in cmds if c[0] == "a"], res) if r[1] == -1}
+        # a failed alloc in the dry run may succeed in the real interleaving; resolve by simulation
+        cmds2, dead = [], set()
+        for c in cmds:
+            if c[0] == "a":
+                cmds2.append(c)
+                r = probe(buf, cmds2)[-1]
+                if r[1] == -1:
+                    dead.add(c[1])
+            elif c[1] not in dead:
+                cmds2.append(c)
+        add(f"random_{k}", buf, cmds2)
+    out = os.path.join(GOLD, "allocator_kat.json.gz")
+    with gzip.open(out, "wt", compresslevel=9) as f:
+        json.dump(dict(source="CadR::CircularAllocationMemory via oracle/ref_alloc_probe.cpp", base=0x10000000, cases=cases), f,
+                  separators=(",", ":"))
+    print(f"{out}: {len(cases)} cases, {os.path.getsize(out) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    if not os.path.isdir(REF):
+        raise SystemExit("oracle/_ref missing: run `make -C oracle ref` in the build container first")
+    golden_process_drawables()
+    golden_allocator()
