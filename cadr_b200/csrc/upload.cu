@@ -137,8 +137,6 @@ int launchUpload(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n, con
 		if(r.bytes == 0) continue;
 		if(r.dstAddr == 0)
 			return setError(CADR_E_LOGIC, "upload: region %u has a null destination", i);
-		if(stagingBase == nullptr)
-			return setError(CADR_E_LOGIC, "upload: null staging block");
 		if(r.bytes >= UPLOAD_DMA_THRESHOLD) {
 			CADR_CUDA(cudaMemcpyAsync(reinterpret_cast<void*>(r.dstAddr), base + r.srcOffset, r.bytes, cudaMemcpyHostToDevice, s));
 		}

@@ -1,0 +1,49 @@
+"""GPU: the C++ facade end to end — CadR::Renderer frames on a real B200 against the oracle.
+
+facade_scene_test drives a dynamic scene (uploads through DataStorage/StagingManager, handle-table growth over
+both level transitions, realloc-on-write, swap-remove, a StateSet with two parents) through
+beginFrame .. executeCopyOperations .. recordDrawableProcessing .. recordDrawableCulling .. submit, and dumps
+what the GPU produced.  The oracle runs on the device image reconstructed from the copy regions the facade issued."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from facade_dump import parse
+from helpers import assert_tier_x_equal
+from test_host_cpu import check_frame_against_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "cadr_b200", "host", "bin")
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_data_allocation_scenarios_on_device():
+    r = subprocess.run([os.path.join(BIN, "data_allocation_test"), "0", "420"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+@pytest.fixture(scope="module")
+def gpu_frames(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("facade") / "scene.bin")
+    r = subprocess.run([os.path.join(BIN, "facade_scene_test"), "0", out, "5"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    frames = parse(out)
+    os.remove(out)
+    return frames
+
+
+def test_facade_frames_on_gpu_match_oracle(gpu_frames):
+    assert [f["level"] for f in gpu_frames] == [1, 2, 2, 3, 3]
+    for f in gpu_frames:
+        assert f["has_device"]
+        mem, lst, ind, ptr = check_frame_against_oracle(f)
+        # Tier R: what the GPU wrote into the indirect / pointers buffers
+        assert np.array_equal(f["gpu_indirect"], ind)
+        assert np.array_equal(f["gpu_pointers"], ptr)
+        # Tier X: compacted command lists of the same frame
+        ref = ob.cull_compact(mem, f["root"], f["level"], lst, f["n"], ind, ptr, f["cull"], f["planes"], f["eye"], f["regions"])
+        assert_tier_x_equal(f["gpu_cull"], ref)
+        assert ref["num_instances"] > 0
