@@ -1,0 +1,84 @@
+"""Multi-GPU sharding of the drawable-processing path: one process per GPU.
+
+  partition()   cut the flattened drawable list into `world` contiguous slices balanced by INSTANCE count, at drawable
+                boundaries only; StateSet ranges are contiguous in flatten order (StateSet.cpp:233-264), so
+                concatenating per-rank outputs in rank order keeps every StateSet's commands contiguous per rank.
+  Exchange      the one real exchange step: all-gather of every rank's compacted command list (commands, forwarded
+                pointers, tags) and per-range counters into one buffer on every rank, plus a directory
+                {rank, range} -> (command offset, count) a renderer walks.  Instance-index lists stay on the owning GPU
+                (gathering 4 B per survivor costs more NVLink time than the cull itself at p ~ 0.5).
+
+torch.distributed is plumbing here: NCCL over NVLink on GPUs, gloo on CPU tensors in the tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def partition(instance_counts: np.ndarray, world: int) -> list[tuple[int, int]]:
+    """-> [(first, count)] per rank; slices are contiguous, cover [0, n), and differ by less than one drawable's
+    instances from the ideal share (empty lists weigh one so that drawable-only work is balanced too)."""
+    w = np.maximum(np.asarray(instance_counts, dtype=np.int64), 1)
+    n = len(w)
+    cum = np.concatenate([[0], np.cumsum(w)])
+    total = int(cum[-1])
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r / world
+        k = int(np.searchsorted(cum, target, side="left"))
+        k = min(max(k, cuts[-1]), n)
+        # pick the boundary closer to the target
+        if k > cuts[-1] and k <= n and abs(cum[k - 1] - target) <= abs(cum[min(k, n)] - target):
+            k -= 1
+        cuts.append(max(k, cuts[-1]))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1] - cuts[r]) for r in range(world)]
+
+
+class Exchange:
+    """All-gather of per-rank Tier X outputs.  Buffers are padded to the largest rank's capacity so that one
+    all_gather_into_tensor per array suffices (NVSwitch: every peer at full bandwidth; the payload is small)."""
+
+    def __init__(self, cmd_capacity: int, num_ranges: int, device: torch.device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        caps = torch.tensor([cmd_capacity, num_ranges], dtype=torch.int64, device=device)
+        allcaps = torch.empty(self.world * 2, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(allcaps, caps, group=group)
+        allcaps = allcaps.view(self.world, 2).cpu()
+        self.cmd_cap = int(allcaps[:, 0].max())
+        self.num_ranges = int(allcaps[:, 1].max())
+        self.sizes = dict(cmd=self.cmd_cap * 20, ptr=self.cmd_cap * 32, tag=self.cmd_cap * 8, counters=64 + 8 * self.num_ranges)
+        self.gathered = {k: torch.empty(self.world * v, dtype=torch.uint8, device=device) for k, v in self.sizes.items()}
+        self.bytes_per_rank = sum(self.sizes.values())
+
+    def run(self, cmd: torch.Tensor, ptr: torch.Tensor, tag: torch.Tensor, counters: torch.Tensor) -> None:
+        """Inputs are this rank's uint8 views (at least `sizes[...]` bytes each, or shorter: then they are padded)."""
+        for k, t in (("cmd", cmd), ("ptr", ptr), ("tag", tag), ("counters", counters)):
+            n = self.sizes[k]
+            if t.numel() < n:
+                t = torch.cat([t, torch.zeros(n - t.numel(), dtype=torch.uint8, device=t.device)])
+            dist.all_gather_into_tensor(self.gathered[k], t[:n].contiguous(), group=self.group)
+
+    def directory(self, regions_per_rank: list[np.ndarray]) -> list[dict]:
+        """Host view after a sync: one entry per (rank, range) with commands: where they start in the gathered command
+        buffer and how many there are."""
+        cnt = self.gathered["counters"].view(self.world, -1)[:, 64:].contiguous().view(torch.int64).cpu().numpy()
+        out = []
+        for r in range(self.world):
+            reg = regions_per_rank[r]
+            for s in range(reg.shape[0]):
+                c = int(cnt[r, s] & 0xFFFFFFFF)
+                if c:
+                    out.append(dict(rank=r, range=s, first_command=r * self.cmd_cap + int(reg[s, 0]), count=c,
+                                    instances=int(cnt[r, s] >> 32)))
+        return out
+
+    def commands(self) -> dict:
+        """numpy views of the gathered arrays: cmd [world*cap,5] u32, ptr [.,4] u64, tag [.,2] u32."""
+        g = {k: v.cpu().numpy() for k, v in self.gathered.items()}
+        return dict(cmd=g["cmd"].view(np.uint32).reshape(-1, 5), ptr=g["ptr"].view(np.uint64).reshape(-1, 4),
+                    tag=g["tag"].view(np.uint32).reshape(-1, 2))
