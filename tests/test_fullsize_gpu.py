@@ -1,0 +1,157 @@
+"""GPU: BASELINE.json's full sizes (C3 = 100 k x 1000 = 100 M instances, C2 = 10 M x 1), checked through
+size-independent properties — conservation (everything / nothing visible), index checksums, idempotence — and
+against the oracle on a random sample of drawables whose matrix lists are copied back from the device."""
+import numpy as np
+import pytest
+import torch
+
+from cadr_b200 import synth
+from cadr_b200.frame import DeviceScene
+from cadr_b200.synth_torch import TorchArena, fill_matrix_lists
+from oracle import binding as ob
+
+pytestmark = pytest.mark.gpu
+
+BIG = 1e9
+ALL_IN = np.array([[1, 0, 0, BIG], [-1, 0, 0, BIG], [0, 1, 0, BIG], [0, -1, 0, BIG], [0, 0, 1, BIG], [0, 0, -1, BIG]], np.float32)
+NONE = ALL_IN.copy(); NONE[0, 3] = -BIG
+
+
+def build(ctx, scene):
+    dev = torch.device("cuda", 0)
+    arena = TorchArena(dev)
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        ds = DeviceScene(ctx, scene, alloc=arena.alloc, free=arena.free, upload=False, stream=stream.cuda_stream)
+        ds.upload_static(with_matrices=False)
+        fill_matrix_lists(scene, arena.tensor(ds.arena))
+    torch.cuda.synchronize()
+    return ds, arena, stream
+
+
+def gpu_summary(ds, arena, scene):
+    """Order-independent digest of a Tier X result, computed on the device."""
+    c = ds.read_counters()
+    ncmd = ds.cmd_cap
+    cmd = arena.tensor(ds.cmd_out).view(torch.int32)[:ncmd * 5].view(ncmd, 5)
+    tag = arena.tensor(ds.tag_out).view(torch.int32)[:ncmd * 2].view(ncmd, 2)
+    inst = arena.tensor(ds.inst_out).view(torch.int32)
+    used = torch.zeros(ncmd, dtype=torch.bool, device=cmd.device)
+    iused = torch.zeros(ds.inst_cap, dtype=torch.bool, device=cmd.device)
+    for s in range(scene.num_state_sets):
+        used[int(scene.regions[s, 0]):int(scene.regions[s, 0]) + int(c["cmd_count"][s])] = True
+        iused[int(scene.regions[s, 2]):int(scene.regions[s, 2]) + int(c["inst_count"][s])] = True
+    k = cmd[used, 1].to(torch.int64)
+    key = tag[used, 0].to(torch.int64) * 3 + tag[used, 1].to(torch.int64)
+    ii = inst[:ds.inst_cap][iused].to(torch.int64)
+    return dict(status=c["status"], cmd_count=c["cmd_count"].copy(), inst_count=c["inst_count"].copy(),
+                sum_k=int(k.sum()), key_digest=int((key * k).sum()), idx_sum=int(ii.sum()), idx_sq=int((ii * ii).sum()),
+                used=used, cmd=cmd, tag=tag, inst=inst)
+
+
+def sample_check(ctx, ds, arena, scene, planes, eye, summary, sample):
+    """Oracle on `sample` drawables (their lists copied back) vs the GPU's commands for the same drawables."""
+    a = arena.tensor(ds.arena)
+    segs, n_inst = [], 0
+    for d in sample:
+        k = int(scene.drawable_ml[d]); off = int(scene.ml_off[k]); size = 64 + 64 * int(scene.ml_count[k])
+        segs.append((ds.arena + off, a[off:off + size].cpu().numpy()))
+        n_inst += int(scene.ml_count[k])
+    meta = a[:scene.metadata_extent()].cpu().numpy()
+    sub_list = np.ascontiguousarray(scene.drawables[sample])
+    mem = ob.Memory([(ds.arena, meta)] + segs + [(0x7F2000000000, sub_list)])
+    ind, ptr = ob.process_drawables(mem, ds.root, scene.handle_level, 0x7F2000000000, len(sample))
+    cull = scene.cull[sample].copy(); cull[:, 10] = 0
+    regions = np.array([[0, 3 * len(sample) * 4, 0, n_inst]], np.uint32)
+    ref = ob.cull_compact(mem, ds.root, scene.handle_level, 0x7F2000000000, len(sample), ind, ptr, cull, planes, eye, regions)
+    exp = {}
+    for ci in range(int(ref["cmd_count"][0])):
+        d, lod = int(sample[ref["tag"][ci, 0]]), int(ref["tag"][ci, 1])
+        k, first = int(ref["cmd"][ci, 1]), int(ref["cmd"][ci, 4])
+        exp[(d, lod)] = (int(ref["cmd"][ci, 0]), int(ref["cmd"][ci, 2]), np.sort(ref["inst"][first:first + k]))
+    # GPU commands of the sampled drawables
+    tag, cmd = summary["tag"], summary["cmd"]
+    sel = summary["used"] & torch.isin(tag[:, 0], torch.tensor(sample, dtype=torch.int32, device=tag.device))
+    g_tag, g_cmd = tag[sel].cpu().numpy(), cmd[sel].cpu().numpy()
+    got = {}
+    for t, c in zip(g_tag, g_cmd):
+        run = summary["inst"][int(c[4]) & 0xFFFFFFFF:(int(c[4]) & 0xFFFFFFFF) + int(c[1])].cpu().numpy().astype(np.uint32)
+        key = (int(t[0]), int(t[1]))
+        prev = got.get(key)
+        got[key] = (int(c[0]), int(c[2]), np.sort(np.concatenate([prev[2], run])) if prev else np.sort(run))
+    assert got.keys() == exp.keys()
+    for key in exp:
+        assert got[key][:2] == exp[key][:2] and np.array_equal(got[key][2], exp[key][2]), key
+    return sum(len(v[2]) for v in exp.values())
+
+
+def test_c3_full_size_100m_instances(ctx):
+    scene = synth.config3(100_000, 1000, state_sets=64, host_matrices=False)
+    assert scene.total_instances == 100_000_000 and scene.handle_level == 2
+    ds, arena, stream = build(ctx, scene)
+    try:
+        with torch.cuda.stream(stream):
+            ds.record_drawable_processing()
+            stream.synchronize()
+            # Tier R at full size: every drawable resolves to its own list and the shared LOD-0 primitive set
+            ind = arena.tensor(ds.indirect).view(torch.int32)[:scene.n * 4].view(-1, 4)
+            ptr = arena.tensor(ds.pointers).view(torch.int64)[:scene.n * 4].view(-1, 4)
+            assert bool((ind[:, 0] == 36).all() and (ind[:, 1] == 1000).all() and (ind[:, 2] == 0).all() and (ind[:, 3] == 0).all())
+            exp_ml = torch.from_numpy((np.uint64(ds.arena) + scene.ml_off[scene.drawable_ml]).astype(np.int64)).cuda()
+            assert bool((ptr[:, 2] == exp_ml).all()) and bool((ptr[:, 3] == 0).all())
+
+            # conservation: an all-containing frustum keeps every instance exactly once
+            ds.cull(ALL_IN, np.zeros(3, np.float32)); stream.synchronize()
+            s = gpu_summary(ds, arena, scene)
+            assert s["status"] == 0 and s["sum_k"] == 100_000_000 and int(s["inst_count"].sum()) == 100_000_000
+            assert np.array_equal(s["inst_count"], scene.regions[:, 3].astype(np.int64))
+            assert s["idx_sum"] == 100_000 * (999 * 1000 // 2) and s["idx_sq"] == 100_000 * (999 * 1000 * 1999 // 6)
+            ds.cull(NONE, np.zeros(3, np.float32)); stream.synchronize()
+            z = ds.read_counters()
+            assert int(z["inst_count"].sum()) == 0 and int(z["cmd_count"].sum()) == 0
+
+            # a real camera: idempotent, and equal to the oracle on a sample of drawables
+            planes, eye = synth.orbit_camera(30, 1500.0, far=3000.0)
+            ds.cull(planes, eye); stream.synchronize()
+            a = gpu_summary(ds, arena, scene)
+            ds.cull(planes, eye); stream.synchronize()
+            b = gpu_summary(ds, arena, scene)
+            for k in ("sum_k", "key_digest", "idx_sum", "idx_sq"):
+                assert a[k] == b[k]
+            assert np.array_equal(a["inst_count"], b["inst_count"]) and np.array_equal(a["cmd_count"], b["cmd_count"])
+            p = a["sum_k"] / 1e8
+            assert 0.05 < p < 0.8
+            vis = np.nonzero(np.bincount(a["tag"][a["used"], 0].cpu().numpy(), minlength=scene.n))[0]
+            rng = np.random.default_rng(5)
+            sample = np.unique(np.concatenate([rng.choice(vis, 25, replace=False), rng.integers(0, scene.n, 15)]))
+            assert sample_check(ctx, ds, arena, scene, planes, eye, b, sample) > 1000
+    finally:
+        ds.close()
+
+
+def test_c2_full_size_10m_drawables(ctx):
+    scene = synth.config2(10_000_000, host_matrices=False)
+    assert scene.handle_level == 3
+    ds, arena, stream = build(ctx, scene)
+    try:
+        with torch.cuda.stream(stream):
+            ds.record_drawable_processing(); stream.synchronize()
+            ind = arena.tensor(ds.indirect).view(torch.int32)[:scene.n * 4].view(-1, 4)
+            ptr = arena.tensor(ds.pointers).view(torch.int64)[:scene.n * 4].view(-1, 4)
+            assert bool((ind[:, 0] == 36).all() and (ind[:, 1] == 1).all())
+            exp_ml = torch.from_numpy((np.uint64(ds.arena) + scene.ml_off[scene.drawable_ml]).astype(np.int64)).cuda()
+            assert bool((ptr[:, 2] == exp_ml).all())
+            assert int(torch.unique(ptr[:, 0]).numel()) == 1      # one shared geometry
+            ds.cull(ALL_IN, np.zeros(3, np.float32)); stream.synchronize()
+            s = gpu_summary(ds, arena, scene)
+            assert s["status"] == 0 and s["sum_k"] == 10_000_000 and int(s["cmd_count"].sum()) == 10_000_000 and s["idx_sum"] == 0
+            planes, eye = synth.orbit_camera(100, 1500.0, far=1500.0)
+            ds.cull(planes, eye); stream.synchronize()
+            a = gpu_summary(ds, arena, scene)
+            assert 0.05 < a["sum_k"] / 1e7 < 0.8
+            rng = np.random.default_rng(6)
+            vis = a["tag"][a["used"], 0].cpu().numpy()
+            sample = np.unique(np.concatenate([rng.choice(vis, 300, replace=False), rng.integers(0, scene.n, 300)]))
+            assert sample_check(ctx, ds, arena, scene, planes, eye, a, sample) >= 300
+    finally:
+        ds.close()
