@@ -258,11 +258,13 @@ def run_b200(args):
     def timed(fn, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        torch.cuda.nvtx.range_push("timed")      # ncu --nvtx --nvtx-include "timed/" lists exactly these launches
         e0.record(stream_t)
         for k in range(steps):
             fn(args.warmup + k)
         e1.record(stream_t)
         barrier()
+        torch.cuda.nvtx.range_pop()
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device=dev)
