@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--drawables", type=int, default=0, help="override the drawable count (debug)")
     ap.add_argument("--instances", type=int, default=1000, help="matrices per list for c3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused", action="store_true", help="two calls (process_drawables, cull_compact) instead of process_and_cull")
     ap.add_argument("--cpu-sample", type=int, default=0, help="drawables in the CPU sample (0: auto)")
     return ap.parse_args()
 
@@ -232,8 +233,11 @@ def run_b200(args):
 
     def step_device(k, with_exchange=True):
         planes, eye = cams[k % 360]
-        ds.process_drawables()
-        ds.cull(planes, eye)
+        if args.unfused:
+            ds.process_drawables()
+            ds.cull(planes, eye)
+        else:
+            ds.process_and_cull(planes, eye)
         if world > 1 and with_exchange:
             exchange()
 
@@ -242,8 +246,12 @@ def run_b200(args):
 
     def step_e2e(k):
         planes, eye = cams[k % 360]
-        ds.record_drawable_processing()           # pinned host list -> device (48 B/drawable), then the kernel
-        ds.cull(planes, eye)
+        if args.unfused:
+            ds.record_drawable_processing()       # pinned host list -> device (48 B/drawable), then the kernel
+            ds.cull(planes, eye)
+        else:
+            ds.upload_drawable_list()             # the same DMA (Renderer.cpp:635-644)
+            ds.process_and_cull(planes, eye)
         if world > 1:
             exchange()
         counters_host.copy_(counters_dev, non_blocking=True)
@@ -308,10 +316,20 @@ def run_b200(args):
     k_process, k_small, k_large = (float(kt[:, i].mean()) for i in range(3))
     p = float(np.mean(surv)) / inst
     if args.workload == "c3":
+        # per instance: 64 B matrix read + 4 B index written per survivor
         dom_name, dom_ms = "cullLargeKernel", k_large
-    else:
+        alg_bytes = (64.0 + 4.0 * p) * inst
+        alg_note = "(64 + 4p) B per instance"
+    elif args.unfused:
         dom_name, dom_ms = "cullSmallKernel", k_small
-    alg_bytes = (64.0 + 4.0 * p) * inst
+        alg_bytes = (16 + 32 + 48 + 64 + 64.0 * p) * inst
+        alg_note = "per drawable: 16 indirect + 32 pointers + 48 cull record + 64 matrix read, 64p written (command 20 + pointers 32 + tag 8 + index 4)"
+    else:
+        # fused pass, one matrix per drawable: 48 list + 8 leaf entry + 4 numMatrices + 64 matrix + 48 cull record read,
+        # 48 Tier R records + 64p (command 20 + pointers 32 + tag 8 + index 4) written
+        dom_name, dom_ms = "cullSmallKernel", k_small
+        alg_bytes = (48 + 8 + 4 + 64 + 48 + 48 + 64.0 * p) * inst
+        alg_note = "per drawable: 172 B read (list 48, leaf 8, numMatrices 4, matrix 64, cull record 48) + 48 B Tier R records + 64p B written"
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
     total_inst = inst * world
@@ -327,10 +345,12 @@ def run_b200(args):
         "e2e": {"value": round(e2e_value / 1e6, 1), "unit": "M instances/s", "h2d_bytes_per_step": scene.n * 48 + 232,
                 "d2h_bytes_per_step": ds.counters_bytes, "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": int(launches),
-        "kernels_ms": {"processDrawablesKernel": round(k_process, 4), "cullSmallKernel": round(k_small, 4), "cullLargeKernel": round(k_large, 4)},
+        "kernels_ms": {"processDrawablesKernel": round(k_process, 4), "cullSmallKernel" + ("" if args.unfused else "<fused>"): round(k_small, 4),
+                       "cullLargeKernel": round(k_large, 4)},
+        "entry": "cadr_b200_process_drawables + cadr_b200_cull_compact" if args.unfused else "cadr_b200_process_and_cull",
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": recorded_traffic(dom_name), "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": int(alg_bytes), "launch_ms": round(dom_ms, 4)},
+                     "algorithmic_bytes_per_launch": int(alg_bytes), "algorithmic_bytes": alg_note, "launch_ms": round(dom_ms, 4)},
         "clocks": clocks,
     }
     if world > 1:

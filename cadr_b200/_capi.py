@@ -110,6 +110,7 @@ SYMBOLS = {
     "cadr_b200_process_drawables": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
     "cadr_b200_record_drawable_processing": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
     "cadr_b200_cull_compact": (C.c_int, [_P, C.POINTER(CullParams), _P]),
+    "cadr_b200_process_and_cull": (C.c_int, [_P, C.POINTER(CullParams), _P]),
     "cadr_b200_cull_counters_bytes": (C.c_size_t, [C.c_uint32]),
     "cadr_b200_set_profiling": (C.c_int, [_P, C.c_int]),
     "cadr_b200_kernel_times": (C.c_int, [_P, C.POINTER(C.c_float), C.c_uint32]),
@@ -253,6 +254,9 @@ class Context:
 
     def cull_compact(self, params: CullParams, stream: int = 0) -> None:
         check(self._l.cadr_b200_cull_compact(self._h, C.byref(params), _P(stream)))
+
+    def process_and_cull(self, params: CullParams, stream: int = 0) -> None:
+        check(self._l.cadr_b200_process_and_cull(self._h, C.byref(params), _P(stream)))
 
     def cull_counters_bytes(self, num_state_sets: int) -> int:
         return self._l.cadr_b200_cull_counters_bytes(num_state_sets)

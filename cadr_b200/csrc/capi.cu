@@ -320,7 +320,14 @@ int cadr_b200_cull_compact(cadr_ctx* ctx, const cadr_cull_params* params, cadr_s
 {
 	REQUIRE_DEVICE(ctx);
 	if(!params) return setError(CADR_E_LOGIC, "cull_compact: null params");
-	return launchCullCompact(ctx, *params, ctx->pick(stream));
+	return launchCullCompact(ctx, *params, ctx->pick(stream), false);
+}
+
+int cadr_b200_process_and_cull(cadr_ctx* ctx, const cadr_cull_params* params, cadr_stream stream)
+{
+	REQUIRE_DEVICE(ctx);
+	if(!params) return setError(CADR_E_LOGIC, "process_and_cull: null params");
+	return launchCullCompact(ctx, *params, ctx->pick(stream), true);
 }
 
 size_t cadr_b200_cull_counters_bytes(uint32_t numStateSets)

@@ -182,7 +182,9 @@ __device__ __forceinline__ void writeCommandRecord(const CullArgs& A, uint32_t c
 // ---------------------------------------------------------------------------------------------------
 // small lists + work-item queueing: one thread per drawable
 // ---------------------------------------------------------------------------------------------------
-template<int LEVEL>
+// FUSED = true additionally does the work of processDrawablesKernel for the same drawable (handle resolve + Tier R
+// records), so the drawable list is read once per frame and the indirect / pointers records are not re-read.
+template<int LEVEL, bool FUSED>
 __global__ void __launch_bounds__(CS_THREADS)
 cullSmallKernel(const __grid_constant__ CullArgs A)
 {
@@ -197,7 +199,31 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 	const bool valid = d < A.n;
 
 	uint32_t N = 0;
-	if(valid) N = ldg_stream_u4(A.indirect + d).y;  // IndirectData.instanceCount == ml.numMatrices
+	uint4 p0 = make_uint4(0, 0, 0, 0), p1 = p0;
+	uint64_t psBaseResolved = 0;
+	if constexpr(FUSED) {
+		if(valid) {
+			// processDrawables.comp main() :92-113 for this drawable (see process_drawables.cu)
+			const uint4* rec = reinterpret_cast<const uint4*>(A.drawableList) + size_t(d) * 3;
+			const uint4 ra = ldg_stream_u4(rec), rb = ldg_stream_u4(rec + 1), rc = ldg_stream_u4(rec + 2);
+			const uint64_t ml = lookupHandle<LEVEL>(A.root, uint64_t(rb.x) | (uint64_t(rb.y) << 32));
+			const uint64_t psb = lookupHandle<LEVEL>(A.root, uint64_t(rc.x) | (uint64_t(rc.y) << 32));
+			const uint64_t vd = lookupHandle<LEVEL>(A.root, uint64_t(ra.x) | (uint64_t(ra.y) << 32));
+			const uint64_t id = lookupHandle<LEVEL>(A.root, uint64_t(ra.z) | (uint64_t(ra.w) << 32));
+			const uint64_t dd = lookupHandle<LEVEL>(A.root, uint64_t(rb.z) | (uint64_t(rb.w) << 32));
+			N = ldg_u32(ml);
+			const uint32_t psCount = ldg_u32(psb + rc.z), psFirst = ldg_u32(psb + rc.z + 4);
+			p0 = make_uint4(uint32_t(vd), uint32_t(vd >> 32), uint32_t(id), uint32_t(id >> 32));
+			p1 = make_uint4(uint32_t(ml), uint32_t(ml >> 32), uint32_t(dd), uint32_t(dd >> 32));
+			psBaseResolved = psb;
+			st_stream_u4(const_cast<uint4*>(A.indirect) + d, make_uint4(psCount, N, psFirst, 0u));
+			st_stream_u4(const_cast<uint4*>(A.pointers) + 2ull * d, p0);
+			st_stream_u4(const_cast<uint4*>(A.pointers) + 2ull * d + 1, p1);
+		}
+	}
+	else {
+		if(valid) N = ldg_stream_u4(A.indirect + d).y;  // IndirectData.instanceCount == ml.numMatrices
+	}
 
 	// ---- number of work items this drawable needs in the large-list queue --------------------------
 	uint32_t nChunks = (N > SMALL_MAX) ? (N + CHUNK - 1) / CHUNK : 0;
@@ -207,14 +233,15 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 	// ---- per-drawable records (needed by both paths) -------------------------------------------------
 	uint32_t psOff[3] = {0, 0, 0};
 	uint32_t stateSet = 0xffffffffu;
-	uint4 p0 = make_uint4(0, 0, 0, 0), p1 = p0;
 	LodInfo L;
 	L.sphere = make_float4(0.f, 0.f, 0.f, -1.f); L.lodCount = 1; L.thr0 = L.thr1 = 0.f;
 	if(valid && N > 0) {
 		uint4 ca = ldg_stream_u4(A.cullData + 3ull * d), cb = ldg_stream_u4(A.cullData + 3ull * d + 1),
 		      cc = ldg_stream_u4(A.cullData + 3ull * d + 2);
-		p0 = ldg_stream_u4(A.pointers + 2ull * d);
-		p1 = ldg_stream_u4(A.pointers + 2ull * d + 1);
+		if constexpr(!FUSED) {
+			p0 = ldg_stream_u4(A.pointers + 2ull * d);
+			p1 = ldg_stream_u4(A.pointers + 2ull * d + 1);
+		}
 		L = unpackLod(ca, cb, cc, psOff, stateSet);
 	}
 	const uint64_t matrixList = uint64_t(p1.x) | (uint64_t(p1.y) << 32);
@@ -299,7 +326,7 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 	if(nChunks) {
 		uint32_t base = sChunkBase + (chunkIncl - nChunks);
 		for(int w = 0; w < warp; w++) base += sChunkTot[w];
-		const uint64_t psBase = primitiveSetBase<LEVEL>(A, d);
+		const uint64_t psBase = FUSED ? psBaseResolved : primitiveSetBase<LEVEL>(A, d);
 		uint32_t ps[3][2] = {{0, 0}, {0, 0}, {0, 0}};
 #pragma unroll
 		for(int l = 0; l < 3; l++)
@@ -337,7 +364,7 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 			atomicOr(&A.hdr->status, CADR_CULL_STATUS_REGION_OVERFLOW);
 		}
 		else {
-			const uint64_t psBase = primitiveSetBase<LEVEL>(A, d);
+			const uint64_t psBase = FUSED ? psBaseResolved : primitiveSetBase<LEVEL>(A, d);
 			uint32_t ci = reg.x + cmdOff, ii = reg.z + instOff;
 #pragma unroll
 			for(int l = 0; l < 3; l++) {
@@ -711,7 +738,7 @@ static int cullVariant()
 	return v ? std::atoi(v) : 1;   // 1 = TMA pipeline (default), 0 = direct-load version
 }
 
-int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s)
+int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, bool fused)
 {
 	if(p.handleLevel < 1 || p.handleLevel > 3)
 		return setError(CADR_E_LOGIC, "cull_compact: handleLevel must be 1, 2 or 3 (got %u)", p.handleLevel);
@@ -755,10 +782,19 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s)
 
 	uint32_t gridS = (p.numDrawables + CS_THREADS - 1) / CS_THREADS;
 	ctx->timeBegin(KS_CULL_SMALL, s);
-	switch(p.handleLevel) {
-	case 1: cullSmallKernel<1><<<gridS, CS_THREADS, 0, s>>>(A); break;
-	case 2: cullSmallKernel<2><<<gridS, CS_THREADS, 0, s>>>(A); break;
-	default: cullSmallKernel<3><<<gridS, CS_THREADS, 0, s>>>(A); break;
+	if(fused) {
+		switch(p.handleLevel) {
+		case 1: cullSmallKernel<1, true><<<gridS, CS_THREADS, 0, s>>>(A); break;
+		case 2: cullSmallKernel<2, true><<<gridS, CS_THREADS, 0, s>>>(A); break;
+		default: cullSmallKernel<3, true><<<gridS, CS_THREADS, 0, s>>>(A); break;
+		}
+	}
+	else {
+		switch(p.handleLevel) {
+		case 1: cullSmallKernel<1, false><<<gridS, CS_THREADS, 0, s>>>(A); break;
+		case 2: cullSmallKernel<2, false><<<gridS, CS_THREADS, 0, s>>>(A); break;
+		default: cullSmallKernel<3, false><<<gridS, CS_THREADS, 0, s>>>(A); break;
+		}
 	}
 	ctx->timeEnd(KS_CULL_SMALL, s);
 	ctx->launches++;

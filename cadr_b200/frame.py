@@ -120,6 +120,16 @@ class DeviceScene:
         s = self.stream if stream is None else stream
         self.ctx.cull_compact(self.cull_params(planes, eye), stream=s)
 
+    def process_and_cull(self, planes: np.ndarray, eye: np.ndarray, stream: int | None = None) -> None:
+        """Tier R + Tier X in one pass over the (already resident) drawable list."""
+        s = self.stream if stream is None else stream
+        self.ctx.process_and_cull(self.cull_params(planes, eye), stream=s)
+
+    def upload_drawable_list(self, stream: int | None = None) -> None:
+        """The per-frame DMA of Renderer::recordDrawableProcessing (Renderer.cpp:635-644) on its own."""
+        s = self.stream if stream is None else stream
+        self.ctx.memcpy_h2d(self.drawable_list, self.host_list_ptr, self.scene.n * 48, stream=s)
+
     # -- read-back ---------------------------------------------------------------------------------
     def _read(self, addr: int, nbytes: int, dtype) -> np.ndarray:
         out = np.empty(nbytes, dtype=np.uint8)

@@ -222,13 +222,18 @@ void Renderer::submit()
 	if(!_processingRecorded) return;
 	if(!hasDevice()) throw DeviceError("CadR::Renderer::submit(): this renderer has no CUDA device; there is no CPU fallback");
 	if(_collectFrameInfo) cadr_b200_set_profiling(_ctx, 1);
-	// staging -> device copy of the flattened list, then the processing kernel (Renderer.cpp:635-692)
-	check(cadr_b200_record_drawable_processing(_ctx, reinterpret_cast<const cadr_drawable_gpu_data*>(_drawableStagingData),
-	                                           _dataStorage->handleTableDeviceAddress(), _dataStorage->handleLevel(),
-	                                           _drawableBufferAddress, _drawIndirectBufferAddress, _drawablePointersBufferAddress,
-	                                           _recordedDrawables, _stream));
+	if(!_cullingRecorded) {
+		// staging -> device copy of the flattened list, then the processing kernel (Renderer.cpp:635-692)
+		check(cadr_b200_record_drawable_processing(_ctx, reinterpret_cast<const cadr_drawable_gpu_data*>(_drawableStagingData),
+		                                           _dataStorage->handleTableDeviceAddress(), _dataStorage->handleLevel(),
+		                                           _drawableBufferAddress, _drawIndirectBufferAddress, _drawablePointersBufferAddress,
+		                                           _recordedDrawables, _stream));
+	}
 	if(_cullingRecorded) {
+		// culling recorded: the same DMA, then ONE pass that resolves handles, writes the indirect / pointers
+		// records (identical to the processing kernel's) and culls
 		ensureCullBuffers();
+		check(cadr_b200_memcpy_h2d(_ctx, _drawableBufferAddress, _drawableStagingData, _recordedDrawables * sizeof(DrawableGpuData), _stream));
 		check(cadr_b200_memcpy_h2d(_ctx, _cullDataBufferAddress, _cullStagingData, _recordedDrawables * sizeof(DrawableCullData), _stream));
 		check(cadr_b200_memcpy_h2d(_ctx, _cullRegionsAddress, _cull.regions.data(), _cull.regions.size() * sizeof(cadr_stateset_region), _stream));
 		cadr_cull_params p{};
@@ -247,7 +252,7 @@ void Renderer::submit()
 		p.counters = _cull.counters;
 		p.chunkWorkspace = _cullWorkspaceAddress;
 		p.chunkCapacity = uint32_t(_rangeChunks);
-		check(cadr_b200_cull_compact(_ctx, &p, _stream));
+		check(cadr_b200_process_and_cull(_ctx, &p, _stream));
 	}
 }
 

@@ -261,6 +261,12 @@ CADR_API int  cadr_b200_record_drawable_processing(cadr_ctx* ctx, const cadr_dra
 /* No reference counterpart.  Specification: DESIGN.md "Tier X". */
 CADR_API int  cadr_b200_cull_compact(cadr_ctx* ctx, const cadr_cull_params* params, cadr_stream stream);
 
+/* cadr_b200_process_drawables + cadr_b200_cull_compact in ONE pass over the drawable list: the first kernel also
+ * resolves the handles and writes params->indirectData / params->drawablePointers (which are OUTPUTS here, with
+ * exactly the contents cadr_b200_process_drawables produces), so the 48-byte records are read once per frame and
+ * the 16+32-byte Tier R records are not read back.  Results are identical to the two-call sequence. */
+CADR_API int  cadr_b200_process_and_cull(cadr_ctx* ctx, const cadr_cull_params* params, cadr_stream stream);
+
 /* Size of the counters buffer for `numStateSets` StateSets. */
 CADR_API size_t cadr_b200_cull_counters_bytes(uint32_t numStateSets);
 

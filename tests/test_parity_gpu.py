@@ -206,3 +206,42 @@ def test_patch_handles_matches_oracle(ctx, kw):
         assert np.array_equal(ind, e_ind) and np.array_equal(ptr, e_ptr)
     finally:
         ds.close()
+
+
+@pytest.mark.parametrize("kw,frame", X_CASES[:4], ids=lambda v: f"seed{v['seed']}" if isinstance(v, dict) else f"f{v}")
+def test_fused_process_and_cull_equals_two_calls(ctx, kw, frame):
+    """cadr_b200_process_and_cull == cadr_b200_process_drawables + cadr_b200_cull_compact, output for output."""
+    sc = synth.random_scene(**kw)
+    planes, eye = synth.orbit_camera(frame, 250.0, far=500.0)
+    ds = DeviceScene(ctx, sc)
+    try:
+        ds.upload_drawable_list()
+        ctx.memset(ds.indirect, 0xEE, sc.n * 16); ctx.memset(ds.pointers, 0xEE, sc.n * 32)
+        ds.process_and_cull(planes, eye)
+        ctx.sync(ds.stream)
+        ind, ptr = ds.read_tier_r()
+        got = ds.read_tier_x()
+        _, e_ind, e_ptr = _oracle_r(ds)
+        assert np.array_equal(ind, e_ind) and np.array_equal(ptr, e_ptr)      # Tier R records written by the fused pass
+        _, _, ref = oracle_tier_x(sc, planes, eye, arena_base=ds.arena, list_base=ds.drawable_list)
+        assert_tier_x_equal(got, ref)
+    finally:
+        ds.close()
+
+
+def test_fused_baseline_shapes(ctx):
+    for sc, far in ((synth.config2(150_001), 1500.0), (synth.config3(300, 1000, state_sets=16), 3000.0)):
+        planes, eye = synth.orbit_camera(40, 1500.0, far=far)
+        ds = DeviceScene(ctx, sc)
+        try:
+            ds.upload_drawable_list()
+            ds.process_and_cull(planes, eye)
+            ctx.sync(ds.stream)
+            ind, ptr = ds.read_tier_r()
+            got = ds.read_tier_x()
+            _, e_ind, e_ptr = _oracle_r(ds)
+            assert np.array_equal(ind, e_ind) and np.array_equal(ptr, e_ptr)
+            _, _, ref = oracle_tier_x(sc, planes, eye, arena_base=ds.arena, list_base=ds.drawable_list)
+            assert_tier_x_equal(got, ref)
+        finally:
+            ds.close()
