@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--instances", type=int, default=1000, help="matrices per list for c3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="two calls (process_drawables, cull_compact) instead of process_and_cull")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU: peer = records stored into every rank's gathered arrays by the cull kernels over NVLink; "
+                         "nccl = all_gather_into_tensor after the cull (baseline)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="drawables in the CPU sample (0: auto)")
     return ap.parse_args()
 
@@ -222,38 +225,44 @@ def run_b200(args):
     cams = [camera(args, k) for k in range(360)]
 
     # multi-GPU exchange: every rank ends up with all ranks' compacted command lists and per-range counters
-    ex = None
+    ex = px = None
     if world > 1:
-        from cadr_b200.shard import Exchange
-        ex = Exchange(ds.cmd_cap, scene.num_state_sets, dev)
-        parts = [arena.tensor(ds.cmd_out), arena.tensor(ds.ptr_out), arena.tensor(ds.tag_out), arena.tensor(ds.counters)]
+        from cadr_b200.shard import Exchange, PeerExchange
+        if args.exchange == "nccl":
+            ex = Exchange(ds.cmd_cap, scene.num_state_sets, dev)
+            parts = [arena.tensor(ds.cmd_out), arena.tensor(ds.ptr_out), arena.tensor(ds.tag_out), arena.tensor(ds.counters)]
+        else:
+            px = PeerExchange(ctx, ds.cmd_cap, scene.num_state_sets)
 
-    def exchange():
-        ex.run(*parts)
-
-    def step_device(k, with_exchange=True):
+    def run_cull(k, with_exchange):
         planes, eye = cams[k % 360]
+        if px is not None and with_exchange:
+            p = ds.cull_params(planes, eye)
+            px.begin_frame(p)
+            if args.unfused:
+                ds.process_drawables()
+                ctx.cull_compact(p, stream=stream)
+            else:
+                ctx.process_and_cull(p, stream=stream)
+            px.end_frame(ds.counters, stream=stream)
+            return
         if args.unfused:
             ds.process_drawables()
             ds.cull(planes, eye)
         else:
             ds.process_and_cull(planes, eye)
-        if world > 1 and with_exchange:
-            exchange()
+        if ex is not None and with_exchange:
+            ex.run(*parts)
+
+    def step_device(k, with_exchange=True):
+        run_cull(k, with_exchange)
 
     counters_host = torch.empty(ds.counters_bytes, dtype=torch.uint8).pin_memory()
     counters_dev = arena.tensor(ds.counters)
 
     def step_e2e(k):
-        planes, eye = cams[k % 360]
-        if args.unfused:
-            ds.record_drawable_processing()       # pinned host list -> device (48 B/drawable), then the kernel
-            ds.cull(planes, eye)
-        else:
-            ds.upload_drawable_list()             # the same DMA (Renderer.cpp:635-644)
-            ds.process_and_cull(planes, eye)
-        if world > 1:
-            exchange()
+        ds.upload_drawable_list()                 # pinned host list -> device, 48 B/drawable (Renderer.cpp:635-644)
+        run_cull(k, True)
         counters_host.copy_(counters_dev, non_blocking=True)
         stream_t.synchronize()                    # the host consumes the counts every frame
 
@@ -356,12 +365,15 @@ def run_b200(args):
     if world > 1:
         line["cull_only"] = {"value": round(total_inst * args.steps / (ms_cull_only * 1e-3) / 1e6, 1), "unit": "M instances/s",
                              "ms_per_step": round(ms_cull_only / args.steps, 4)}
-        line["exchange_bytes_per_rank"] = int(ex.bytes_per_rank)
+        line["exchange"] = ("fused: cull kernels store records into every rank's gathered arrays over NVLink peer mappings (no collective call)"
+                            if px is not None else f"NCCL all_gather_into_tensor of {ex.bytes_per_rank} padded bytes per rank after the cull")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, desc, threads, _ = cpu_sample_run(args, 5, 1)
         line["cpu_baseline"] = {"value": round(v / 1e6, 3), "unit": "M instances/s", "cores": threads, "kind": "port", "sample": desc}
     if rank == 0:
         print(json.dumps(line))
+    if px is not None:
+        px.close()
     ds.close()
     ctx.close()
     if world > 1:

@@ -10,8 +10,8 @@ Layout (only what the hot path needs):
 Importing the package does not load the shared library; `cadr_b200.Context(...)` does and raises if it was
 not built.  There is no CPU/PyTorch fallback anywhere in this package.
 """
-from ._capi import (CadrError, Context, CopyRegion, CullParams, HandlePatch, LogicError, NoDevice,  # noqa: F401
+from ._capi import (CadrError, Context, CopyRegion, CullParams, ExchangeSync, HandlePatch, LogicError, NoDevice,  # noqa: F401
                     OutOfResources, Timeout, LIB_PATH, SYMBOLS, lib)
 
-__all__ = ["CadrError", "Context", "CopyRegion", "CullParams", "HandlePatch", "LogicError", "NoDevice",
+__all__ = ["CadrError", "Context", "CopyRegion", "CullParams", "ExchangeSync", "HandlePatch", "LogicError", "NoDevice",
            "OutOfResources", "Timeout", "LIB_PATH", "SYMBOLS", "lib"]

@@ -82,6 +82,24 @@ class CullParams(C.Structure):
         ("chunkWorkspace", C.c_uint64),
         ("chunkCapacity", C.c_uint32),
         ("reserved1", C.c_uint32),
+        ("exchangeWorld", C.c_uint32),
+        ("exchangeRank", C.c_uint32),
+        ("exchangeCmdCapacity", C.c_uint32),
+        ("reserved2", C.c_uint32),
+        ("exchangeCmd", C.c_uint64 * 8),
+        ("exchangePtr", C.c_uint64 * 8),
+        ("exchangeTag", C.c_uint64 * 8),
+    ]
+
+
+class ExchangeSync(C.Structure):
+    _fields_ = [
+        ("world", C.c_uint32), ("rank", C.c_uint32),
+        ("frameSeq", C.c_uint64),
+        ("localCounters", C.c_uint64),
+        ("countersBytes", C.c_uint32), ("reserved", C.c_uint32),
+        ("peerCounters", C.c_uint64 * 8),
+        ("peerFlags", C.c_uint64 * 8),
     ]
 
 
@@ -111,6 +129,11 @@ SYMBOLS = {
     "cadr_b200_record_drawable_processing": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
     "cadr_b200_cull_compact": (C.c_int, [_P, C.POINTER(CullParams), _P]),
     "cadr_b200_process_and_cull": (C.c_int, [_P, C.POINTER(CullParams), _P]),
+    "cadr_b200_ipc_export": (C.c_int, [_P, C.c_uint64, C.c_char_p]),
+    "cadr_b200_ipc_import": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_uint64)]),
+    "cadr_b200_ipc_close": (C.c_int, [_P, C.c_uint64]),
+    "cadr_b200_exchange_publish": (C.c_int, [_P, C.POINTER(ExchangeSync), _P]),
+    "cadr_b200_exchange_wait": (C.c_int, [_P, C.POINTER(ExchangeSync), _P]),
     "cadr_b200_cull_counters_bytes": (C.c_size_t, [C.c_uint32]),
     "cadr_b200_set_profiling": (C.c_int, [_P, C.c_int]),
     "cadr_b200_kernel_times": (C.c_int, [_P, C.POINTER(C.c_float), C.c_uint32]),
@@ -133,7 +156,7 @@ def lib() -> C.CDLL:
             f = getattr(l, name)  # AttributeError if the library does not export a declared symbol
             f.restype = res
             f.argtypes = args
-        if l.cadr_b200_abi_version() != 1:
+        if l.cadr_b200_abi_version() != 2:
             raise ImportError("libcadr_b200.so ABI version mismatch")
         _lib = l
     return _lib
@@ -257,6 +280,26 @@ class Context:
 
     def process_and_cull(self, params: CullParams, stream: int = 0) -> None:
         check(self._l.cadr_b200_process_and_cull(self._h, C.byref(params), _P(stream)))
+
+    # -- multi-GPU plumbing
+    def ipc_export(self, addr: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(self._l.cadr_b200_ipc_export(self._h, addr, buf))
+        return buf.raw
+
+    def ipc_import(self, handle: bytes) -> int:
+        a = C.c_uint64()
+        check(self._l.cadr_b200_ipc_import(self._h, handle, C.byref(a)))
+        return a.value
+
+    def ipc_close(self, addr: int) -> None:
+        check(self._l.cadr_b200_ipc_close(self._h, addr))
+
+    def exchange_publish(self, sync: "ExchangeSync", stream: int = 0) -> None:
+        check(self._l.cadr_b200_exchange_publish(self._h, C.byref(sync), _P(stream)))
+
+    def exchange_wait(self, sync: "ExchangeSync", stream: int = 0) -> None:
+        check(self._l.cadr_b200_exchange_wait(self._h, C.byref(sync), _P(stream)))
 
     def cull_counters_bytes(self, num_state_sets: int) -> int:
         return self._l.cadr_b200_cull_counters_bytes(num_state_sets)

@@ -79,6 +79,11 @@ struct CullArgs {
 	uint32_t  n;
 	float4 plane[6];
 	float4 eye;
+	// fused multi-GPU exchange: gathered arrays of every rank (peer mappings), 0 ranks = write cmdOut/ptrOut/tagOut
+	uint32_t  xWorld, xSlotBase;          // xSlotBase = rank * capacity
+	uint8_t*  xCmd[CADR_MAX_PEERS];
+	uint4*    xPtr[CADR_MAX_PEERS];
+	uint2*    xTag[CADR_MAX_PEERS];
 };
 
 struct Mat { float4 c0, c1, c2, c3; };  // column-major mat4
@@ -172,6 +177,19 @@ __device__ __forceinline__ void writeCommandRecord(const CullArgs& A, uint32_t c
                                                    uint32_t firstIndex, uint32_t firstInstance, uint32_t d, uint32_t lod,
                                                    uint4 p0, uint4 p1)
 {
+	if(A.xWorld > 1) {
+		// fused exchange: the record goes to slot (rank * capacity + ci) of EVERY rank's gathered arrays over NVLink
+		// peer mappings while the cull is still running (the local copy is one of them)
+		const uint64_t slot = uint64_t(A.xSlotBase) + ci;
+		for(uint32_t r = 0; r < A.xWorld; r++) {
+			uint32_t* c = reinterpret_cast<uint32_t*>(A.xCmd[r] + 20ull * slot);
+			c[0] = indexCount; c[1] = instanceCount; c[2] = firstIndex; c[3] = 0u; c[4] = firstInstance;
+			A.xPtr[r][2ull * slot] = p0;
+			A.xPtr[r][2ull * slot + 1] = p1;
+			A.xTag[r][slot] = make_uint2(d, lod);
+		}
+		return;
+	}
 	uint32_t* c = reinterpret_cast<uint32_t*>(A.cmdOut + 20ull * ci);
 	c[0] = indexCount; c[1] = instanceCount; c[2] = firstIndex; c[3] = 0u; c[4] = firstInstance;
 	A.ptrOut[2ull * ci] = p0;
@@ -749,12 +767,20 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 	CADR_CUDA(cudaMemsetAsync(reinterpret_cast<void*>(p.counters), 0, cadr_b200_cull_counters_bytes(p.numStateSets), s));
 	if(p.numDrawables == 0)
 		return CADR_OK;
+	const bool exchange = p.exchangeWorld > 1;
 	if(!p.handleTableRoot || !p.drawableList || !p.indirectData || !p.drawablePointers || !p.cullData ||
-	   !p.stateSetRegions || !p.cmdOut || !p.ptrOut || !p.tagOut || !p.instOut)
+	   !p.stateSetRegions || !p.instOut || (!exchange && (!p.cmdOut || !p.ptrOut || !p.tagOut)))
 		return setError(CADR_E_LOGIC, "cull_compact: null device address");
-	if((p.drawableList | p.indirectData | p.drawablePointers | p.cullData | p.stateSetRegions | p.ptrOut | p.chunkWorkspace) & 15)
+	if(exchange) {
+		if(p.exchangeWorld > CADR_MAX_PEERS || p.exchangeRank >= p.exchangeWorld)
+			return setError(CADR_E_LOGIC, "cull_compact: bad exchange world/rank (%u/%u)", p.exchangeRank, p.exchangeWorld);
+		for(uint32_t r = 0; r < p.exchangeWorld; r++)
+			if(!p.exchangeCmd[r] || !p.exchangePtr[r] || !p.exchangeTag[r] || (p.exchangePtr[r] & 15) || (p.exchangeTag[r] & 7) || (p.exchangeCmd[r] & 3))
+				return setError(CADR_E_LOGIC, "cull_compact: exchange buffers of rank %u missing or misaligned", r);
+	}
+	if((p.drawableList | p.indirectData | p.drawablePointers | p.cullData | p.stateSetRegions | (exchange ? 0 : p.ptrOut) | p.chunkWorkspace) & 15)
 		return setError(CADR_E_LOGIC, "cull_compact: record buffers must be 16-byte aligned");
-	if((p.cmdOut & 3) || (p.tagOut & 7) || (p.instOut & 3))
+	if((p.instOut & 3) || (!exchange && ((p.cmdOut & 3) || (p.tagOut & 7))))
 		return setError(CADR_E_LOGIC, "cull_compact: output buffers misaligned");
 	if(p.numStateSets == 0)
 		return setError(CADR_E_LOGIC, "cull_compact: numStateSets must be > 0");
@@ -779,6 +805,13 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 	A.n = p.numDrawables;
 	for(int k = 0; k < 6; k++) A.plane[k] = make_float4(p.planes[k][0], p.planes[k][1], p.planes[k][2], p.planes[k][3]);
 	A.eye = make_float4(p.eye[0], p.eye[1], p.eye[2], 0.f);
+	A.xWorld = exchange ? p.exchangeWorld : 0;
+	A.xSlotBase = exchange ? p.exchangeRank * p.exchangeCmdCapacity : 0;
+	for(uint32_t r = 0; r < CADR_MAX_PEERS; r++) {
+		A.xCmd[r] = reinterpret_cast<uint8_t*>(exchange && r < p.exchangeWorld ? p.exchangeCmd[r] : 0);
+		A.xPtr[r] = reinterpret_cast<uint4*>(exchange && r < p.exchangeWorld ? p.exchangePtr[r] : 0);
+		A.xTag[r] = reinterpret_cast<uint2*>(exchange && r < p.exchangeWorld ? p.exchangeTag[r] : 0);
+	}
 
 	uint32_t gridS = (p.numDrawables + CS_THREADS - 1) / CS_THREADS;
 	ctx->timeBegin(KS_CULL_SMALL, s);

@@ -82,3 +82,105 @@ class Exchange:
         g = {k: v.cpu().numpy() for k, v in self.gathered.items()}
         return dict(cmd=g["cmd"].view(np.uint32).reshape(-1, 5), ptr=g["ptr"].view(np.uint64).reshape(-1, 4),
                     tag=g["tag"].view(np.uint32).reshape(-1, 2))
+
+
+class PeerExchange:
+    """The fused exchange: no collective call per frame.  Every rank owns gathered arrays (commands, pointers, tags,
+    counters) and a flag array, all exported through CUDA IPC and mapped by every peer once at set-up.  During a
+    frame the cull kernels store each emitted record directly into ALL ranks' gathered arrays over NVLink
+    (cadr_cull_params.exchange*), so the transfer overlaps the cull item by item; afterwards a one-CTA kernel
+    publishes the rank's counters and raises a frame flag on every peer, and a second one makes the stream wait for
+    all peers' flags.  Gathered arrays are double-buffered by frame parity: a rank can run at most one frame ahead
+    of a peer (it cannot pass the wait), so set k&1 is never overwritten while a peer still reads frame k-2... k."""
+
+    def __init__(self, ctx, cmd_capacity: int, num_ranges: int, group=None):
+        import ctypes as C
+        from . import _capi
+        self.ctx, self.group = ctx, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        caps = [None] * self.world
+        dist.all_gather_object(caps, (int(cmd_capacity), int(num_ranges)), group=group)
+        self.cmd_cap = max(c[0] for c in caps)
+        self.num_ranges = max(c[1] for c in caps)
+        self.counters_bytes = 64 + 8 * self.num_ranges
+        sizes = dict(cmd=self.world * self.cmd_cap * 20, ptr=self.world * self.cmd_cap * 32, tag=self.world * self.cmd_cap * 8,
+                     counters=self.world * self.counters_bytes)
+        self.sizes = sizes
+        # two sets (frame parity) of gathered arrays + one flag array
+        self.local = [{k: ctx.arena_alloc(max(v, 256)) for k, v in sizes.items()} for _ in range(2)]
+        self.flags = ctx.arena_alloc(256)
+        ctx.memset(self.flags, 0, 256)
+        for st in self.local:
+            ctx.memset(st["counters"], 0, sizes["counters"])
+        ctx.sync()
+        mine = dict(sets=[{k: ctx.ipc_export(a) for k, a in st.items()} for st in self.local], flags=ctx.ipc_export(self.flags))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        self.peer = []   # [rank] -> {"sets": [{cmd,ptr,tag,counters}], "flags": addr}
+        self._imported = []
+        for r, h in enumerate(everyone):
+            if r == self.rank:
+                self.peer.append(dict(sets=self.local, flags=self.flags))
+                continue
+            sets = []
+            for st in h["sets"]:
+                m = {k: ctx.ipc_import(v) for k, v in st.items()}
+                self._imported += list(m.values())
+                sets.append(m)
+            f = ctx.ipc_import(h["flags"])
+            self._imported.append(f)
+            self.peer.append(dict(sets=sets, flags=f))
+        self.frame = 0
+        self._C, self._capi = C, _capi
+        dist.barrier(group=group)
+
+    def begin_frame(self, params) -> None:
+        """Point the cull at this frame's gathered arrays (modifies `params` in place)."""
+        self.frame += 1
+        k = self.frame & 1
+        params.exchangeWorld, params.exchangeRank, params.exchangeCmdCapacity = self.world, self.rank, self.cmd_cap
+        for r in range(self.world):
+            s = self.peer[r]["sets"][k]
+            params.exchangeCmd[r], params.exchangePtr[r], params.exchangeTag[r] = s["cmd"], s["ptr"], s["tag"]
+
+    def _sync(self, local_counters: int):
+        s = self._capi.ExchangeSync()
+        s.world, s.rank, s.frameSeq = self.world, self.rank, self.frame
+        s.localCounters, s.countersBytes = local_counters, self.counters_bytes
+        k = self.frame & 1
+        for r in range(self.world):
+            s.peerCounters[r] = self.peer[r]["sets"][k]["counters"]
+            s.peerFlags[r] = self.peer[r]["flags"]
+        return s
+
+    def end_frame(self, local_counters: int, stream: int = 0) -> None:
+        """After the cull kernels of the frame: publish counters + flag to every peer, then wait for all peers."""
+        s = self._sync(local_counters)
+        self.ctx.exchange_publish(s, stream)
+        self.ctx.exchange_wait(s, stream)
+
+    def read(self) -> dict:
+        """Host view of the current frame's gathered arrays (after a sync)."""
+        k = self.frame & 1
+        out = {}
+        for name, dt in (("cmd", np.uint32), ("ptr", np.uint64), ("tag", np.uint32), ("counters", np.uint8)):
+            buf = np.empty(self.sizes[name], np.uint8)
+            self.ctx.memcpy_d2h(buf, self.local[k][name])
+            out[name] = buf
+        self.ctx.sync()
+        cnt = out["counters"].reshape(self.world, self.counters_bytes)[:, 64:].copy().view(np.uint64)
+        return dict(cmd=out["cmd"].view(np.uint32).reshape(-1, 5), ptr=out["ptr"].view(np.uint64).reshape(-1, 4),
+                    tag=out["tag"].view(np.uint32).reshape(-1, 2), counts=cnt,
+                    status=out["counters"].reshape(self.world, self.counters_bytes)[:, :4].copy().view(np.uint32)[:, 0])
+
+    def close(self) -> None:
+        self.ctx.sync()
+        dist.barrier(group=self.group)
+        for a in self._imported:
+            self.ctx.ipc_close(a)
+        self._imported = []
+        for st in self.local:
+            for a in st.values():
+                self.ctx.arena_free(a)
+        self.ctx.arena_free(self.flags)
+        self.local = []

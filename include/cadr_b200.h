@@ -40,7 +40,7 @@ extern "C" {
 # define CADR_API __attribute__((visibility("default")))
 #endif
 
-#define CADR_B200_ABI_VERSION 1
+#define CADR_B200_ABI_VERSION 2
 
 /* ---- error codes (src/CadR/Exceptions.h:13-40) ------------------------------------------------- */
 enum {
@@ -139,6 +139,8 @@ typedef struct cadr_cull_header {
 #define CADR_CULL_SMALL_LIST_MAX         32u    /* lists up to this size are evaluated by one thread  */
 #define CADR_CULL_WORK_ITEM_INSTANCES    1024u
 
+#define CADR_MAX_PEERS 8
+
 typedef struct cadr_cull_params {
 	/* Tier R inputs, same meaning as the push constants (processDrawables.comp:68-74) */
 	uint64_t handleTableRoot;
@@ -165,7 +167,31 @@ typedef struct cadr_cull_params {
 	uint64_t chunkWorkspace;     /* CADR_CULL_WORK_ITEM_BYTES per work item of the large-list kernel, 16-B aligned */
 	uint32_t chunkCapacity;      /* >= sum over drawables with > 32 matrices of ceil(numMatrices/1024) */
 	uint32_t reserved1;
+	/* Multi-GPU, fused exchange (no reference counterpart).  With exchangeWorld >= 2 the kernels store
+	 * every emitted command / pointers / tag record straight into the gathered arrays of ALL ranks over NVLink peer
+	 * mappings (slot exchangeRank * exchangeCmdCapacity + index) while the cull is still running; cmdOut / ptrOut /
+	 * tagOut are then ignored.  exchangeCmd[r] etc. are rank r's gathered arrays as mapped in THIS process
+	 * (cadr_b200_ipc_import; entry [exchangeRank] is the local buffer).  exchangeWorld 0 or 1: no exchange. */
+	uint32_t exchangeWorld;
+	uint32_t exchangeRank;
+	uint32_t exchangeCmdCapacity;
+	uint32_t reserved2;
+	uint64_t exchangeCmd[CADR_MAX_PEERS];
+	uint64_t exchangePtr[CADR_MAX_PEERS];
+	uint64_t exchangeTag[CADR_MAX_PEERS];
 } cadr_cull_params;
+
+/* Publishing a rank's per-range counters to its peers and signalling "frame complete" (stream-ordered after the
+ * cull kernels), and waiting until every peer has done the same.  Flags are monotonically increasing frame
+ * sequence numbers, one u64 per rank in each rank's flag array. */
+typedef struct cadr_exchange_sync {
+	uint32_t world, rank;
+	uint64_t frameSeq;                        /* > 0, strictly increasing per call pair                      */
+	uint64_t localCounters;                   /* this rank's counters buffer (header + packed counts)         */
+	uint32_t countersBytes, reserved;
+	uint64_t peerCounters[CADR_MAX_PEERS];    /* rank r's gathered counters [world][countersBytes] as mapped here */
+	uint64_t peerFlags[CADR_MAX_PEERS];       /* rank r's flag array [world] u64 as mapped here                  */
+} cadr_exchange_sync;
 
 /* ---- upload ------------------------------------------------------------------ */
 
@@ -266,6 +292,19 @@ CADR_API int  cadr_b200_cull_compact(cadr_ctx* ctx, const cadr_cull_params* para
  * exactly the contents cadr_b200_process_drawables produces), so the 48-byte records are read once per frame and
  * the 16+32-byte Tier R records are not read back.  Results are identical to the two-call sequence. */
 CADR_API int  cadr_b200_process_and_cull(cadr_ctx* ctx, const cadr_cull_params* params, cadr_stream stream);
+
+/* ---- multi-GPU plumbing: one process per GPU, buffers shared through CUDA IPC ------------------------------- */
+
+#define CADR_IPC_HANDLE_BYTES 64
+/* Export a buffer returned by cadr_b200_arena_alloc / map a peer's exported buffer into this process. */
+CADR_API int  cadr_b200_ipc_export(cadr_ctx* ctx, uint64_t devAddr, unsigned char handle[CADR_IPC_HANDLE_BYTES]);
+CADR_API int  cadr_b200_ipc_import(cadr_ctx* ctx, const unsigned char handle[CADR_IPC_HANDLE_BYTES], uint64_t* devAddr);
+CADR_API int  cadr_b200_ipc_close(cadr_ctx* ctx, uint64_t devAddr);
+/* Copy this rank's counters into slot `rank` of every peer's gathered counters, then raise flag[rank] = frameSeq
+ * on every peer (release at system scope). */
+CADR_API int  cadr_b200_exchange_publish(cadr_ctx* ctx, const cadr_exchange_sync* sync, cadr_stream stream);
+/* Block the stream (not the host) until every peer's flag in the LOCAL flag array has reached frameSeq. */
+CADR_API int  cadr_b200_exchange_wait(cadr_ctx* ctx, const cadr_exchange_sync* sync, cadr_stream stream);
 
 /* Size of the counters buffer for `numStateSets` StateSets. */
 CADR_API size_t cadr_b200_cull_counters_bytes(uint32_t numStateSets);
