@@ -122,37 +122,60 @@ int launchScatterCopy(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n
 	return shipUnitsAndLaunch(ctx, numUnits, s);
 }
 
-// Regions of at least this size go out as their own DMA (what vkCmdCopyBuffer does for every region);
-// smaller ones are packed so that thousands of tiny allocations cost one DMA + one kernel.
-constexpr uint64_t UPLOAD_DMA_THRESHOLD = 256u << 10;
+// Three ways for a region to reach the device, chosen per call:
+//   * regions of at least UPLOAD_DMA_THRESHOLD bytes go out as their own DMA (what vkCmdCopyBuffer does for every
+//     region; the reference's regions are few and large because staging mirrors the device layout);
+//   * the remaining regions, when their sources are dense in the staging block (>= half of the span they cover),
+//     are shipped with ONE DMA of that span into the device mirror and scattered by ONE kernel launch — thousands
+//     of rewritten allocations cost one copy-engine transfer at PCIe speed plus an HBM-speed scatter;
+//   * otherwise they are packed on the host first (one DMA of the packed bytes + one scatter launch).
+constexpr uint64_t UPLOAD_DMA_THRESHOLD = 1u << 20;
 
 int launchUpload(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n, const void* stagingBase, cudaStream_t s)
 {
 	const uint8_t* base = static_cast<const uint8_t*>(stagingBase);
-	std::vector<cadr_copy_region> small;   // srcOffset rewritten to the offset inside the packed block
+	std::vector<cadr_copy_region> small;   // srcOffset rewritten below to the offset inside the device mirror
 	std::vector<uint32_t> smallIdx;
-	size_t packedBytes = 0;
+	uint64_t lo = ~0ull, hi = 0, sum = 0;
 	for(uint32_t i = 0; i < n; i++) {
 		const cadr_copy_region& r = regions[i];
 		if(r.bytes == 0) continue;
 		if(r.dstAddr == 0)
 			return setError(CADR_E_LOGIC, "upload: region %u has a null destination", i);
+		if(base == nullptr && r.srcOffset == 0)
+			return setError(CADR_E_LOGIC, "upload: region %u has a null source", i);
 		if(r.bytes >= UPLOAD_DMA_THRESHOLD) {
 			CADR_CUDA(cudaMemcpyAsync(reinterpret_cast<void*>(r.dstAddr), base + r.srcOffset, r.bytes, cudaMemcpyHostToDevice, s));
+			continue;
 		}
-		else {
-			small.push_back(cadr_copy_region{r.dstAddr, packedBytes, r.bytes});
-			smallIdx.push_back(i);
-			packedBytes += (r.bytes + 15) & ~uint64_t(15);  // 16-B aligned slots keep the fast path
-		}
+		small.push_back(r);
+		smallIdx.push_back(i);
+		lo = r.srcOffset < lo ? r.srcOffset : lo;
+		hi = r.srcOffset + r.bytes > hi ? r.srcOffset + r.bytes : hi;
+		sum += r.bytes;
 	}
 	if(small.empty())
 		return CADR_OK;
-	size_t numUnits = countUnits(small.data(), uint32_t(small.size()));
-	size_t unitBytes = (numUnits * sizeof(CopyUnit) + 255) & ~size_t(255);
+	const size_t numUnits = countUnits(small.data(), uint32_t(small.size()));
+	const size_t unitBytes = (numUnits * sizeof(CopyUnit) + 255) & ~size_t(255);
 	CADR_CUDA(cudaEventSynchronize(ctx->hostScratchFree));
-	if(int r = ctx->ensureHostScratch(unitBytes + packedBytes)) return r;
 	if(int r = ctx->ensureDevScratch(unitBytes)) return r;
+
+	lo &= ~uint64_t(15);                                   // keep 16-byte phase: the scatter kernel's fast path
+	const uint64_t span = hi - lo;
+	if(sum * 2 >= span) {
+		// dense: one DMA of the span, regions keep their relative positions
+		if(int r = ctx->ensureHostScratch(unitBytes)) return r;
+		if(int r = ctx->ensureDevMirror(span)) return r;
+		for(auto& q : small) q.srcOffset -= lo;
+		fillUnits(static_cast<CopyUnit*>(ctx->hostScratch), small.data(), uint32_t(small.size()), reinterpret_cast<uint64_t>(ctx->devMirror));
+		CADR_CUDA(cudaMemcpyAsync(ctx->devMirror, base + lo, span, cudaMemcpyHostToDevice, s));
+		return shipUnitsAndLaunch(ctx, numUnits, s);
+	}
+	// sparse: pack on the host (16-B aligned slots keep the fast path)
+	size_t packedBytes = 0;
+	for(auto& q : small) { uint64_t b = q.bytes; q.srcOffset = packedBytes; packedBytes += (b + 15) & ~uint64_t(15); }
+	if(int r = ctx->ensureHostScratch(unitBytes + packedBytes)) return r;
 	if(int r = ctx->ensureDevMirror(packedBytes)) return r;
 	fillUnits(static_cast<CopyUnit*>(ctx->hostScratch), small.data(), uint32_t(small.size()), reinterpret_cast<uint64_t>(ctx->devMirror));
 	uint8_t* pack = static_cast<uint8_t*>(ctx->hostScratch) + unitBytes;

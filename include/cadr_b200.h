@@ -249,9 +249,10 @@ CADR_API int  cadr_b200_memset(cadr_ctx* ctx, uint64_t dstAddr, int value, size_
 /* ---- upload path -------------------------------------------------------------------------------- */
 
 /* DataMemory::recordUploads (src/CadR/DataMemory.cpp:400-446): copy `n` regions from the host staging
- * block `stagingBase` to device addresses.  Regions at or above CADR_UPLOAD_DMA_THRESHOLD bytes go out
- * as individual async DMA copies (what vkCmdCopyBuffer does); smaller ones are packed into one DMA to
- * a device mirror followed by ONE scatter-copy kernel launch.  `stagingBase` may be NULL: srcOffset is then an
+ * block `stagingBase` to device addresses.  Regions of 1 MiB or more go out as individual async DMA
+ * copies (what vkCmdCopyBuffer does); the others travel with ONE DMA (the span they cover in the staging
+ * block when they are dense in it, else a host-packed copy) into a device mirror and are placed by ONE
+ * scatter-copy kernel launch.  `stagingBase` may be NULL: srcOffset is then an
  * absolute host address (regions that live in different staging blocks go out in one call). */
 CADR_API int  cadr_b200_upload(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n,
                                const void* stagingBase, cadr_stream stream);

@@ -184,6 +184,14 @@ def test_upload_scatter_and_patch(ctx):
         ob.upload(ob.Memory([(arena, host2)]), regions, staging[::-1].copy())
         assert np.array_equal(got, host2)
         ctx.arena_free(stage_dev)
+        # sparse sources (host-packed path) and a region above 1 MiB (its own DMA) in one call
+        big = rng.integers(0, 256, 24 << 20, dtype=np.uint8)
+        sparse = np.array([[arena + 4096 * i, (1 << 20) * i + 16 * i, 700 + i] for i in range(20)] +
+                          [[arena + (1 << 20), 5 << 20, (1 << 20) + 12345]], np.uint64)
+        ctx.upload(sparse, big)
+        ctx.memcpy_d2h(got, arena); ctx.sync()
+        ob.upload(ob.Memory([(arena, host2)]), sparse, big)
+        assert np.array_equal(got, host2)
     finally:
         ctx.arena_free(arena)
 
