@@ -143,6 +143,62 @@ __device__ __forceinline__ int evalInstance(const Mat& m, const LodInfo& L, cons
 	return visible ? lod : -1;
 }
 
+// Two instances at once with Blackwell's packed fp32 pipe (FFMA2 / FADD2 / FMUL2, sm_100): every component of a
+// packed operation is the same IEEE-754 operation evalInstance() performs, so results are bit-identical; the FP
+// instruction count per instance halves.  Used by the large-list kernel, where each lane owns two instances.
+__device__ __forceinline__ void evalInstancePair(const Mat& a, const Mat& b, const LodInfo& L, const float4 (&plane)[6],
+                                                 const float4& eye, int& lodA, int& lodB, bool& nearA, bool& nearB)
+{
+#define CADR_P2(u, v) make_float2((u), (v))
+#define CADR_D2(u) make_float2((u), (u))
+	const float4 sp = L.sphere;
+	const float2 bx = CADR_D2(sp.x), by = CADR_D2(sp.y), bz = CADR_D2(sp.z);
+	const float2 cx = __ffma2_rn(CADR_P2(a.c2.x, b.c2.x), bz, __ffma2_rn(CADR_P2(a.c1.x, b.c1.x), by, __ffma2_rn(CADR_P2(a.c0.x, b.c0.x), bx, CADR_P2(a.c3.x, b.c3.x))));
+	const float2 cy = __ffma2_rn(CADR_P2(a.c2.y, b.c2.y), bz, __ffma2_rn(CADR_P2(a.c1.y, b.c1.y), by, __ffma2_rn(CADR_P2(a.c0.y, b.c0.y), bx, CADR_P2(a.c3.y, b.c3.y))));
+	const float2 cz = __ffma2_rn(CADR_P2(a.c2.z, b.c2.z), bz, __ffma2_rn(CADR_P2(a.c1.z, b.c1.z), by, __ffma2_rn(CADR_P2(a.c0.z, b.c0.z), bx, CADR_P2(a.c3.z, b.c3.z))));
+	auto sq = [](float ax, float ay, float az, float bx_, float by_, float bz_) {
+		const float2 x = CADR_P2(ax, bx_), y = CADR_P2(ay, by_), z = CADR_P2(az, bz_);
+		return __ffma2_rn(z, z, __ffma2_rn(y, y, __fmul2_rn(x, x)));
+	};
+	const float2 s0 = sq(a.c0.x, a.c0.y, a.c0.z, b.c0.x, b.c0.y, b.c0.z);
+	const float2 s1 = sq(a.c1.x, a.c1.y, a.c1.z, b.c1.x, b.c1.y, b.c1.z);
+	const float2 s2 = sq(a.c2.x, a.c2.y, a.c2.z, b.c2.x, b.c2.y, b.c2.z);
+	const float sA01 = (s0.x < s1.x) ? s1.x : s0.x, sA = (sA01 < s2.x) ? s2.x : sA01;
+	const float sB01 = (s0.y < s1.y) ? s1.y : s0.y, sB = (sB01 < s2.y) ? s2.y : sB01;
+	const float2 r = __fmul2_rn(CADR_P2(__fsqrt_rn(sA), __fsqrt_rn(sB)), CADR_D2(sp.w));
+
+	const bool nonEmpty = sp.w >= 0.f;
+	bool visA = nonEmpty, visB = nonEmpty, npA = false, npB = false;
+#pragma unroll
+	for(int k = 0; k < 6; k++) {
+		const float2 dot = __ffma2_rn(CADR_D2(plane[k].z), cz, __ffma2_rn(CADR_D2(plane[k].y), cy, __ffma2_rn(CADR_D2(plane[k].x), cx, CADR_D2(plane[k].w))));
+		const float2 t = __fadd2_rn(dot, r);
+		visA = visA && (dot.x >= -r.x); visB = visB && (dot.y >= -r.y);
+		npA = npA || (fabsf(t.x) < 1e-5f); npB = npB || (fabsf(t.y) < 1e-5f);
+	}
+	const float2 dx = __fadd2_rn(cx, CADR_D2(-eye.x)), dy = __fadd2_rn(cy, CADR_D2(-eye.y)), dz = __fadd2_rn(cz, CADR_D2(-eye.z));
+	const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+	const float distA = __fsqrt_rn(d2.x), distB = __fsqrt_rn(d2.y);
+	int la = 0, lb = 0;
+	bool ntA = false, ntB = false;
+	if(L.lodCount > 1) {
+		la += (L.thr0 <= distA) ? 1 : 0; lb += (L.thr0 <= distB) ? 1 : 0;
+		const float2 e = __fadd2_rn(CADR_P2(distA, distB), CADR_D2(-L.thr0));
+		ntA = ntA || (fabsf(e.x) < 1e-5f); ntB = ntB || (fabsf(e.y) < 1e-5f);
+	}
+	if(L.lodCount > 2) {
+		la += (L.thr1 <= distA) ? 1 : 0; lb += (L.thr1 <= distB) ? 1 : 0;
+		const float2 e = __fadd2_rn(CADR_P2(distA, distB), CADR_D2(-L.thr1));
+		ntA = ntA || (fabsf(e.x) < 1e-5f); ntB = ntB || (fabsf(e.y) < 1e-5f);
+	}
+	nearA = nonEmpty && (npA || (visA && ntA));
+	nearB = nonEmpty && (npB || (visB && ntB));
+	lodA = visA ? la : -1;
+	lodB = visB ? lb : -1;
+#undef CADR_P2
+#undef CADR_D2
+}
+
 __device__ __forceinline__ LodInfo unpackLod(uint4 a, uint4 b, uint4 c, uint32_t (&psOff)[3], uint32_t& stateSet)
 {
 	LodInfo L;
@@ -544,14 +600,15 @@ cullLargeKernel(const __grid_constant__ CullArgs A)
 		const uint32_t jw = warp * TP_PER_WARP + lane;
 		// branch-free evaluation of both batches (index clamped, result masked) so that the two independent
 		// instruction streams interleave; a tail item re-evaluates its last matrix in the idle lanes
-#pragma unroll
-		for(int b = 0; b < TP_BATCHES; b++) {
-			const uint32_t jj = jw + b * 32;
-			Mat m = loadMatSmem(st.mats, min(jj, cnt - 1u), lane);
-			bool nb;
-			int l = evalInstance(m, L, A.plane, A.eye, nb);
-			lod[b] = (jj < cnt) ? l : -1;
-			nbv[b] = nb && (jj < cnt);
+		static_assert(TP_BATCHES == 2, "the packed evaluation pairs the lane's two instances");
+		{
+			const Mat m0 = loadMatSmem(st.mats, min(jw, cnt - 1u), lane);
+			const Mat m1 = loadMatSmem(st.mats, min(jw + 32u, cnt - 1u), lane);
+			int l0, l1;
+			bool n0, n1;
+			evalInstancePair(m0, m1, L, A.plane, A.eye, l0, l1, n0, n1);
+			lod[0] = (jw < cnt) ? l0 : -1;        nbv[0] = n0 && (jw < cnt);
+			lod[1] = (jw + 32u < cnt) ? l1 : -1;  nbv[1] = n1 && (jw + 32u < cnt);
 		}
 #pragma unroll
 		for(int b = 0; b < TP_BATCHES; b++) {
