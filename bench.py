@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--workload", default="c3", choices=["c3", "c2"])
     ap.add_argument("--drawables", type=int, default=0, help="override the drawable count (debug)")
     ap.add_argument("--instances", type=int, default=1000, help="matrices per list for c3")
+    ap.add_argument("--state-sets", type=int, default=64, help="StateSets for c3 (debug: 1 makes drawable order == list order)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="two calls (process_drawables, cull_compact) instead of process_and_cull")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
@@ -62,7 +63,7 @@ def parse_args():
 def make_scene(args, rank: int, host_matrices: bool, drawables: int | None = None) -> synth.Scene:
     if args.workload == "c3":
         n = drawables or args.drawables or 100_000
-        return synth.config3(n, args.instances, state_sets=64, seed=0xC0FFEE03 + rank, host_matrices=host_matrices)
+        return synth.config3(n, args.instances, state_sets=args.state_sets, seed=0xC0FFEE03 + rank, host_matrices=host_matrices)
     n = drawables or args.drawables or 10_000_000
     return synth.config2(n, seed=0xC0FFEE02 + rank, host_matrices=host_matrices)
 
