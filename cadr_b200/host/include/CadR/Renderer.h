@@ -79,6 +79,11 @@ class Renderer {
 	bool _collectFrameInfo = false;
 	FrameInfo _inProgress, _completed;
 	uint64_t _countsEpoch = 0;
+	// device-resident drawable list: only ranges whose records changed since they were last copied are
+	// written to the staging list and DMA'd; the reference re-copies the whole list every frame (Renderer.cpp:635-644)
+	bool _incrementalList = true, _residentValid = false;
+	std::vector<std::pair<size_t, size_t>> _dirtyRanges;   // [first, count) in drawables
+	size_t _lastListUploadBytes = 0;
 	static Renderer* _defaultRenderer;
 	void freeDrawableBuffers() noexcept;
 	void ensureCullBuffers();
@@ -114,6 +119,9 @@ public:
 	void notifyInstanceCountsChanged() noexcept { _countsEpoch++; }   ///< drawables / matrix-list sizes / LOD tables changed
 	uint64_t countsEpoch() const { return _countsEpoch; }
 	bool hasDevice() const;
+	/// Off: copy the whole flattened list every frame exactly like the reference.  On (default): copy what changed.
+	void setIncrementalDrawableUpload(bool on) { _incrementalList = on; _residentValid = false; }
+	size_t lastDrawableUploadBytes() const { return _lastListUploadBytes; }   ///< list + culling records DMA'd by the last submit()
 	cadr_ctx* context() const { return _ctx; }
 	void* stream() const { return _stream; }
 	size_t frameNumber() const noexcept { return _frameNumber; }

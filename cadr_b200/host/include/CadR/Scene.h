@@ -186,6 +186,12 @@ class StateSet {                  // src/CadR/StateSet.{h,cpp} (Vulkan pipeline/
 	// worst-case output sizes of the culling extension for this StateSet, recomputed when instance counts change
 	uint64_t _totalsEpoch = ~0ull, _instanceTotal = 0, _commandTotal = 0, _chunkTotal = 0;
 	void updateCullTotals();
+	// device-resident drawable list: where this StateSet's records were placed the last time they were copied
+	// (one entry per recording of the StateSet in a frame: a StateSet with several parents is recorded several times)
+	uint64_t _modCount = 0;                  ///< bumped whenever _drawableDataList / _drawableCullList change
+	struct Placement { size_t first; uint32_t range; uint64_t modCount; };
+	std::vector<Placement> _placements;
+	size_t _placementFrame = ~size_t(0), _placementCursor = 0;
 	void appendDrawableInternal(Drawable& d, const DrawableGpuData& gpuData);
 	void removeDrawableInternal(Drawable& d) noexcept;
 public:

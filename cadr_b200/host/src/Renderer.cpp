@@ -107,6 +107,7 @@ size_t Renderer::prepareSceneRendering(StateSet& stateSetRoot)
 		check(cadr_b200_host_alloc(_ctx, n * sizeof(DrawableCullData), &p));
 		_cullStagingData = static_cast<DrawableCullData*>(p);
 		_drawableCapacity = n;
+		_residentValid = false;      // new buffers: nothing is resident
 	}
 	return numDrawables;
 }
@@ -140,12 +141,23 @@ void Renderer::recordStateSetRange(StateSet& ss, size_t first)
 {
 	const size_t n = ss._drawableDataList.size();
 	if(first + n > _drawableCapacity) throw LogicError("CadR::Renderer: more drawables recorded than prepareSceneRendering() counted");
-	// copy the StateSet's records into the staging list (StateSet.cpp:233-237)
-	std::memcpy(&_drawableStagingData[first], ss._drawableDataList.data(), n * sizeof(DrawableGpuData));
 	const uint32_t rangeIndex = uint32_t(_drawRanges.size());
-	DrawableCullData* c = &_cullStagingData[first];
-	std::memcpy(c, ss._drawableCullList.data(), n * sizeof(DrawableCullData));
-	for(size_t i = 0; i < n; i++) c[i].stateSetIndex = rangeIndex;
+	// was exactly this content copied to exactly this place before?  (k-th recording of the StateSet in the frame)
+	if(ss._placementFrame != _frameNumber) { ss._placementFrame = _frameNumber; ss._placementCursor = 0; }
+	const size_t k = ss._placementCursor++;
+	if(ss._placements.size() <= k) ss._placements.resize(k + 1, StateSet::Placement{~size_t(0), ~0u, ~0ull});
+	StateSet::Placement& pl = ss._placements[k];
+	const bool resident = _incrementalList && _residentValid && pl.first == first && pl.range == rangeIndex && pl.modCount == ss._modCount;
+	if(!resident) {
+		// copy the StateSet's records into the staging list (StateSet.cpp:233-237)
+		std::memcpy(&_drawableStagingData[first], ss._drawableDataList.data(), n * sizeof(DrawableGpuData));
+		DrawableCullData* c = &_cullStagingData[first];
+		std::memcpy(c, ss._drawableCullList.data(), n * sizeof(DrawableCullData));
+		for(size_t i = 0; i < n; i++) c[i].stateSetIndex = rangeIndex;
+		if(!_dirtyRanges.empty() && _dirtyRanges.back().first + _dirtyRanges.back().second == first) _dirtyRanges.back().second += n;
+		else _dirtyRanges.emplace_back(first, n);
+		pl = StateSet::Placement{first, rangeIndex, ss._modCount};
+	}
 	_drawRanges.push_back(DrawRange{&ss, first, n, _drawablePointersBufferAddress + first * drawablePointersRecordSize,
 	                                first * sizeof(cadr_indirect_data)});
 	ss.updateCullTotals();
@@ -222,19 +234,31 @@ void Renderer::submit()
 	if(!_processingRecorded) return;
 	if(!hasDevice()) throw DeviceError("CadR::Renderer::submit(): this renderer has no CUDA device; there is no CPU fallback");
 	if(_collectFrameInfo) cadr_b200_set_profiling(_ctx, 1);
+	// staging -> device copy of the flattened list (Renderer.cpp:635-644) — only the ranges that changed since they
+	// were last copied; with incremental upload off, recordStateSetRange marked every range dirty
+	_lastListUploadBytes = 0;
+	for(auto& [first, count] : _dirtyRanges) {
+		check(cadr_b200_memcpy_h2d(_ctx, _drawableBufferAddress + first * sizeof(DrawableGpuData), &_drawableStagingData[first],
+		                           count * sizeof(DrawableGpuData), _stream));
+		_lastListUploadBytes += count * sizeof(DrawableGpuData);
+		if(_cullingRecorded) {
+			check(cadr_b200_memcpy_h2d(_ctx, _cullDataBufferAddress + first * sizeof(DrawableCullData), &_cullStagingData[first],
+			                           count * sizeof(DrawableCullData), _stream));
+			_lastListUploadBytes += count * sizeof(DrawableCullData);
+		}
+	}
+	_dirtyRanges.clear();
+	_residentValid = _cullingRecorded;   // kept simple: residency is tracked across frames that upload both arrays
 	if(!_cullingRecorded) {
-		// staging -> device copy of the flattened list, then the processing kernel (Renderer.cpp:635-692)
-		check(cadr_b200_record_drawable_processing(_ctx, reinterpret_cast<const cadr_drawable_gpu_data*>(_drawableStagingData),
-		                                           _dataStorage->handleTableDeviceAddress(), _dataStorage->handleLevel(),
-		                                           _drawableBufferAddress, _drawIndirectBufferAddress, _drawablePointersBufferAddress,
-		                                           _recordedDrawables, _stream));
+		// the processing kernel (Renderer.cpp:669-692)
+		check(cadr_b200_process_drawables(_ctx, _dataStorage->handleTableDeviceAddress(), _dataStorage->handleLevel(),
+		                                  _drawableBufferAddress, _drawIndirectBufferAddress, _drawablePointersBufferAddress,
+		                                  _recordedDrawables, _stream));
 	}
 	if(_cullingRecorded) {
 		// culling recorded: the same DMA, then ONE pass that resolves handles, writes the indirect / pointers
 		// records (identical to the processing kernel's) and culls
 		ensureCullBuffers();
-		check(cadr_b200_memcpy_h2d(_ctx, _drawableBufferAddress, _drawableStagingData, _recordedDrawables * sizeof(DrawableGpuData), _stream));
-		check(cadr_b200_memcpy_h2d(_ctx, _cullDataBufferAddress, _cullStagingData, _recordedDrawables * sizeof(DrawableCullData), _stream));
 		check(cadr_b200_memcpy_h2d(_ctx, _cullRegionsAddress, _cull.regions.data(), _cull.regions.size() * sizeof(cadr_stateset_region), _stream));
 		cadr_cull_params p{};
 		p.handleTableRoot = _dataStorage->handleTableDeviceAddress();

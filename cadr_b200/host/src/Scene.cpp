@@ -120,6 +120,7 @@ void Drawable::create(Geometry& geometry, uint32_t primitiveSetOffset, MatrixLis
 		if(_stateSet == &stateSet) {
 			_stateSet->_drawableDataList[_indexIntoStateSet] = gpuData;
 			_stateSet->_drawableCullList[_indexIntoStateSet].lodPrimitiveSetOffset[0] = primitiveSetOffset;
+			_stateSet->_modCount++;
 			_stateSet->renderer().notifyInstanceCountsChanged();
 			return;
 		}
@@ -141,6 +142,7 @@ void Drawable::setCullData(const BoundingSphere& bs, uint32_t lodCount, const ui
 		c.lodPrimitiveSetOffset[l] = lodPrimitiveSetOffsets ? lodPrimitiveSetOffsets[l] : _stateSet->_drawableDataList[_indexIntoStateSet].primitiveSetOffset;
 	for(uint32_t l = 0; l + 1 < lodCount; l++)
 		c.lodThreshold[l] = lodThresholds ? lodThresholds[l] : 0.f;
+	_stateSet->_modCount++;
 	_stateSet->renderer().notifyInstanceCountsChanged();
 }
 
@@ -191,6 +193,7 @@ void StateSet::appendDrawableInternal(Drawable& d, const DrawableGpuData& gpuDat
 	c.lodPrimitiveSetOffset[0] = gpuData.primitiveSetOffset;
 	_drawableCullList.push_back(c);
 	_drawablePtrList.emplace_back(&d);
+	_modCount++;
 	_renderer->notifyInstanceCountsChanged();
 }
 
@@ -209,6 +212,7 @@ void StateSet::removeDrawableInternal(Drawable& d) noexcept
 	_drawableDataList.pop_back();
 	_drawableCullList.pop_back();
 	_drawablePtrList.pop_back();
+	_modCount++;
 	_renderer->notifyInstanceCountsChanged();
 }
 
@@ -231,6 +235,7 @@ void StateSet::removeAllDrawables() noexcept
 	_drawableDataList.clear();
 	_drawableCullList.clear();
 	_drawablePtrList.clear();
+	_modCount++;
 	_renderer->notifyInstanceCountsChanged();
 }
 

@@ -213,9 +213,10 @@ int main(int argc, char** argv)
 				}
 				if(instCap) { r.readDevice(big2.data(), c.instances, instCap * 4); putBytes(big2.data(), instCap * 4); }
 			}
-			fprintf(stderr, "frame %d: %zu drawables, %zu ranges, handle level %u (%llu handles), %zu DataMemory, staging in use %zu / pooled %zu\n",
+			fprintf(stderr, "frame %d: %zu drawables, %zu ranges, handle level %u (%llu handles), %zu DataMemory, staging in use %zu / pooled %zu, list upload %zu bytes\n",
 			        frame, n, ranges.size(), r.dataStorage().handleLevel(), (unsigned long long)r.dataStorage().handleTable().highestHandle(),
-			        r.dataStorage().dataMemoryList().size(), r.stagingManager().numBlocksInUse(), r.stagingManager().numBlocksAvailable());
+			        r.dataStorage().dataMemoryList().size(), r.stagingManager().numBlocksInUse(), r.stagingManager().numBlocksAvailable(),
+			        r.lastDrawableUploadBytes());
 		}
 		drawables.clear();
 	}

@@ -32,7 +32,17 @@ def gpu_frames(tmp_path_factory):
     assert r.returncode == 0, r.stderr
     frames = parse(out)
     os.remove(out)
+    for f, line in zip(frames, [l for l in r.stderr.splitlines() if l.startswith("frame ")]):
+        f["list_upload_bytes"] = int(line.split("list upload ")[1].split()[0])
     return frames
+
+
+def test_facade_uploads_only_changed_drawable_ranges(gpu_frames):
+    """Device-resident drawable list: frame 0 copies everything, a frame that only rewrites transforms
+    copies nothing — and the results above are identical either way."""
+    assert gpu_frames[0]["list_upload_bytes"] == gpu_frames[0]["n"] * 96     # 48 B record + 48 B culling record
+    assert gpu_frames[4]["list_upload_bytes"] == 0                           # frame 4 only rewrites a MatrixList
+    assert 0 < gpu_frames[2]["list_upload_bytes"] <= gpu_frames[2]["n"] * 96
 
 
 def test_facade_frames_on_gpu_match_oracle(gpu_frames):
