@@ -31,6 +31,7 @@ struct cadr_ctx {
 	cudaStream_t stream = nullptr;
 	uint64_t launches = 0;
 	bool profiling = false;
+	bool largeKernelConfigured = false;   // dynamic shared-memory opt-in of cullLargeKernel done on this device
 	cudaEvent_t evBegin[cadr::KS_COUNT] = {};
 	cudaEvent_t evEnd[cadr::KS_COUNT] = {};
 	bool evUsed[cadr::KS_COUNT] = {};

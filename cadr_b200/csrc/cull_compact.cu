@@ -77,6 +77,8 @@ struct CullArgs {
 	WorkItem* items;
 	uint32_t  chunkCapacity;
 	uint32_t  n;
+	uint32_t  numStateSets;
+	uint32_t  pad0;
 	float4 plane[6];
 	float4 eye;
 	// fused multi-GPU exchange: gathered arrays of every rank (peer mappings), 0 ranks = write cmdOut/ptrOut/tagOut
@@ -299,11 +301,6 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 		if(valid) N = ldg_stream_u4(A.indirect + d).y;  // IndirectData.instanceCount == ml.numMatrices
 	}
 
-	// ---- number of work items this drawable needs in the large-list queue --------------------------
-	uint32_t nChunks = (N > SMALL_MAX) ? (N + CHUNK - 1) / CHUNK : 0;
-	uint32_t chunkIncl = warpInclusiveScan(nChunks, lane);
-	if(lane == 31) sChunkTot[warp] = chunkIncl;
-
 	// ---- per-drawable records (needed by both paths) -------------------------------------------------
 	uint32_t psOff[3] = {0, 0, 0};
 	uint32_t stateSet = 0xffffffffu;
@@ -317,8 +314,18 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 			p1 = ldg_stream_u4(A.pointers + 2ull * d + 1);
 		}
 		L = unpackLod(ca, cb, cc, psOff, stateSet);
+		if(stateSet >= A.numStateSets) {
+			// a culling record that points outside the region table: report it and leave the drawable out
+			atomicOr(&A.hdr->status, CADR_CULL_STATUS_BAD_RANGE_INDEX);
+			N = 0;
+		}
 	}
 	const uint64_t matrixList = uint64_t(p1.x) | (uint64_t(p1.y) << 32);
+
+	// ---- number of work items this drawable needs in the large-list queue --------------------------
+	uint32_t nChunks = (N > SMALL_MAX) ? (N + CHUNK - 1) / CHUNK : 0;
+	uint32_t chunkIncl = warpInclusiveScan(nChunks, lane);
+	if(lane == 31) sChunkTot[warp] = chunkIncl;
 
 	// ---- evaluate short lists ------------------------------------------------------------------------
 	const bool small = valid && N > 0 && N <= SMALL_MAX;
@@ -860,6 +867,8 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 	A.items = reinterpret_cast<WorkItem*>(p.chunkWorkspace);
 	A.chunkCapacity = p.chunkCapacity;
 	A.n = p.numDrawables;
+	A.numStateSets = p.numStateSets;
+	A.pad0 = 0;
 	for(int k = 0; k < 6; k++) A.plane[k] = make_float4(p.planes[k][0], p.planes[k][1], p.planes[k][2], p.planes[k][3]);
 	A.eye = make_float4(p.eye[0], p.eye[1], p.eye[2], 0.f);
 	A.xWorld = exchange ? p.exchangeWorld : 0;
@@ -899,10 +908,9 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 			cullLargeLdgKernel<<<gridL, CL_THREADS, 0, s>>>(A);
 		}
 		else {
-			static bool attrSet = false;
-			if(!attrSet) {
+			if(!ctx->largeKernelConfigured) {   // per device (a process may hold one context per GPU)
 				CADR_CUDA(cudaFuncSetAttribute(cullLargeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TP_SMEM_BYTES)));
-				attrSet = true;
+				ctx->largeKernelConfigured = true;
 			}
 			uint32_t gridL = uint32_t(ctx->smCount);       // persistent: one CTA per SM (215 KB of shared memory each)
 			if(gridL > p.chunkCapacity) gridL = p.chunkCapacity;

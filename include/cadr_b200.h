@@ -126,7 +126,7 @@ typedef struct cadr_command_tag { uint32_t drawableIndex, lod; } cadr_command_ta
  *                  of vkCmdDrawIndexedIndirectCount),
  *   high 32 bits = number of instance indices emitted for the StateSet. */
 typedef struct cadr_cull_header {
-	uint32_t status;          /* bit 0: a region overflowed, bit 1: chunk workspace overflowed       */
+	uint32_t status;          /* bit 0: a region overflowed, bit 1: chunk workspace overflowed, bit 2: bad range index */
 	uint32_t nearBandCount;   /* instances within 1e-5 of a frustum plane or LOD threshold           */
 	uint32_t chunkCount;      /* internal: work items queued for the large-list kernel               */
 	uint32_t chunkCursor;     /* internal: work items taken                                          */
@@ -135,6 +135,7 @@ typedef struct cadr_cull_header {
 } cadr_cull_header;           /* 64 B */
 #define CADR_CULL_STATUS_REGION_OVERFLOW 1u
 #define CADR_CULL_STATUS_CHUNK_OVERFLOW  2u
+#define CADR_CULL_STATUS_BAD_RANGE_INDEX 4u     /* a culling record's stateSetIndex >= numStateSets: drawable skipped */
 #define CADR_CULL_WORK_ITEM_BYTES        128u   /* one self-contained descriptor per <= 1024 matrices */
 #define CADR_CULL_SMALL_LIST_MAX         32u    /* lists up to this size are evaluated by one thread  */
 #define CADR_CULL_WORK_ITEM_INSTANCES    1024u

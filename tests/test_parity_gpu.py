@@ -152,6 +152,32 @@ def test_tier_x_region_overflow_is_reported(ctx):
         ds.close()
 
 
+def test_tier_x_bad_range_index_is_reported_not_followed(ctx):
+    sc = synth.random_scene(23, n=400, num_lists=40)
+    sc.cull = sc.cull.copy()
+    bad = np.arange(0, sc.n, 7)
+    sc.cull[bad, 10] = 0x7FFFFFF0                      # far outside the region table
+    planes, eye = synth.orbit_camera(5, 250.0, far=500.0)
+    ds = DeviceScene(ctx, sc)
+    try:
+        ds.record_drawable_processing()
+        ds.cull(planes, eye); ctx.sync(ds.stream)
+        got = ds.read_tier_x()
+        assert got["status"] == 4
+        # everything else is processed as if the bad drawables had empty lists
+        ok = synth.random_scene(23, n=400, num_lists=40)
+        ok.ml_count = ok.ml_count.copy()
+        keep = np.ones(sc.n, bool); keep[bad] = False
+        emitted = np.unique(got["tag"][np.concatenate([np.arange(int(sc.regions[s, 0]), int(sc.regions[s, 0]) + int(got["cmd_count"][s]))
+                                                       for s in range(sc.num_state_sets)]).astype(int), 0]) if got["cmd_count"].sum() else np.array([])
+        assert not np.intersect1d(emitted, bad).size
+        _, _, ref = oracle_tier_x(ok, planes, eye, arena_base=ds.arena, list_base=ds.drawable_list)
+        ref_keep = sum(len(e[6]) for lst in canonicalise(ref).values() for e in lst if keep[e[0]])
+        assert int(got["inst_count"].sum()) == ref_keep
+    finally:
+        ds.close()
+
+
 def test_upload_scatter_and_patch(ctx):
     rng = np.random.default_rng(9)
     size = 3 << 20
