@@ -44,8 +44,8 @@ from cadr_b200 import synth  # noqa: E402
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c2"])
     ap.add_argument("--drawables", type=int, default=0, help="override the drawable count (debug)")
@@ -320,6 +320,12 @@ def run_b200(args):
             stream_t.synchronize()
             ktimes.append(ctx.kernel_times())
             surv.append(int(ds.read_counters()["inst_count"].sum()))
+        # Tier R on its own (what the reference's shader computes): the processing kernel over the same drawable list
+        tier_r = []
+        for k in range(10):
+            ds.process_drawables()
+            stream_t.synchronize()
+            tier_r.append(ctx.kernel_times()[0])
         ctx.set_profiling(False)
 
     kt = np.array(ktimes)
@@ -362,6 +368,10 @@ def run_b200(args):
                      "frac": round(achieved / peak, 4), "traffic": recorded_traffic(dom_name), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(alg_bytes), "algorithmic_bytes": alg_note, "launch_ms": round(dom_ms, 4)},
         "clocks": clocks,
+        "tier_r": {"kernel": "processDrawablesKernel", "drawables": scene.n, "launch_ms": round(float(np.median(tier_r[2:])), 4),
+                   "value": round(scene.n / (float(np.median(tier_r[2:])) * 1e-3) / 1e6, 1), "unit": "M drawables/s",
+                   "algorithmic_bytes_per_drawable": 140 if args.workload == "c3" else 108,
+                   "frac": round((140 if args.workload == "c3" else 108) * scene.n / (float(np.median(tier_r[2:])) * 1e-3) / 1e9 / peak, 4)},
     }
     if world > 1:
         line["cull_only"] = {"value": round(total_inst * args.steps / (ms_cull_only * 1e-3) / 1e6, 1), "unit": "M instances/s",
