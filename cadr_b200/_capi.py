@@ -134,6 +134,8 @@ SYMBOLS = {
     "cadr_b200_ipc_close": (C.c_int, [_P, C.c_uint64]),
     "cadr_b200_exchange_publish": (C.c_int, [_P, C.POINTER(ExchangeSync), _P]),
     "cadr_b200_exchange_wait": (C.c_int, [_P, C.POINTER(ExchangeSync), _P]),
+    "cadr_b200_consume_check": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
+    "cadr_b200_consume_check_culled": (C.c_int, [_P, C.POINTER(CullParams), C.c_uint32, C.c_uint32, C.c_uint64, _P]),
     "cadr_b200_cull_counters_bytes": (C.c_size_t, [C.c_uint32]),
     "cadr_b200_set_profiling": (C.c_int, [_P, C.c_int]),
     "cadr_b200_kernel_times": (C.c_int, [_P, C.POINTER(C.c_float), C.c_uint32]),
@@ -280,6 +282,13 @@ class Context:
 
     def process_and_cull(self, params: CullParams, stream: int = 0) -> None:
         check(self._l.cadr_b200_process_and_cull(self._h, C.byref(params), _P(stream)))
+
+    # -- consumer-side contract check
+    def consume_check(self, indirect: int, pointers: int, first: int, n: int, digest_out: int, stream: int = 0) -> None:
+        check(self._l.cadr_b200_consume_check(self._h, indirect, pointers, first, n, digest_out, _P(stream)))
+
+    def consume_check_culled(self, params: "CullParams", rng: int, max_commands: int, digest_out: int, stream: int = 0) -> None:
+        check(self._l.cadr_b200_consume_check_culled(self._h, C.byref(params), rng, max_commands, digest_out, _P(stream)))
 
     # -- multi-GPU plumbing
     def ipc_export(self, addr: int) -> bytes:

@@ -508,13 +508,22 @@ def config1(boxes_per_side: int = 100, seed: int = 1) -> Scene:
 
 def random_scene(seed: int, n: int = 300, num_geometries: int = 7, num_lists: int = 50, max_count: int = 70,
                  state_sets: int = 5, first_handle: int = 1, force_level: int = 0, big_lists: int = 0,
-                 with_drawable_data: bool = True, cube: float = 400.0) -> Scene:
+                 with_drawable_data: bool = True, cube: float = 400.0, valid_geometry: bool = False) -> Scene:
     """Ragged scene for parity tests: empty lists, shared lists/geometries, 1-3 LODs, empty spheres, several
     primitive sets per geometry, optional per-drawable data, StateSets of uneven size."""
     rng = np.random.default_rng(seed)
     geos = []
     for g in range(num_geometries):
         P = int(rng.integers(1, 5))
+        if valid_geometry:
+            # real geometry for the consumer-side check: 12-byte positions, u32 indices < vertex count, primitive
+            # sets that stay inside the index array
+            V, I = int(rng.integers(3, 40)), int(rng.integers(6, 120))
+            first = rng.integers(0, I - 2, P)
+            count = np.array([int(rng.integers(1, min(40, I - f) + 1)) for f in first])
+            geos.append(dict(vertices=rng.random((V, 3), dtype=np.float32), indices=rng.integers(0, V, I).astype(np.uint32),
+                             primitive_sets=np.stack([count, first], axis=1).astype(np.uint32)))
+            continue
         geos.append(dict(vertices=rng.integers(0, 256, int(rng.integers(1, 200)), dtype=np.uint8),
                          indices=rng.integers(0, 256, int(rng.integers(1, 300)), dtype=np.uint8),
                          primitive_sets=rng.integers(0, 1 << 20, (P, 2), dtype=np.uint32)))

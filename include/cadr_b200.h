@@ -311,6 +311,22 @@ CADR_API int  cadr_b200_exchange_wait(cadr_ctx* ctx, const cadr_exchange_sync* s
 /* Size of the counters buffer for `numStateSets` StateSets. */
 CADR_API size_t cadr_b200_cull_counters_bytes(uint32_t numStateSets);
 
+/* ---- consumer-side contract check -------------------------------------------------------------- */
+
+/* Walk drawables [first, first+n) of the Tier R outputs like the reference's vertex shader
+ * (examples/RenderingPerformance/shader.vert:99-113): for every instance and vertex of every draw fetch
+ * indices[gl_VertexIndex], the 12-byte vertex it selects and matrices[gl_InstanceIndex], and fold them into
+ * digestOut[0] (order-independent 64-bit sum of hashes) and digestOut[1] (number of fetches).  digestOut: 16 bytes of
+ * device memory.  Geometry must be real (indices < vertex count). */
+CADR_API int  cadr_b200_consume_check(cadr_ctx* ctx, uint64_t indirectData, uint64_t drawablePointers, uint64_t firstDrawable,
+                                      uint64_t numDrawables, uint64_t digestOut, cadr_stream stream);
+/* The same for one draw range of a cadr_b200_cull_compact result, read the way vkCmdDrawIndexedIndirectCount would
+ * (count from the counters buffer, at most maxCommands draws; instance k of a command is matrix
+ * instOut[firstInstance + k]).  The digest is keyed by drawable index, so it does not depend on emission order or on
+ * how a long list was cut into commands. */
+CADR_API int  cadr_b200_consume_check_culled(cadr_ctx* ctx, const cadr_cull_params* params, uint32_t range, uint32_t maxCommands,
+                                             uint64_t digestOut, cadr_stream stream);
+
 /* ---- timing (FrameInfo timestamps, src/CadR/Renderer.cpp:436,660,696,778) ----------------------- */
 
 /* When enabled, process_drawables / cull_compact / upload bracket each kernel with CUDA events.

@@ -47,6 +47,11 @@ def lib() -> C.CDLL:
         l.oracle_upload.argtypes = [C.POINTER(Segment), C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
         l.oracle_patch_handles.restype = C.c_uint64
         l.oracle_patch_handles.argtypes = [C.POINTER(Segment), C.c_uint32, C.c_uint64, C.c_int, C.c_void_p, C.c_uint32]
+        l.oracle_consume_check.restype = C.c_uint64
+        l.oracle_consume_check.argtypes = [C.POINTER(Segment), C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        l.oracle_consume_check_culled.restype = C.c_uint64
+        l.oracle_consume_check_culled.argtypes = [C.POINTER(Segment), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                  C.c_uint32, C.c_uint32, C.c_void_p]
         l.oracle_max_threads.restype = C.c_int
         _lib = l
     return _lib
@@ -138,3 +143,28 @@ def patch_handles(mem: Memory, root: int, level: int, patches: np.ndarray) -> No
     faults = lib().oracle_patch_handles(mem.segs, mem.n, root, level, p.ctypes.data, p.shape[0])
     if faults:
         raise RuntimeError(f"oracle: {faults} handle patches outside the arena")
+
+
+def consume_check(mem: Memory, indirect: np.ndarray, pointers: np.ndarray, first: int, count: int) -> tuple[int, int]:
+    """Tier R consumer walk -> (digest, fetches)."""
+    ind = np.ascontiguousarray(indirect, dtype=np.uint32)
+    ptr = np.ascontiguousarray(pointers, dtype=np.uint64)
+    out = np.zeros(2, np.uint64)
+    faults = lib().oracle_consume_check(mem.segs, mem.n, ind.ctypes.data, ptr.ctypes.data, first, count, out.ctypes.data)
+    if faults:
+        raise RuntimeError(f"oracle: {faults} draws fetched outside device memory")
+    return int(out[0]), int(out[1])
+
+
+def consume_check_culled(mem: Memory, res: dict, rng: int) -> tuple[int, int]:
+    """Tier X consumer walk over draw range `rng` of a cull result -> (digest, fetches)."""
+    cmd = np.ascontiguousarray(res["cmd"], dtype=np.uint32)
+    ptr = np.ascontiguousarray(res["ptr"], dtype=np.uint64)
+    tag = np.ascontiguousarray(res["tag"], dtype=np.uint32)
+    inst = np.ascontiguousarray(res["inst"], dtype=np.uint32)
+    out = np.zeros(2, np.uint64)
+    faults = lib().oracle_consume_check_culled(mem.segs, mem.n, cmd.ctypes.data, ptr.ctypes.data, tag.ctypes.data, inst.ctypes.data,
+                                               int(res["regions"][rng, 0]), int(res["cmd_count"][rng]), out.ctypes.data)
+    if faults:
+        raise RuntimeError(f"oracle: {faults} commands fetched outside device memory")
+    return int(out[0]), int(out[1])

@@ -340,6 +340,79 @@ uint64_t oracle_patch_handles(const oracle_segment* segs, uint32_t numSegs, uint
 	return faults;
 }
 
+/* ------------------------------------------------------------------------------------------------------
+ * Consumer-side contract check: the fetches of the reference's vertex shader,
+ * /root/reference/examples/RenderingPerformance/shader.vert:99-113:
+ *   dp = DrawablePointers[gl_DrawID]; index = indexData.indices[gl_VertexIndex];
+ *   vertex = vertexData + index*12;   M = matrixList.matrices[gl_InstanceIndex]
+ * folded into an order-independent digest (sum of 64-bit hashes, number of fetches).
+ * ---------------------------------------------------------------------------------------------------- */
+static inline uint64_t mix64(uint64_t z)
+{
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+
+static inline uint64_t fetch_and_hash(const oracle_mem* m, uint64_t vd, uint64_t id, uint64_t ml, uint32_t drawKey,
+                                      uint32_t instance, uint32_t vertexIndex, int* fault)
+{
+	uint32_t index = load32(m, id + 4ull * vertexIndex, fault);
+	uint32_t p0 = load32(m, vd + 12ull * index, fault), p1 = load32(m, vd + 12ull * index + 4, fault), p2 = load32(m, vd + 12ull * index + 8, fault);
+	uint64_t mat = ml + 64ull + 64ull * instance;
+	uint32_t m0 = load32(m, mat, fault), m5 = load32(m, mat + 20, fault);
+	uint32_t m12 = load32(m, mat + 48, fault), m13 = load32(m, mat + 52, fault), m14 = load32(m, mat + 56, fault);
+	uint64_t h = mix64(((uint64_t)drawKey << 32 | instance) + 0x9E3779B97F4A7C15ull);
+	h = mix64(h ^ ((uint64_t)vertexIndex << 32 | index));
+	h = mix64(h ^ ((uint64_t)p0 | (uint64_t)p1 << 32));
+	h = mix64(h ^ ((uint64_t)p2 | (uint64_t)m12 << 32));
+	h = mix64(h ^ ((uint64_t)m13 | (uint64_t)m14 << 32));
+	return mix64(h ^ ((uint64_t)m0 | (uint64_t)m5 << 32));
+}
+
+/* Tier R: one vkCmdDrawIndirect per drawable.  out[0] = digest, out[1] = fetches; returns faults. */
+uint64_t oracle_consume_check(const oracle_segment* segs, uint32_t numSegs, const uint8_t* indirect, const uint8_t* pointers,
+                              uint32_t first, uint32_t count, uint64_t* out)
+{
+	oracle_mem m = { segs, numSegs };
+	uint64_t sum = 0, n = 0, faults = 0;
+	for(uint32_t i = first; i < first + count; i++) {
+		uint32_t cmd[4];  memcpy(cmd, indirect + (size_t)i * 16, 16);
+		uint64_t ptr[4];  memcpy(ptr, pointers + (size_t)i * 32, 32);
+		int fault = 0;
+		for(uint32_t j = 0; j < cmd[1]; j++)
+			for(uint32_t v = 0; v < cmd[0]; v++) {
+				sum += fetch_and_hash(&m, ptr[0], ptr[1], ptr[2], i, j + cmd[3], v + cmd[2], &fault);
+				n++;
+			}
+		faults += (uint64_t)fault;
+	}
+	out[0] = sum; out[1] = n;
+	return faults;
+}
+
+/* Tier X: commands [cmdFirst, cmdFirst + numCmds) of one draw range. */
+uint64_t oracle_consume_check_culled(const oracle_segment* segs, uint32_t numSegs, const uint8_t* cmdBuf, const uint8_t* ptrBuf,
+                                     const uint8_t* tagBuf, const uint32_t* inst, uint32_t cmdFirst, uint32_t numCmds, uint64_t* out)
+{
+	oracle_mem m = { segs, numSegs };
+	uint64_t sum = 0, n = 0, faults = 0;
+	for(uint32_t c = cmdFirst; c < cmdFirst + numCmds; c++) {
+		uint32_t cmd[5];  memcpy(cmd, cmdBuf + (size_t)c * 20, 20);
+		uint64_t ptr[4];  memcpy(ptr, ptrBuf + (size_t)c * 32, 32);
+		uint32_t tag[2];  memcpy(tag, tagBuf + (size_t)c * 8, 8);
+		int fault = 0;
+		for(uint32_t k = 0; k < cmd[1]; k++)
+			for(uint32_t v = 0; v < cmd[0]; v++) {
+				sum += fetch_and_hash(&m, ptr[0], ptr[1], ptr[2], tag[0], inst[cmd[4] + k], v + cmd[2], &fault);
+				n++;
+			}
+		faults += (uint64_t)fault;
+	}
+	out[0] = sum; out[1] = n;
+	return faults;
+}
+
 int oracle_max_threads(void)
 {
 #ifdef _OPENMP
