@@ -30,6 +30,7 @@ CULL_BYTES = 48
 ML_HEADER = 64
 MAT_BYTES = 64
 SMALL_MAX = 32       # mirrors cadr_b200/csrc/cull_compact.cu
+MID_MAX = 512
 CHUNK = 1024
 
 
@@ -187,8 +188,13 @@ class Scene:
     @property
     def chunk_capacity(self) -> int:
         c = self.ml_count[self.drawable_ml].astype(np.int64)
-        big = c[c > SMALL_MAX]
+        big = c[c > MID_MAX]
         return int(((big + CHUNK - 1) // CHUNK).sum())
+
+    @property
+    def mid_capacity(self) -> int:
+        c = self.ml_count[self.drawable_ml].astype(np.int64)
+        return int(((c > SMALL_MAX) & (c <= MID_MAX)).sum())
 
     # -- materialisation -----------------------------------------------------------------------------
     def image(self, base: int, with_matrices: bool = True) -> np.ndarray:
@@ -372,7 +378,7 @@ def build_scene(name: str, *, geometries: list[dict] | dict, ml_count: np.ndarra
     # ---- per-StateSet output regions, sized for the worst case -------------------------------------
     S = int(ss.max()) + 1 if n else 1
     cnt = ml_count[dm].astype(np.int64)
-    cmds = np.where(cnt > SMALL_MAX, 3 * ((cnt + CHUNK - 1) // CHUNK), np.minimum(cnt, 3))
+    cmds = np.where(cnt > MID_MAX, 3 * ((cnt + CHUNK - 1) // CHUNK), np.minimum(cnt, 3))
     cmd_cap = np.bincount(ss, weights=cmds, minlength=S).astype(np.int64)
     inst_cap = np.bincount(ss, weights=cnt, minlength=S).astype(np.int64)
     regions = np.zeros((S, 4), dtype=np.uint32)
