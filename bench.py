@@ -328,13 +328,14 @@ def run_b200(args):
             tier_r.append(ctx.kernel_times()[0])
         ctx.set_profiling(False)
 
+    large_name = {"0": "cullLargeLdgKernel", "1": "cullLargeKernel"}.get(os.environ.get("CADR_B200_CULL_VARIANT", "2"), "cullLargeWarpKernel")
     kt = np.array(ktimes)
     k_process, k_small, k_large = (float(kt[:, i].mean()) for i in range(3))
     k_mid = float(kt[:, 5].mean())
     p = float(np.mean(surv)) / inst
     if args.workload == "c3":
         # per instance: 64 B matrix read + 4 B index written per survivor
-        dom_name, dom_ms = ("cullLargeKernel", k_large) if k_large >= k_mid else ("cullMidKernel", k_mid)
+        dom_name, dom_ms = (large_name, k_large) if k_large >= k_mid else ("cullMidKernel", k_mid)
         alg_bytes = (64.0 + 4.0 * p) * inst
         alg_note = "(64 + 4p) B per instance"
     elif args.unfused:
@@ -363,7 +364,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": ds.counters_bytes, "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": int(launches),
         "kernels_ms": {"processDrawablesKernel": round(k_process, 4), "cullSmallKernel" + ("" if args.unfused else "<fused>"): round(k_small, 4),
-                       "cullMidKernel": round(k_mid, 4), "cullLargeKernel": round(k_large, 4)},
+                       "cullMidKernel": round(k_mid, 4), large_name: round(k_large, 4)},
         "entry": "cadr_b200_process_drawables + cadr_b200_cull_compact" if args.unfused else "cadr_b200_process_and_cull",
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": recorded_traffic(dom_name), "peak_source": peak_src,

@@ -41,7 +41,7 @@
 namespace cadr {
 
 constexpr uint32_t SMALL_MAX  = 32;    // lists up to this many matrices are handled by one thread
-constexpr uint32_t MID_MAX    = 512;   // lists up to this many matrices are handled by one warp, inside cullSmallKernel
+constexpr uint32_t MID_MAX    = 512;   // lists up to this many matrices are handled by one warp of cullMidKernel
 constexpr uint32_t CHUNK      = 1024;  // instances per work item of the large-list kernel
 constexpr int      CS_THREADS = 256;
 
@@ -483,100 +483,165 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// medium lists (33..512 matrices): persistent warps, one list per warp at a time
+// medium and long lists: persistent warps, one list (or one work item of a very long list) per warp at a time
 // ---------------------------------------------------------------------------------------------------
-// Coalesced 2-KiB reads (32 consecutive matrices per step, next step prefetched), LODs parked in a warp-private
-// shared-memory strip, ONE 64-bit atomic per list to reserve its output ranges, then a second pass over the strip
-// (not over the matrices) writes the compacted indices.  Without this path such lists would each occupy a whole
-// work item of the large-list kernel and pay its per-item latency (measured: 7 % of the roofline at 64 matrices
-// per list).
+// Coalesced 2-KiB reads (32 consecutive matrices per step as 256-bit loads, next step prefetched), LODs parked in a
+// warp-private shared-memory strip, ONE 64-bit atomic per list to reserve its output ranges, then a second pass over
+// the strip (not over the matrices) writes the compacted indices.  24-32 independent warps per SM keep enough loads in
+// flight to stream HBM at 0.96-0.99 of the measured copy peak from 500 matrices per list upwards; this simple
+// structure beats the TMA producer/consumer pipeline below (0.93), whose single group of consumer warps is
+// issue-bound while it evaluates an item.
 constexpr int CM_THREADS = 256;
 
+struct ListJob {              // what a warp needs to process [first, first + count) of one MatrixList
+	const uint8_t* mats;      // address of matrix `first`
+	uint32_t count, first, drawable, stateSet;
+	LodInfo L;
+	uint32_t psCount, psFirst;   // lanes 0..2: {indexCount, firstIndex} of LOD `lane`
+	uint4 p0, p1;             // DrawablePointers to forward
+};
+
+__device__ __forceinline__ void processListWarp(const CullArgs& A, const ListJob& J, int8_t* strip, int lane)
+{
+	const uint32_t lt = (1u << lane) - 1u;
+	const uint32_t N = J.count;
+	uint32_t t0 = 0, t1 = 0, t2 = 0, nb = 0;
+	Mat cur, nxt;
+	if(uint32_t(lane) < N) cur = loadMat(J.mats + 64ull * lane);
+	for(uint32_t j0 = 0; j0 < N; j0 += 32) {
+		const uint32_t j = j0 + lane;
+		if(j + 32 < N) nxt = loadMat(J.mats + 64ull * (j + 32));     // prefetch the next step
+		int lod = -1;
+		bool nbi = false;
+		if(j < N) lod = evalInstance(cur, J.L, A.plane, A.eye, nbi);
+		strip[j] = int8_t(lod);
+		t0 += __popc(__ballot_sync(0xffffffffu, lod == 0));
+		t1 += __popc(__ballot_sync(0xffffffffu, lod == 1));
+		t2 += __popc(__ballot_sync(0xffffffffu, lod == 2));
+		nb += __popc(__ballot_sync(0xffffffffu, nbi));
+		cur = nxt;
+	}
+	const uint32_t nInst = t0 + t1 + t2, nCmd = (t0 ? 1u : 0u) + (t1 ? 1u : 0u) + (t2 ? 1u : 0u);
+	if(lane == 0 && nb) atomicAdd(&A.hdr->nearBandCount, nb);
+	if(nInst) {   // warp-uniform
+		unsigned long long base = 0;
+		uint4 reg = make_uint4(0, 0, 0, 0);
+		if(lane == 0) {
+			base = atomicAdd(A.counts + J.stateSet, (unsigned long long)nCmd | ((unsigned long long)nInst << 32));
+			reg = ldg_u4(reinterpret_cast<uint64_t>(A.regions + J.stateSet));
+		}
+		base = __shfl_sync(0xffffffffu, base, 0);
+		reg.x = __shfl_sync(0xffffffffu, reg.x, 0); reg.y = __shfl_sync(0xffffffffu, reg.y, 0);
+		reg.z = __shfl_sync(0xffffffffu, reg.z, 0); reg.w = __shfl_sync(0xffffffffu, reg.w, 0);
+		const uint32_t cOff = uint32_t(base), iOff = uint32_t(base >> 32);
+		if(cOff + nCmd > reg.y || iOff + nInst > reg.w) {
+			if(lane == 0) atomicOr(&A.hdr->status, CADR_CULL_STATUS_REGION_OVERFLOW);
+		}
+		else {
+			uint32_t i0 = reg.z + iOff, i1 = i0 + t0, i2 = i1 + t1;
+			if(lane < 3) {
+				const uint32_t tl = (lane == 0) ? t0 : (lane == 1) ? t1 : t2;
+				if(tl) {
+					const uint32_t ci = reg.x + cOff + ((lane > 0 && t0) ? 1u : 0u) + ((lane > 1 && t1) ? 1u : 0u);
+					writeCommandRecord(A, ci, J.psCount, tl, J.psFirst, (lane == 0) ? i0 : (lane == 1) ? i1 : i2,
+					                   J.drawable, uint32_t(lane), J.p0, J.p1);
+				}
+			}
+			__syncwarp();   // the strip was written by other lanes
+			for(uint32_t j0 = 0; j0 < N; j0 += 32) {
+				const uint32_t j = j0 + lane;
+				const int lod = (j < N) ? int(strip[j]) : -1;
+				const unsigned b0 = __ballot_sync(0xffffffffu, lod == 0), b1 = __ballot_sync(0xffffffffu, lod == 1),
+				               b2 = __ballot_sync(0xffffffffu, lod == 2);
+				if(lod == 0) A.instOut[i0 + __popc(b0 & lt)] = J.first + j;
+				if(lod == 1) A.instOut[i1 + __popc(b1 & lt)] = J.first + j;
+				if(lod == 2) A.instOut[i2 + __popc(b2 & lt)] = J.first + j;
+				i0 += __popc(b0); i1 += __popc(b1); i2 += __popc(b2);
+			}
+		}
+	}
+	__syncwarp();       // the strip is reused by the warp's next job
+}
+
+// per-drawable records of a queued medium list (everything but the matrices); issued one list ahead of its use
+struct MidInfo { uint32_t d, N, stateSet; uint4 p0, p1; LodInfo L; uint32_t psOff[3]; };
+
 template<int LEVEL>
-__global__ void __launch_bounds__(CM_THREADS)
+__device__ __forceinline__ MidInfo loadMidInfo(const CullArgs& A, uint32_t idx, uint32_t total)
+{
+	MidInfo I;
+	I.d = 0; I.N = 0; I.stateSet = 0;
+	if(idx < total) {
+		I.d = A.midQueue[idx];
+		I.N = ldg_u4(reinterpret_cast<uint64_t>(A.indirect + I.d)).y;
+		I.p0 = ldg_u4(reinterpret_cast<uint64_t>(A.pointers + 2ull * I.d));
+		I.p1 = ldg_u4(reinterpret_cast<uint64_t>(A.pointers + 2ull * I.d + 1));
+		I.L = unpackLod(ldg_u4(reinterpret_cast<uint64_t>(A.cullData + 3ull * I.d)),
+		                ldg_u4(reinterpret_cast<uint64_t>(A.cullData + 3ull * I.d + 1)),
+		                ldg_u4(reinterpret_cast<uint64_t>(A.cullData + 3ull * I.d + 2)), I.psOff, I.stateSet);
+	}
+	return I;
+}
+
+template<int LEVEL>
+__global__ void __launch_bounds__(CM_THREADS, 3)
 cullMidKernel(const __grid_constant__ CullArgs A)
 {
 	__shared__ int8_t sLodStrip[CM_THREADS / 32][MID_MAX];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	int8_t* strip = sLodStrip[warp];
-	const uint32_t lt = (1u << lane) - 1u;
 	uint32_t total = A.hdr->midCount;
 	if(total > A.midCapacity) total = A.midCapacity;
 
-	uint32_t next = 0;
-	if(lane == 0) next = atomicAdd(&A.hdr->midCursor, 1u);
-	for(;;) {
-		const uint32_t idx = __shfl_sync(0xffffffffu, next, 0);
-		if(idx >= total) break;
-		if(lane == 0) next = atomicAdd(&A.hdr->midCursor, 1u);     // prefetch the next list while this one is processed
-		const uint32_t d = A.midQueue[idx];
-		const uint32_t N = ldg_u4(reinterpret_cast<uint64_t>(A.indirect + d)).y;
-		const uint4 p0 = ldg_u4(reinterpret_cast<uint64_t>(A.pointers + 2ull * d));
-		const uint4 p1 = ldg_u4(reinterpret_cast<uint64_t>(A.pointers + 2ull * d + 1));
-		uint32_t psOff[3], stateSet;
-		const LodInfo L = unpackLod(ldg_u4(reinterpret_cast<uint64_t>(A.cullData + 3ull * d)),
-		                            ldg_u4(reinterpret_cast<uint64_t>(A.cullData + 3ull * d + 1)),
-		                            ldg_u4(reinterpret_cast<uint64_t>(A.cullData + 3ull * d + 2)), psOff, stateSet);
-		const uint8_t* mats = reinterpret_cast<const uint8_t*>(uint64_t(p1.x) | (uint64_t(p1.y) << 32)) + CADR_MATRIX_LIST_HEADER_BYTES;
-		uint64_t psAddr = 0;
-		if(lane < 3) psAddr = primitiveSetBase<LEVEL>(A, d) + psOff[lane];     // resolved early: off the critical path
+	// two queue indices ahead: idx (being processed), idx1 (its records are in flight), idx2 (just requested)
+	uint32_t a = 0;
+	if(lane == 0) a = atomicAdd(&A.hdr->midCursor, 2u);
+	a = __shfl_sync(0xffffffffu, a, 0);
+	uint32_t idx = a, idx1 = a + 1;
+	MidInfo cur = loadMidInfo<LEVEL>(A, idx, total);
+	while(idx < total) {
+		uint32_t idx2 = 0;
+		if(lane == 0) idx2 = atomicAdd(&A.hdr->midCursor, 1u);
+		const MidInfo nxt = loadMidInfo<LEVEL>(A, idx1, total);       // loads for the NEXT list overlap this one
+		ListJob J;
+		J.mats = reinterpret_cast<const uint8_t*>(uint64_t(cur.p1.x) | (uint64_t(cur.p1.y) << 32)) + CADR_MATRIX_LIST_HEADER_BYTES;
+		J.count = cur.N; J.first = 0; J.drawable = cur.d; J.stateSet = cur.stateSet; J.L = cur.L; J.p0 = cur.p0; J.p1 = cur.p1;
+		J.psCount = J.psFirst = 0;
+		if(lane < 3) {
+			const uint64_t psAddr = primitiveSetBase<LEVEL>(A, cur.d) + ((lane == 0) ? cur.psOff[0] : (lane == 1) ? cur.psOff[1] : cur.psOff[2]);
+			J.psCount = ldg_u32(psAddr); J.psFirst = ldg_u32(psAddr + 4);
+		}
+		processListWarp(A, J, sLodStrip[warp], lane);
+		idx = idx1;
+		idx1 = __shfl_sync(0xffffffffu, idx2, 0);
+		cur = nxt;
+	}
+}
 
-		uint32_t t0 = 0, t1 = 0, t2 = 0, nb = 0;
-		Mat cur, nxt;
-		if(uint32_t(lane) < N) cur = loadMat(mats + 64ull * lane);
-		for(uint32_t j0 = 0; j0 < N; j0 += 32) {
-			const uint32_t j = j0 + lane;
-			if(j + 32 < N) nxt = loadMat(mats + 64ull * (j + 32));
-			int lod = -1;
-			bool nbi = false;
-			if(j < N) lod = evalInstance(cur, L, A.plane, A.eye, nbi);
-			strip[j & (MID_MAX - 1)] = int8_t(lod);
-			t0 += __popc(__ballot_sync(0xffffffffu, lod == 0));
-			t1 += __popc(__ballot_sync(0xffffffffu, lod == 1));
-			t2 += __popc(__ballot_sync(0xffffffffu, lod == 2));
-			nb += __popc(__ballot_sync(0xffffffffu, nbi));
-			cur = nxt;
-		}
-		const uint32_t nInst = t0 + t1 + t2, nCmd = (t0 ? 1u : 0u) + (t1 ? 1u : 0u) + (t2 ? 1u : 0u);
-		if(lane == 0 && nb) atomicAdd(&A.hdr->nearBandCount, nb);
-		if(nInst) {   // warp-uniform
-			unsigned long long base = 0;
-			uint4 reg = make_uint4(0, 0, 0, 0);
-			if(lane == 0) {
-				base = atomicAdd(A.counts + stateSet, (unsigned long long)nCmd | ((unsigned long long)nInst << 32));
-				reg = ldg_u4(reinterpret_cast<uint64_t>(A.regions + stateSet));
-			}
-			base = __shfl_sync(0xffffffffu, base, 0);
-			reg.x = __shfl_sync(0xffffffffu, reg.x, 0); reg.y = __shfl_sync(0xffffffffu, reg.y, 0);
-			reg.z = __shfl_sync(0xffffffffu, reg.z, 0); reg.w = __shfl_sync(0xffffffffu, reg.w, 0);
-			const uint32_t cOff = uint32_t(base), iOff = uint32_t(base >> 32);
-			if(cOff + nCmd > reg.y || iOff + nInst > reg.w) {
-				if(lane == 0) atomicOr(&A.hdr->status, CADR_CULL_STATUS_REGION_OVERFLOW);
-			}
-			else {
-				uint32_t i0 = reg.z + iOff, i1 = i0 + t0, i2 = i1 + t1;
-				if(lane < 3) {
-					const uint32_t tl = (lane == 0) ? t0 : (lane == 1) ? t1 : t2;
-					if(tl) {
-						const uint32_t ci = reg.x + cOff + ((lane > 0 && t0) ? 1u : 0u) + ((lane > 1 && t1) ? 1u : 0u);
-						writeCommandRecord(A, ci, ldg_u32(psAddr), tl, ldg_u32(psAddr + 4), (lane == 0) ? i0 : (lane == 1) ? i1 : i2,
-						                   d, uint32_t(lane), p0, p1);
-					}
-				}
-				__syncwarp();   // the strip was written by other lanes
-				for(uint32_t j0 = 0; j0 < N; j0 += 32) {
-					const uint32_t j = j0 + lane;
-					const int lod = (j < N) ? int(strip[j & (MID_MAX - 1)]) : -1;
-					const unsigned b0 = __ballot_sync(0xffffffffu, lod == 0), b1 = __ballot_sync(0xffffffffu, lod == 1),
-					               b2 = __ballot_sync(0xffffffffu, lod == 2);
-					if(lod == 0) A.instOut[i0 + __popc(b0 & lt)] = j;
-					if(lod == 1) A.instOut[i1 + __popc(b1 & lt)] = j;
-					if(lod == 2) A.instOut[i2 + __popc(b2 & lt)] = j;
-					i0 += __popc(b0); i1 += __popc(b1); i2 += __popc(b2);
-				}
-			}
-		}
-		__syncwarp();       // the strip is reused by the next list
+// very long lists: one warp per 1024-matrix work item (self-contained descriptor written by cullSmallKernel)
+__global__ void __launch_bounds__(CM_THREADS)
+cullLargeWarpKernel(const __grid_constant__ CullArgs A)
+{
+	__shared__ int8_t sLodStrip[CM_THREADS / 32][CHUNK];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t total = A.hdr->chunkCount;
+	if(total > A.chunkCapacity) total = A.chunkCapacity;
+	uint32_t next = 0;
+	if(lane == 0) next = atomicAdd(&A.hdr->chunkCursor, 1u);
+	for(;;) {
+		const uint32_t item = __shfl_sync(0xffffffffu, next, 0);
+		if(item >= total) break;
+		if(lane == 0) next = atomicAdd(&A.hdr->chunkCursor, 1u);
+		const uint4* w = reinterpret_cast<const uint4*>(A.items + item);
+		const uint4 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4], w5 = w[5];
+		ListJob J;
+		J.mats = reinterpret_cast<const uint8_t*>(uint64_t(w0.x) | (uint64_t(w0.y) << 32));
+		J.count = w0.z; J.first = w0.w; J.drawable = w1.x; J.stateSet = w1.y;
+		J.L.sphere = make_float4(__uint_as_float(w2.x), __uint_as_float(w2.y), __uint_as_float(w2.z), __uint_as_float(w2.w));
+		J.L.lodCount = w1.z; J.L.thr0 = __uint_as_float(w3.x); J.L.thr1 = __uint_as_float(w3.y);
+		J.psCount = (lane == 0) ? w4.x : (lane == 1) ? w4.z : w5.x;
+		J.psFirst = (lane == 0) ? w4.y : (lane == 1) ? w4.w : w5.y;
+		J.p0 = w[6]; J.p1 = w[7];
+		processListWarp(A, J, sLodStrip[warp], lane);
 	}
 }
 
@@ -934,7 +999,7 @@ cullLargeLdgKernel(const __grid_constant__ CullArgs A)
 static int cullVariant()
 {
 	const char* v = std::getenv("CADR_B200_CULL_VARIANT");
-	return v ? std::atoi(v) : 1;   // 1 = TMA pipeline (default), 0 = direct-load version
+	return v ? std::atoi(v) : 2;   // 2 = warp per work item (default), 1 = TMA pipeline, 0 = first direct-load version
 }
 
 int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, bool fused)
@@ -1042,6 +1107,12 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 			uint32_t gridL = uint32_t(ctx->smCount) * 2u;   // two CTAs per SM (launch bounds)
 			if(gridL > p.chunkCapacity) gridL = p.chunkCapacity;
 			cullLargeLdgKernel<<<gridL, CL_THREADS, 0, s>>>(A);
+		}
+		else if(variant == 2) {
+			uint32_t gridL = uint32_t(ctx->smCount) * 4u;   // persistent warps, like cullMidKernel
+			const uint32_t need = (p.chunkCapacity + CM_THREADS / 32 - 1) / (CM_THREADS / 32);
+			if(gridL > need) gridL = need;
+			cullLargeWarpKernel<<<gridL, CM_THREADS, 0, s>>>(A);
 		}
 		else {
 			if(!ctx->largeKernelConfigured) {   // per device (a process may hold one context per GPU)
