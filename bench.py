@@ -18,10 +18,14 @@ VkDrawIndexedIndirectCommand lists (Tier X), through the C ABI of libcadr_b200.s
             workload.  The reference's own GPU path cannot run here (no Vulkan ICD) and it has no CPU path other
             than running the GLSL on a CPU ICD, so the port is the baseline ("kind": "port").
 
-Workloads (BASELINE.json configs): c3 = 100k geometries x 1000-instance MatrixLists (100 M instances), 64
-StateSets, 3 LODs — the configuration north_star's target is quoted on; c2 = 10 M drawables x 1 matrix.
-Multi-GPU (torchrun): every rank culls its own c3-shaped shard (weak scaling, config 5 = 8 x 125 M), then the
-compacted command lists + per-StateSet counters are all-gathered over NCCL into one buffer on every rank.
+Workloads (BASELINE.json configs): c3 = configs[2], 100k geometries x 1000-instance MatrixLists (100 M instances),
+64 StateSets, 3 LODs — the configuration north_star's target is quoted on, and the default; c2 = configs[1], 10 M
+drawables x 1 matrix; c4 = configs[3], c3 with 10 % of the MatrixLists rewritten every frame through the upload path
+(device-resident: staging already in HBM, scatter kernel + cull; e2e: cadr_b200_upload from pinned host staging,
+640 MB over PCIe per frame, + cull); c5 = configs[4], the c3 shape at 125 M instances per GPU (8 GPUs = 1 B).
+Multi-GPU (torchrun): every rank culls its own shard (weak scaling); the compacted command lists and per-StateSet
+counters of all ranks end up in one buffer on every rank — stored there by the cull kernels themselves over NVLink
+peer mappings (default), or all-gathered with NCCL after the cull (--exchange nccl, the baseline).
 """
 from __future__ import annotations
 
@@ -47,7 +51,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"])
     ap.add_argument("--drawables", type=int, default=0, help="override the drawable count (debug)")
     ap.add_argument("--instances", type=int, default=1000, help="matrices per list for c3")
     ap.add_argument("--state-sets", type=int, default=64, help="StateSets for c3 (debug: 1 makes drawable order == list order)")
@@ -60,16 +64,23 @@ def parse_args():
     return ap.parse_args()
 
 
+C3_SHAPED = ("c3", "c4", "c5")
+
+
+def c3_drawables(args) -> int:
+    return args.drawables or (125_000 if args.workload == "c5" else 100_000)
+
+
 def make_scene(args, rank: int, host_matrices: bool, drawables: int | None = None) -> synth.Scene:
-    if args.workload == "c3":
-        n = drawables or args.drawables or 100_000
+    if args.workload in C3_SHAPED:
+        n = drawables or c3_drawables(args)
         return synth.config3(n, args.instances, state_sets=args.state_sets, seed=0xC0FFEE03 + rank, host_matrices=host_matrices)
     n = drawables or args.drawables or 10_000_000
     return synth.config2(n, seed=0xC0FFEE02 + rank, host_matrices=host_matrices)
 
 
 def camera(args, frame: int):
-    far = 3000.0 if args.workload == "c3" else 1500.0
+    far = 3000.0 if args.workload in C3_SHAPED else 1500.0
     return synth.orbit_camera(frame, 1500.0, far=far)
 
 
@@ -137,7 +148,7 @@ def cpu_sample_run(args, steps: int, warmup: int, sample_drawables: int | None =
     from oracle import binding as ob
     threads = ob.max_threads()
     if sample_drawables is None:
-        sample_drawables = args.cpu_sample or (8000 if args.workload == "c3" else 4_000_000)
+        sample_drawables = args.cpu_sample or (8000 if args.workload in C3_SHAPED else 4_000_000)
     sc = make_scene(args, 0, host_matrices=True, drawables=sample_drawables)
     base, lst = 0x7F1200000000, 0x7F2000000000
     img = sc.image(base)
@@ -180,13 +191,21 @@ def run_reference(args):
 
 
 def workload_config(args, n_gpus: int) -> dict:
-    if args.workload == "c3":
-        n = args.drawables or 100_000
-        return {"workload": f"BASELINE configs[2]: synthetic CAD assembly, {n} geometries x {args.instances}-instance MatrixLists "
-                            f"({n * args.instances / 1e6:.0f} M instances) per GPU, 64 StateSets, 3-level LOD, orbiting camera 1 deg/frame",
+    if args.workload in C3_SHAPED:
+        n = c3_drawables(args)
+        which = {"c3": "configs[2]: synthetic CAD assembly", "c5": "configs[4]: 1 B-instance scene sharded over 8 GPUs, this is the per-GPU shard",
+                 "c4": "configs[3]: dynamic scene, 10 % of the MatrixLists rewritten per frame through the upload path, then culled"}[args.workload]
+        if n_gpus == 1:
+            mg = "single GPU"
+        elif args.exchange == "peer":
+            mg = "each rank culls its own shard; the cull kernels store command records into every rank's gathered arrays over NVLink peer mappings"
+        else:
+            mg = "each rank culls its own shard; command lists + counters all-gathered with NCCL after the cull"
+        return {"workload": f"BASELINE {which}, {n} geometries x {args.instances}-instance MatrixLists "
+                            f"({n * args.instances / 1e6:.0f} M instances) per GPU, {args.state_sets} StateSets, 3-level LOD, orbiting camera 1 deg/frame",
                 "per_gpu_instances": n * args.instances, "gpus": n_gpus,
-                "l2": "inputs (6.4 GB of matrices per GPU) are far larger than the 126 MB L2; no flush needed",
-                "multi_gpu": "each rank culls its own shard; command lists + counters all-gathered over NCCL" if n_gpus > 1 else "single GPU"}
+                "l2": f"inputs ({n * args.instances * 64 / 1e9:.1f} GB of matrices per GPU) are far larger than the 126 MB L2; no flush needed",
+                "multi_gpu": mg}
     n = args.drawables or 10_000_000
     return {"workload": f"BASELINE configs[1]: {n} drawables x 1 matrix, single StateSet, orbiting camera", "per_gpu_instances": n,
             "gpus": n_gpus, "l2": "inputs (1.3 GB matrix lists + 0.5 GB drawable list per GPU) are far larger than the 126 MB L2"}
@@ -225,6 +244,32 @@ def run_b200(args):
     inst = scene.total_instances
     cams = [camera(args, k) for k in range(360)]
 
+    # configs[3]: every frame 10 % of the MatrixLists get all their matrices rewritten (SURVEY Appendix D cfg 4:
+    # lists {(f*10007 + t*7919) mod n}); in-place variant: same device ranges, one copy region per list
+    rewrite = None
+    if args.workload == "c4":
+        from cadr_b200.synth_torch import c3_matrices
+        rw_lists, blk = scene.n // 10, args.instances * 64
+        stage_dev = arena.alloc(rw_lists * blk)
+        with torch.cuda.stream(stream_t):
+            for a in range(0, rw_lists, 2000):
+                b = min(rw_lists, a + 2000)
+                m = c3_matrices(scene.seed ^ 0x5EED, torch.arange(a, b, dtype=torch.int64, device=dev), args.instances,
+                                scene.gen["cube"], scene.gen["sigma"])
+                arena.tensor(stage_dev)[a * blk:b * blk] = m.view(torch.uint8).view(-1)
+        stage_host = ctx.host_alloc(rw_lists * blk)
+        ctx.memcpy_d2h(stage_host, stage_dev, rw_lists * blk, stream=stream)
+        ctx.sync(stream)
+        src = np.arange(rw_lists, dtype=np.uint64) * np.uint64(blk)
+        size = np.full(rw_lists, blk, np.uint64)
+
+        def regions_of(frame):
+            lists = (frame * 10007 + np.arange(rw_lists, dtype=np.int64) * 7919) % scene.n
+            return np.stack([np.uint64(ds.arena) + scene.ml_off[lists] + np.uint64(64), src, size], axis=1)
+
+        rewrite = dict(regions=[regions_of(f) for f in range(16)], stage_dev=stage_dev, stage_host=stage_host,
+                       bytes=rw_lists * blk, lists=rw_lists)
+
     # multi-GPU exchange: every rank ends up with all ranks' compacted command lists and per-range counters
     ex = px = None
     if world > 1:
@@ -256,12 +301,16 @@ def run_b200(args):
             ex.run(*parts)
 
     def step_device(k, with_exchange=True):
+        if rewrite is not None:        # staged bytes already in HBM: scatter kernel only
+            ctx.scatter_copy(rewrite["regions"][k % 16], rewrite["stage_dev"], stream=stream)
         run_cull(k, with_exchange)
 
     counters_host = torch.empty(ds.counters_bytes, dtype=torch.uint8).pin_memory()
     counters_dev = arena.tensor(ds.counters)
 
     def step_e2e(k):
+        if rewrite is not None:        # Renderer::executeCopyOperations: pinned host staging -> device ranges (PCIe)
+            ctx.upload(rewrite["regions"][k % 16], rewrite["stage_host"], stream=stream)
         ds.upload_drawable_list()                 # pinned host list -> device, 48 B/drawable (Renderer.cpp:635-644)
         run_cull(k, True)
         counters_host.copy_(counters_dev, non_blocking=True)
@@ -310,13 +359,20 @@ def run_b200(args):
 
         for k in range(3):
             step_e2e(k)
-        ms_e2e = timed(step_e2e, args.steps)
+        e2e_steps = args.steps if rewrite is None else min(args.steps, 50)    # c4 moves 640 MB over PCIe per step
+        ms_e2e = timed(step_e2e, e2e_steps)
 
         # per-kernel durations (CUDA events recorded by the library around each of its kernels)
         ctx.set_profiling(True)
+        scatter_ms = []
+        if rewrite is not None:
+            for k in range(8):
+                ctx.scatter_copy(rewrite["regions"][k], rewrite["stage_dev"], stream=stream)
+                stream_t.synchronize()
+                scatter_ms.append(ctx.kernel_times()[3])
         ktimes, surv = [], []
         for k in range(min(args.steps, 20)):
-            step_device(args.warmup + k, with_exchange=False)
+            run_cull(args.warmup + k, False)
             stream_t.synchronize()
             ktimes.append(ctx.kernel_times())
             surv.append(int(ds.read_counters()["inst_count"].sum()))
@@ -328,14 +384,14 @@ def run_b200(args):
             tier_r.append(ctx.kernel_times()[0])
         ctx.set_profiling(False)
 
-    large_name = {"0": "cullLargeLdgKernel", "1": "cullLargeKernel"}.get(os.environ.get("CADR_B200_CULL_VARIANT", "2"), "cullLargeWarpKernel")
+    large_name = {"0": "cullLargeLdgKernel", "1": "cullLargeKernel"}.get(os.environ.get("CADR_B200_CULL_VARIANT", "2"), "cullListWarpKernel")
     kt = np.array(ktimes)
     k_process, k_small, k_large = (float(kt[:, i].mean()) for i in range(3))
-    k_mid = float(kt[:, 5].mean())
     p = float(np.mean(surv)) / inst
-    if args.workload == "c3":
+    line_granular = None
+    if args.workload in C3_SHAPED:
         # per instance: 64 B matrix read + 4 B index written per survivor
-        dom_name, dom_ms = (large_name, k_large) if k_large >= k_mid else ("cullMidKernel", k_mid)
+        dom_name, dom_ms = (large_name, k_large) if k_large >= k_small else ("cullSmallKernel", k_small)
         alg_bytes = (64.0 + 4.0 * p) * inst
         alg_note = "(64 + 4p) B per instance"
     elif args.unfused:
@@ -348,11 +404,16 @@ def run_b200(args):
         dom_name, dom_ms = "cullSmallKernel", k_small
         alg_bytes = (48 + 8 + 4 + 64 + 48 + 48 + 64.0 * p) * inst
         alg_note = "per drawable: 172 B read (list 48, leaf 8, numMatrices 4, matrix 64, cull record 48) + 48 B Tier R records + 64p B written"
+        # what DRAM must move at this layout: a B200 L2 miss fetches the whole 128-B line (scripts/l2gran.cu), so the 4-byte
+        # numMatrices + 64-byte matrix of a one-matrix MatrixList block cost 128 B, not 68
+        line_granular = (48 + 8 + 128 + 48 + 48 + 64.0 * p) * inst
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
     total_inst = inst * world
     value = total_inst * args.steps / (ms_total * 1e-3)
-    e2e_value = total_inst * args.steps / (ms_e2e * 1e-3)
+    e2e_value = total_inst * e2e_steps / (ms_e2e * 1e-3)
+    tier_r_ms = float(np.median(tier_r[2:]))
+    tier_r_bytes = 140 if args.workload in C3_SHAPED else 108
 
     line = {
         "metric": "culled+emitted instances/sec", "value": round(value / 1e6, 1), "unit": "M instances/s",
@@ -360,21 +421,34 @@ def run_b200(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world),
         "survivor_fraction": round(p, 4),
-        "e2e": {"value": round(e2e_value / 1e6, 1), "unit": "M instances/s", "h2d_bytes_per_step": scene.n * 48 + 232,
-                "d2h_bytes_per_step": ds.counters_bytes, "ms_per_step": round(ms_e2e / args.steps, 4)},
+        "e2e": {"value": round(e2e_value / 1e6, 1), "unit": "M instances/s",
+                "h2d_bytes_per_step": scene.n * 48 + 232 + (rewrite["bytes"] + rewrite["lists"] * 24 if rewrite else 0),
+                "d2h_bytes_per_step": ds.counters_bytes, "ms_per_step": round(ms_e2e / e2e_steps, 4), "steps": e2e_steps},
         "gpu_launches": int(launches),
         "kernels_ms": {"processDrawablesKernel": round(k_process, 4), "cullSmallKernel" + ("" if args.unfused else "<fused>"): round(k_small, 4),
-                       "cullMidKernel": round(k_mid, 4), large_name: round(k_large, 4)},
+                       large_name: round(k_large, 4)},
         "entry": "cadr_b200_process_drawables + cadr_b200_cull_compact" if args.unfused else "cadr_b200_process_and_cull",
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": recorded_traffic(dom_name), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(alg_bytes), "algorithmic_bytes": alg_note, "launch_ms": round(dom_ms, 4)},
         "clocks": clocks,
-        "tier_r": {"kernel": "processDrawablesKernel", "drawables": scene.n, "launch_ms": round(float(np.median(tier_r[2:])), 4),
-                   "value": round(scene.n / (float(np.median(tier_r[2:])) * 1e-3) / 1e6, 1), "unit": "M drawables/s",
-                   "algorithmic_bytes_per_drawable": 140 if args.workload == "c3" else 108,
-                   "frac": round((140 if args.workload == "c3" else 108) * scene.n / (float(np.median(tier_r[2:])) * 1e-3) / 1e9 / peak, 4)},
+        "tier_r": {"kernel": "processDrawablesKernel", "drawables": scene.n, "launch_ms": round(tier_r_ms, 4),
+                   "value": round(scene.n / (tier_r_ms * 1e-3) / 1e6, 1), "unit": "M drawables/s",
+                   "algorithmic_bytes_per_drawable": tier_r_bytes,
+                   "frac": round(tier_r_bytes * scene.n / (tier_r_ms * 1e-3) / 1e9 / peak, 4)},
     }
+    if line_granular is not None:
+        line["roofline"]["dram_line_granular_bytes_per_launch"] = int(line_granular)
+        line["roofline"]["frac_of_line_granular_floor"] = round(line_granular / (dom_ms * 1e-3) / 1e9 / peak, 4)
+        # Tier R alone on this shape: 48 list + 8 leaf + 128 (line holding numMatrices) read, 48 written
+        line["tier_r"]["frac_of_line_granular_floor"] = round(232 * scene.n / (tier_r_ms * 1e-3) / 1e9 / peak, 4)
+    if rewrite is not None:
+        sc_ms = float(np.median(scatter_ms[2:]))
+        line["upload"] = {"rewritten_lists_per_step": rewrite["lists"], "bytes_per_step": rewrite["bytes"], "kernel": "scatterCopyKernel",
+                          "launch_ms": round(sc_ms, 4), "achieved": round(2 * rewrite["bytes"] / (sc_ms * 1e-3) / 1e9, 1), "unit": "GB/s",
+                          "algorithmic_bytes": "2 x staged bytes (read staging + write arena)",
+                          "frac": round(2 * rewrite["bytes"] / (sc_ms * 1e-3) / 1e9 / peak, 4),
+                          "e2e_note": "e2e steps stage the same bytes from pinned host memory (cadr_b200_upload): PCIe-bound"}
     if world > 1:
         line["cull_only"] = {"value": round(total_inst * args.steps / (ms_cull_only * 1e-3) / 1e6, 1), "unit": "M instances/s",
                              "ms_per_step": round(ms_cull_only / args.steps, 4)}
@@ -387,6 +461,8 @@ def run_b200(args):
         print(json.dumps(line))
     if px is not None:
         px.close()
+    if rewrite is not None:
+        ctx.host_free(rewrite["stage_host"])
     ds.close()
     ctx.close()
     if world > 1:

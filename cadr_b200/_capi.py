@@ -89,9 +89,6 @@ class CullParams(C.Structure):
         ("exchangeCmd", C.c_uint64 * 8),
         ("exchangePtr", C.c_uint64 * 8),
         ("exchangeTag", C.c_uint64 * 8),
-        ("midWorkspace", C.c_uint64),
-        ("midCapacity", C.c_uint32),
-        ("reserved3", C.c_uint32),
     ]
 
 
@@ -161,7 +158,7 @@ def lib() -> C.CDLL:
             f = getattr(l, name)  # AttributeError if the library does not export a declared symbol
             f.restype = res
             f.argtypes = args
-        if l.cadr_b200_abi_version() != 3:
+        if l.cadr_b200_abi_version() != 4:
             raise ImportError("libcadr_b200.so ABI version mismatch")
         _lib = l
     return _lib
@@ -321,8 +318,8 @@ class Context:
         check(self._l.cadr_b200_set_profiling(self._h, 1 if enabled else 0))
 
     def kernel_times(self) -> list[float]:
-        ms = (C.c_float * 6)()
-        check(self._l.cadr_b200_kernel_times(self._h, ms, 6))
+        ms = (C.c_float * 5)()
+        check(self._l.cadr_b200_kernel_times(self._h, ms, 5))
         return list(ms)
 
 

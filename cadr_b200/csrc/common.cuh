@@ -12,7 +12,7 @@
 
 namespace cadr {
 
-enum KernelSlot { KS_PROCESS = 0, KS_CULL_SMALL = 1, KS_CULL_LARGE = 2, KS_SCATTER = 3, KS_PATCH = 4, KS_CULL_MID = 5, KS_COUNT = 6 };
+enum KernelSlot { KS_PROCESS = 0, KS_CULL_SMALL = 1, KS_CULL_LARGE = 2, KS_SCATTER = 3, KS_PATCH = 4, KS_COUNT = 5 };
 
 int setError(int code, const char* fmt, ...);
 int cudaFail(cudaError_t e, const char* what);

@@ -6,27 +6,22 @@
 //
 // Two kernels per frame, both HBM-bound (no tensor-core work: gather + compaction):
 //
-//   cullSmallKernel   one THREAD per drawable.  Lists of <= 32 matrices are evaluated by the drawable's own
-//                     thread (config C2: 10 M drawables x 1 matrix); lists of 33..512 matrices by the drawable's
-//                     warp, one list at a time (coalesced reads, one atomic per list).  Longer lists are cut into work items of
-//                     <= 1024 consecutive matrices; the thread writes one self-contained 128-byte descriptor
-//                     per item (matrix address, count, sphere, LOD table, resolved PrimitiveSets, pointers to
-//                     forward) into a queue reserved with ONE block-aggregated atomic per CTA.
-//   cullLargeKernel   persistent, one CTA per SM, warp-specialised:
-//                       producer warp   pulls item indices from the queue cursor and streams each item's
-//                                       descriptor + up to 64 KiB of matrices into a 3-stage shared-memory ring
-//                                       with TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx::bytes);
-//                       16 consumer warps wait on the stage's mbarrier, read "their" 64 matrices conflict-free
-//                                       from shared memory, evaluate them, compact survivors per LOD with
-//                                       __ballot_sync/__popc into a per-stage stash (rank reserved by one
-//                                       shared-memory atomic per warp and LOD) and release the stage.  The warp
-//                                       that finishes an item last reserves the item's output ranges with ONE
-//                                       64-bit global atomicAdd on the StateSet's packed {commands, instances}
-//                                       counter, writes the <= 3 commands and copies the stash out coalesced.
-//                     No CTA-wide barrier inside the loop: loads of items i+1, i+2 are in flight while item i is
-//                     evaluated, and warps never wait for each other.
-//   cullLargeLdgKernel  the first version of the same stage (direct 256-bit global loads, CTA barriers); kept
-//                     selectable (CADR_B200_CULL_VARIANT=0) for A/B measurements.
+//   cullSmallKernel     one THREAD per drawable.  Lists of <= 32 matrices are evaluated by the drawable's own
+//                       thread (config C2: 10 M drawables x 1 matrix).  Longer lists are cut into work items of
+//                       <= 1024 consecutive matrices; the thread writes one self-contained 128-byte descriptor
+//                       per item (matrix address, count, sphere, LOD table, resolved PrimitiveSets, pointers to
+//                       forward) into a queue reserved with ONE block-aggregated atomic per CTA.
+//   cullListWarpKernel  persistent warps, one work item per warp at a time, software-pipelined ACROSS items: the
+//                       item index is claimed three items ahead, the descriptor is requested two items ahead, and
+//                       the last 32-matrix step of an item already loads the first step of the next one, so no
+//                       dependent load and no atomic round trip is ever waited for in front of a matrix load.
+//                       Default for every list longer than 32 matrices.
+//   cullLargeKernel     the same stage as a warp-specialised TMA pipeline (CADR_B200_CULL_VARIANT=1): persistent,
+//                       one CTA per SM; a producer lane streams each item's descriptor + up to 64 KiB of matrices
+//                       into a 3-stage shared-memory ring with TMA bulk copies (cp.async.bulk ...
+//                       mbarrier::complete_tx::bytes); 16 consumer warps evaluate from shared memory.  Measured
+//                       slower than the warp-per-item kernel (0.93 vs 1.02 of the copy peak); kept for A/B.
+//   cullLargeLdgKernel  the first version (CTA per item, direct loads, CTA barriers; CADR_B200_CULL_VARIANT=0).
 //
 // No per-instance global atomics anywhere.  Emission order of commands inside a StateSet and of instance
 // indices inside a run depends on arrival order, so comparisons canonicalise: merge by (drawableIndex, lod),
@@ -40,9 +35,8 @@
 
 namespace cadr {
 
-constexpr uint32_t SMALL_MAX  = 32;    // lists up to this many matrices are handled by one thread
-constexpr uint32_t MID_MAX    = 512;   // lists up to this many matrices are handled by one warp of cullMidKernel
-constexpr uint32_t CHUNK      = 1024;  // instances per work item of the large-list kernel
+constexpr uint32_t SMALL_MAX  = CADR_CULL_SMALL_LIST_MAX;        // lists up to this many matrices are handled by one thread
+constexpr uint32_t CHUNK      = CADR_CULL_WORK_ITEM_INSTANCES;   // instances per work item of the list kernels
 constexpr int      CS_THREADS = 256;
 
 // Self-contained work item of the large-list kernel: 128 bytes, written by cullSmallKernel.
@@ -77,9 +71,7 @@ struct CullArgs {
 	cadr_cull_header* hdr;
 	unsigned long long* counts;
 	WorkItem* items;
-	uint32_t* midQueue;
 	uint32_t  chunkCapacity;
-	uint32_t  midCapacity;
 	uint32_t  n;
 	uint32_t  numStateSets;
 	float4 plane[6];
@@ -326,7 +318,7 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 	const uint64_t matrixList = uint64_t(p1.x) | (uint64_t(p1.y) << 32);
 
 	// ---- number of work items this drawable needs in the large-list queue --------------------------
-	uint32_t nChunks = (N > MID_MAX) ? (N + CHUNK - 1) / CHUNK : 0;
+	uint32_t nChunks = (N > SMALL_MAX) ? (N + CHUNK - 1) / CHUNK : 0;
 	uint32_t chunkIncl = warpInclusiveScan(nChunks, lane);
 	if(lane == 31) sChunkTot[warp] = chunkIncl;
 
@@ -346,22 +338,6 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 			mask2 |= (lod == 2) ? bit : 0u;
 		}
 	}
-	// ---- medium lists (33..512 matrices) go to cullMidKernel: one warp-aggregated atomic reserves queue slots ----------
-	{
-		const bool isMid = valid && N > SMALL_MAX && N <= MID_MAX;
-		const unsigned midMask = __ballot_sync(0xffffffffu, isMid);
-		if(midMask) {
-			uint32_t base = 0;
-			if(lane == 0) base = atomicAdd(&A.hdr->midCount, uint32_t(__popc(midMask)));
-			base = __shfl_sync(0xffffffffu, base, 0);
-			if(isMid) {
-				const uint32_t slot = base + __popc(midMask & ((1u << lane) - 1u));
-				if(slot < A.midCapacity) A.midQueue[slot] = d;
-				else atomicOr(&A.hdr->status, CADR_CULL_STATUS_CHUNK_OVERFLOW);
-			}
-		}
-	}
-
 	const uint32_t k0 = __popc(mask0), k1 = __popc(mask1), k2 = __popc(mask2);
 	const uint32_t nInst = k0 + k1 + k2;
 	const uint32_t nCmd = (k0 ? 1u : 0u) + (k1 ? 1u : 0u) + (k2 ? 1u : 0u);
@@ -483,165 +459,157 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// medium and long lists: persistent warps, one list (or one work item of a very long list) per warp at a time
+// lists longer than 32 matrices: persistent warps, one work item per warp at a time, pipelined across items
 // ---------------------------------------------------------------------------------------------------
-// Coalesced 2-KiB reads (32 consecutive matrices per step as 256-bit loads, next step prefetched), LODs parked in a
-// warp-private shared-memory strip, ONE 64-bit atomic per list to reserve its output ranges, then a second pass over
-// the strip (not over the matrices) writes the compacted indices.  24-32 independent warps per SM keep enough loads in
-// flight to stream HBM at 0.96-0.99 of the measured copy peak from 500 matrices per list upwards; this simple
-// structure beats the TMA producer/consumer pipeline below (0.93), whose single group of consumer warps is
-// issue-bound while it evaluates an item.
+// Per step a warp reads 32 consecutive matrices as 256-bit loads (2 KiB, full 32-byte sectors) and already has the
+// next step in flight; LODs are parked in a warp-private shared-memory strip; per-LOD counts come from
+// __ballot_sync/__popc; ONE 64-bit atomic per item reserves both output ranges; a second pass over the strip (not
+// over the matrices) writes the compacted indices coalesced.
+//
+// What keeps short items (33..200 matrices) at bandwidth is the pipeline ACROSS items.  Each warp always knows
+//   item A  being evaluated (its first step was loaded during the previous item),
+//   item B  descriptor in registers (requested one item ago): the LAST step of A issues B's first matrix loads, so
+//           they are in flight while A's atomic, command records and index write-out happen,
+//   item C  descriptor just requested,   item D  index being claimed (atomic issued, consumed next iteration),
+// so neither the queue atomic, nor the descriptor fetch, nor the output reservation sits in front of a matrix load.
+// A descriptor lives as ONE 16-byte word per lane (lanes 0..7 hold words 0..7 of the 128-byte item) and is unpacked
+// with shuffles.  Items are claimed in batches (1..8 per atomic, more when the queue is long) so that a queue of
+// millions of short items is not limited by same-address atomic throughput.
 constexpr int CM_THREADS = 256;
 
-struct ListJob {              // what a warp needs to process [first, first + count) of one MatrixList
-	const uint8_t* mats;      // address of matrix `first`
-	uint32_t count, first, drawable, stateSet;
-	LodInfo L;
-	uint32_t psCount, psFirst;   // lanes 0..2: {indexCount, firstIndex} of LOD `lane`
-	uint4 p0, p1;             // DrawablePointers to forward
-};
-
-__device__ __forceinline__ void processListWarp(const CullArgs& A, const ListJob& J, int8_t* strip, int lane)
+__device__ __forceinline__ uint4 loadItemWord(const CullArgs& A, uint32_t item, uint32_t total, int lane)
 {
-	const uint32_t lt = (1u << lane) - 1u;
-	const uint32_t N = J.count;
-	uint32_t t0 = 0, t1 = 0, t2 = 0, nb = 0;
-	Mat cur, nxt;
-	if(uint32_t(lane) < N) cur = loadMat(J.mats + 64ull * lane);
-	for(uint32_t j0 = 0; j0 < N; j0 += 32) {
-		const uint32_t j = j0 + lane;
-		if(j + 32 < N) nxt = loadMat(J.mats + 64ull * (j + 32));     // prefetch the next step
-		int lod = -1;
-		bool nbi = false;
-		if(j < N) lod = evalInstance(cur, J.L, A.plane, A.eye, nbi);
-		strip[j] = int8_t(lod);
-		t0 += __popc(__ballot_sync(0xffffffffu, lod == 0));
-		t1 += __popc(__ballot_sync(0xffffffffu, lod == 1));
-		t2 += __popc(__ballot_sync(0xffffffffu, lod == 2));
-		nb += __popc(__ballot_sync(0xffffffffu, nbi));
-		cur = nxt;
-	}
-	const uint32_t nInst = t0 + t1 + t2, nCmd = (t0 ? 1u : 0u) + (t1 ? 1u : 0u) + (t2 ? 1u : 0u);
-	if(lane == 0 && nb) atomicAdd(&A.hdr->nearBandCount, nb);
-	if(nInst) {   // warp-uniform
-		unsigned long long base = 0;
-		uint4 reg = make_uint4(0, 0, 0, 0);
-		if(lane == 0) {
-			base = atomicAdd(A.counts + J.stateSet, (unsigned long long)nCmd | ((unsigned long long)nInst << 32));
-			reg = ldg_u4(reinterpret_cast<uint64_t>(A.regions + J.stateSet));
-		}
-		base = __shfl_sync(0xffffffffu, base, 0);
-		reg.x = __shfl_sync(0xffffffffu, reg.x, 0); reg.y = __shfl_sync(0xffffffffu, reg.y, 0);
-		reg.z = __shfl_sync(0xffffffffu, reg.z, 0); reg.w = __shfl_sync(0xffffffffu, reg.w, 0);
-		const uint32_t cOff = uint32_t(base), iOff = uint32_t(base >> 32);
-		if(cOff + nCmd > reg.y || iOff + nInst > reg.w) {
-			if(lane == 0) atomicOr(&A.hdr->status, CADR_CULL_STATUS_REGION_OVERFLOW);
-		}
-		else {
-			uint32_t i0 = reg.z + iOff, i1 = i0 + t0, i2 = i1 + t1;
-			if(lane < 3) {
-				const uint32_t tl = (lane == 0) ? t0 : (lane == 1) ? t1 : t2;
-				if(tl) {
-					const uint32_t ci = reg.x + cOff + ((lane > 0 && t0) ? 1u : 0u) + ((lane > 1 && t1) ? 1u : 0u);
-					writeCommandRecord(A, ci, J.psCount, tl, J.psFirst, (lane == 0) ? i0 : (lane == 1) ? i1 : i2,
-					                   J.drawable, uint32_t(lane), J.p0, J.p1);
-				}
-			}
-			__syncwarp();   // the strip was written by other lanes
-			for(uint32_t j0 = 0; j0 < N; j0 += 32) {
-				const uint32_t j = j0 + lane;
-				const int lod = (j < N) ? int(strip[j]) : -1;
-				const unsigned b0 = __ballot_sync(0xffffffffu, lod == 0), b1 = __ballot_sync(0xffffffffu, lod == 1),
-				               b2 = __ballot_sync(0xffffffffu, lod == 2);
-				if(lod == 0) A.instOut[i0 + __popc(b0 & lt)] = J.first + j;
-				if(lod == 1) A.instOut[i1 + __popc(b1 & lt)] = J.first + j;
-				if(lod == 2) A.instOut[i2 + __popc(b2 & lt)] = J.first + j;
-				i0 += __popc(b0); i1 += __popc(b1); i2 += __popc(b2);
-			}
-		}
-	}
-	__syncwarp();       // the strip is reused by the warp's next job
+	uint4 w = make_uint4(0u, 0u, 0u, 0u);     // count 0 = no item
+	if(item < total && lane < 8) w = ldg_stream_u4(reinterpret_cast<const uint4*>(A.items + item) + lane);
+	return w;
 }
 
-// per-drawable records of a queued medium list (everything but the matrices); issued one list ahead of its use
-struct MidInfo { uint32_t d, N, stateSet; uint4 p0, p1; LodInfo L; uint32_t psOff[3]; };
-
-template<int LEVEL>
-__device__ __forceinline__ MidInfo loadMidInfo(const CullArgs& A, uint32_t idx, uint32_t total)
-{
-	MidInfo I;
-	I.d = 0; I.N = 0; I.stateSet = 0;
-	if(idx < total) {
-		I.d = A.midQueue[idx];
-		I.N = ldg_u4(reinterpret_cast<uint64_t>(A.indirect + I.d)).y;
-		I.p0 = ldg_u4(reinterpret_cast<uint64_t>(A.pointers + 2ull * I.d));
-		I.p1 = ldg_u4(reinterpret_cast<uint64_t>(A.pointers + 2ull * I.d + 1));
-		I.L = unpackLod(ldg_u4(reinterpret_cast<uint64_t>(A.cullData + 3ull * I.d)),
-		                ldg_u4(reinterpret_cast<uint64_t>(A.cullData + 3ull * I.d + 1)),
-		                ldg_u4(reinterpret_cast<uint64_t>(A.cullData + 3ull * I.d + 2)), I.psOff, I.stateSet);
-	}
-	return I;
-}
-
-template<int LEVEL>
-__global__ void __launch_bounds__(CM_THREADS, 3)
-cullMidKernel(const __grid_constant__ CullArgs A)
-{
-	__shared__ int8_t sLodStrip[CM_THREADS / 32][MID_MAX];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint32_t total = A.hdr->midCount;
-	if(total > A.midCapacity) total = A.midCapacity;
-
-	// two queue indices ahead: idx (being processed), idx1 (its records are in flight), idx2 (just requested)
-	uint32_t a = 0;
-	if(lane == 0) a = atomicAdd(&A.hdr->midCursor, 2u);
-	a = __shfl_sync(0xffffffffu, a, 0);
-	uint32_t idx = a, idx1 = a + 1;
-	MidInfo cur = loadMidInfo<LEVEL>(A, idx, total);
-	while(idx < total) {
-		uint32_t idx2 = 0;
-		if(lane == 0) idx2 = atomicAdd(&A.hdr->midCursor, 1u);
-		const MidInfo nxt = loadMidInfo<LEVEL>(A, idx1, total);       // loads for the NEXT list overlap this one
-		ListJob J;
-		J.mats = reinterpret_cast<const uint8_t*>(uint64_t(cur.p1.x) | (uint64_t(cur.p1.y) << 32)) + CADR_MATRIX_LIST_HEADER_BYTES;
-		J.count = cur.N; J.first = 0; J.drawable = cur.d; J.stateSet = cur.stateSet; J.L = cur.L; J.p0 = cur.p0; J.p1 = cur.p1;
-		J.psCount = J.psFirst = 0;
-		if(lane < 3) {
-			const uint64_t psAddr = primitiveSetBase<LEVEL>(A, cur.d) + ((lane == 0) ? cur.psOff[0] : (lane == 1) ? cur.psOff[1] : cur.psOff[2]);
-			J.psCount = ldg_u32(psAddr); J.psFirst = ldg_u32(psAddr + 4);
-		}
-		processListWarp(A, J, sLodStrip[warp], lane);
-		idx = idx1;
-		idx1 = __shfl_sync(0xffffffffu, idx2, 0);
-		cur = nxt;
-	}
-}
-
-// very long lists: one warp per 1024-matrix work item (self-contained descriptor written by cullSmallKernel)
-__global__ void __launch_bounds__(CM_THREADS)
-cullLargeWarpKernel(const __grid_constant__ CullArgs A)
+__global__ void __launch_bounds__(CM_THREADS, 4)
+cullListWarpKernel(const __grid_constant__ CullArgs A)
 {
 	__shared__ int8_t sLodStrip[CM_THREADS / 32][CHUNK];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31;
+	int8_t* strip = sLodStrip[threadIdx.x >> 5];
+	const uint32_t lt = (1u << lane) - 1u;
+	const unsigned FULL = 0xffffffffu;
+
 	uint32_t total = A.hdr->chunkCount;
 	if(total > A.chunkCapacity) total = A.chunkCapacity;
-	uint32_t next = 0;
-	if(lane == 0) next = atomicAdd(&A.hdr->chunkCursor, 1u);
-	for(;;) {
-		const uint32_t item = __shfl_sync(0xffffffffu, next, 0);
-		if(item >= total) break;
-		if(lane == 0) next = atomicAdd(&A.hdr->chunkCursor, 1u);
-		const uint4* w = reinterpret_cast<const uint4*>(A.items + item);
-		const uint4 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4], w5 = w[5];
-		ListJob J;
-		J.mats = reinterpret_cast<const uint8_t*>(uint64_t(w0.x) | (uint64_t(w0.y) << 32));
-		J.count = w0.z; J.first = w0.w; J.drawable = w1.x; J.stateSet = w1.y;
-		J.L.sphere = make_float4(__uint_as_float(w2.x), __uint_as_float(w2.y), __uint_as_float(w2.z), __uint_as_float(w2.w));
-		J.L.lodCount = w1.z; J.L.thr0 = __uint_as_float(w3.x); J.L.thr1 = __uint_as_float(w3.y);
-		J.psCount = (lane == 0) ? w4.x : (lane == 1) ? w4.z : w5.x;
-		J.psFirst = (lane == 0) ? w4.y : (lane == 1) ? w4.w : w5.y;
-		J.p0 = w[6]; J.p1 = w[7];
-		processListWarp(A, J, sLodStrip[warp], lane);
+	const uint32_t numWarps = gridDim.x * (CM_THREADS / 32);
+	uint32_t batch = total / (numWarps * 16u);          // long queues: fewer atomics; short queues: best balance
+	batch = batch < 1u ? 1u : (batch > 8u ? 8u : batch);
+
+	// lane 0 owns the claimed index range [rNext, rEnd)
+	uint32_t rNext = 0, rEnd = 0;
+	uint32_t iA, iB, iC;
+	{
+		const uint32_t first = batch < 3u ? 3u : batch;
+		uint32_t r = 0;
+		if(lane == 0) { r = atomicAdd(&A.hdr->chunkCursor, first); rNext = r + 3u; rEnd = r + first; }
+		r = __shfl_sync(FULL, r, 0);
+		iA = r; iB = r + 1u; iC = r + 2u;
+	}
+	uint4 dA = loadItemWord(A, iA, total, lane);
+	uint4 dB = loadItemWord(A, iB, total, lane);
+
+	Mat cur, nxt;
+	{
+		const uint64_t m = uint64_t(__shfl_sync(FULL, dA.x, 0)) | (uint64_t(__shfl_sync(FULL, dA.y, 0)) << 32);
+		const uint32_t n = __shfl_sync(FULL, dA.z, 0);
+		if(uint32_t(lane) < n) cur = loadMat(reinterpret_cast<const uint8_t*>(m) + 64ull * lane);
+	}
+
+	while(iA < total) {
+		// ---- keep the pipeline full: descriptor of C, index of D -------------------------------------
+		const uint4 dC = loadItemWord(A, iC, total, lane);
+		uint32_t iD = 0;
+		if(lane == 0) {
+			if(rNext < rEnd) iD = rNext++;
+			else { iD = atomicAdd(&A.hdr->chunkCursor, batch); rNext = iD + 1u; rEnd = iD + batch; }
+		}
+		// ---- unpack A ----------------------------------------------------------------------------------
+		const uint8_t* matsA = reinterpret_cast<const uint8_t*>(uint64_t(__shfl_sync(FULL, dA.x, 0)) | (uint64_t(__shfl_sync(FULL, dA.y, 0)) << 32));
+		const uint32_t N = __shfl_sync(FULL, dA.z, 0), firstInstance = __shfl_sync(FULL, dA.w, 0);
+		LodInfo L;
+		L.lodCount = __shfl_sync(FULL, dA.z, 1);
+		L.sphere = make_float4(__uint_as_float(__shfl_sync(FULL, dA.x, 2)), __uint_as_float(__shfl_sync(FULL, dA.y, 2)),
+		                       __uint_as_float(__shfl_sync(FULL, dA.z, 2)), __uint_as_float(__shfl_sync(FULL, dA.w, 2)));
+		L.thr0 = __uint_as_float(__shfl_sync(FULL, dA.x, 3)); L.thr1 = __uint_as_float(__shfl_sync(FULL, dA.y, 3));
+		// first step of B (0 matrices when there is no B)
+		const uint8_t* matsB = reinterpret_cast<const uint8_t*>(uint64_t(__shfl_sync(FULL, dB.x, 0)) | (uint64_t(__shfl_sync(FULL, dB.y, 0)) << 32));
+		const uint32_t nB = __shfl_sync(FULL, dB.z, 0);
+
+		// ---- evaluate A, 32 matrices per step, next step (or B's first step) in flight -----------------
+		uint32_t t0 = 0, t1 = 0, t2 = 0, nb = 0;
+		for(uint32_t j0 = 0; j0 < N; j0 += 32) {
+			const uint32_t j = j0 + lane;
+			if(j0 + 32 < N) { if(j + 32 < N) nxt = loadMat(matsA + 64ull * (j + 32)); }
+			else if(uint32_t(lane) < nB) nxt = loadMat(matsB + 64ull * lane);
+			int lod = -1;
+			bool nbi = false;
+			if(j < N) lod = evalInstance(cur, L, A.plane, A.eye, nbi);
+			strip[j] = int8_t(lod);
+			t0 += __popc(__ballot_sync(FULL, lod == 0));
+			t1 += __popc(__ballot_sync(FULL, lod == 1));
+			t2 += __popc(__ballot_sync(FULL, lod == 2));
+			nb += __popc(__ballot_sync(FULL, nbi));
+			cur = nxt;
+		}
+		if(N == 0 && uint32_t(lane) < nB) cur = loadMat(matsB + 64ull * lane);   // never queued; keeps the pipeline sound
+
+		// ---- reserve, emit commands, write the compacted indices ---------------------------------------
+		const uint32_t nInst = t0 + t1 + t2, nCmd = (t0 ? 1u : 0u) + (t1 ? 1u : 0u) + (t2 ? 1u : 0u);
+		if(lane == 0 && nb) atomicAdd(&A.hdr->nearBandCount, nb);
+		if(nInst) {   // warp-uniform
+			const uint32_t stateSet = __shfl_sync(FULL, dA.y, 1);
+			unsigned long long base = 0;
+			uint4 reg = make_uint4(0, 0, 0, 0);
+			if(lane == 0) {
+				base = atomicAdd(A.counts + stateSet, (unsigned long long)nCmd | ((unsigned long long)nInst << 32));
+				reg = ldg_u4(reinterpret_cast<uint64_t>(A.regions + stateSet));
+			}
+			base = __shfl_sync(FULL, base, 0);
+			reg.x = __shfl_sync(FULL, reg.x, 0); reg.y = __shfl_sync(FULL, reg.y, 0);
+			reg.z = __shfl_sync(FULL, reg.z, 0); reg.w = __shfl_sync(FULL, reg.w, 0);
+			const uint32_t cOff = uint32_t(base), iOff = uint32_t(base >> 32);
+			if(cOff + nCmd > reg.y || iOff + nInst > reg.w) {
+				if(lane == 0) atomicOr(&A.hdr->status, CADR_CULL_STATUS_REGION_OVERFLOW);
+			}
+			else {
+				uint32_t i0 = reg.z + iOff, i1 = i0 + t0, i2 = i1 + t1;
+				// lane l (< 3) emits the command of LOD l: PrimitiveSets are words 4 and 5, pointers words 6 and 7
+				const uint32_t drawable = __shfl_sync(FULL, dA.x, 1);
+				const uint4 w4 = make_uint4(__shfl_sync(FULL, dA.x, 4), __shfl_sync(FULL, dA.y, 4), __shfl_sync(FULL, dA.z, 4), __shfl_sync(FULL, dA.w, 4));
+				const uint2 w5 = make_uint2(__shfl_sync(FULL, dA.x, 5), __shfl_sync(FULL, dA.y, 5));
+				const uint4 p0 = make_uint4(__shfl_sync(FULL, dA.x, 6), __shfl_sync(FULL, dA.y, 6), __shfl_sync(FULL, dA.z, 6), __shfl_sync(FULL, dA.w, 6));
+				const uint4 p1 = make_uint4(__shfl_sync(FULL, dA.x, 7), __shfl_sync(FULL, dA.y, 7), __shfl_sync(FULL, dA.z, 7), __shfl_sync(FULL, dA.w, 7));
+				if(lane < 3) {
+					const uint32_t tl = (lane == 0) ? t0 : (lane == 1) ? t1 : t2;
+					if(tl) {
+						const uint32_t ci = reg.x + cOff + ((lane > 0 && t0) ? 1u : 0u) + ((lane > 1 && t1) ? 1u : 0u);
+						const uint32_t psCount = (lane == 0) ? w4.x : (lane == 1) ? w4.z : w5.x;
+						const uint32_t psFirst = (lane == 0) ? w4.y : (lane == 1) ? w4.w : w5.y;
+						writeCommandRecord(A, ci, psCount, tl, psFirst, (lane == 0) ? i0 : (lane == 1) ? i1 : i2,
+						                   drawable, uint32_t(lane), p0, p1);
+					}
+				}
+				__syncwarp();   // the strip was written by other lanes
+				for(uint32_t j0 = 0; j0 < N; j0 += 32) {
+					const uint32_t j = j0 + lane;
+					const int lod = (j < N) ? int(strip[j]) : -1;
+					const unsigned b0 = __ballot_sync(FULL, lod == 0), b1 = __ballot_sync(FULL, lod == 1), b2 = __ballot_sync(FULL, lod == 2);
+					if(lod == 0) A.instOut[i0 + __popc(b0 & lt)] = firstInstance + j;
+					if(lod == 1) A.instOut[i1 + __popc(b1 & lt)] = firstInstance + j;
+					if(lod == 2) A.instOut[i2 + __popc(b2 & lt)] = firstInstance + j;
+					i0 += __popc(b0); i1 += __popc(b1); i2 += __popc(b2);
+				}
+			}
+		}
+		__syncwarp();       // the strip is reused by the next item
+
+		// ---- advance the pipeline ------------------------------------------------------------------------
+		dA = dB; dB = dC;
+		iA = iB; iB = iC; iC = __shfl_sync(FULL, iD, 0);
 	}
 }
 
@@ -1032,8 +1000,6 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 		return setError(CADR_E_LOGIC, "cull_compact: numStateSets must be > 0");
 	if(p.chunkCapacity && !p.chunkWorkspace)
 		return setError(CADR_E_LOGIC, "cull_compact: chunkCapacity > 0 but no chunkWorkspace");
-	if(p.midCapacity && (!p.midWorkspace || (p.midWorkspace & 3)))
-		return setError(CADR_E_LOGIC, "cull_compact: midCapacity > 0 but midWorkspace missing or misaligned");
 
 	CullArgs A;
 	A.root = p.handleTableRoot;
@@ -1050,8 +1016,6 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 	A.counts = reinterpret_cast<unsigned long long*>(p.counters + sizeof(cadr_cull_header));
 	A.items = reinterpret_cast<WorkItem*>(p.chunkWorkspace);
 	A.chunkCapacity = p.chunkCapacity;
-	A.midQueue = reinterpret_cast<uint32_t*>(p.midWorkspace);
-	A.midCapacity = p.midCapacity;
 	A.n = p.numDrawables;
 	A.numStateSets = p.numStateSets;
 	for(int k = 0; k < 6; k++) A.plane[k] = make_float4(p.planes[k][0], p.planes[k][1], p.planes[k][2], p.planes[k][3]);
@@ -1084,22 +1048,6 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 	ctx->launches++;
 	CADR_CUDA(cudaGetLastError());
 
-	if(p.midCapacity) {
-		// persistent warps: four CTAs per SM, never more warps than lists could exist
-		uint32_t gridM = uint32_t(ctx->smCount) * 4u;
-		const uint32_t need = (p.midCapacity + CM_THREADS / 32 - 1) / (CM_THREADS / 32);
-		if(gridM > need) gridM = need;
-		ctx->timeBegin(KS_CULL_MID, s);
-		switch(p.handleLevel) {
-		case 1: cullMidKernel<1><<<gridM, CM_THREADS, 0, s>>>(A); break;
-		case 2: cullMidKernel<2><<<gridM, CM_THREADS, 0, s>>>(A); break;
-		default: cullMidKernel<3><<<gridM, CM_THREADS, 0, s>>>(A); break;
-		}
-		ctx->timeEnd(KS_CULL_MID, s);
-		ctx->launches++;
-		CADR_CUDA(cudaGetLastError());
-	}
-
 	if(p.chunkCapacity) {
 		const int variant = cullVariant();
 		ctx->timeBegin(KS_CULL_LARGE, s);
@@ -1109,10 +1057,10 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 			cullLargeLdgKernel<<<gridL, CL_THREADS, 0, s>>>(A);
 		}
 		else if(variant == 2) {
-			uint32_t gridL = uint32_t(ctx->smCount) * 4u;   // persistent warps, like cullMidKernel
+			uint32_t gridL = uint32_t(ctx->smCount) * 4u;   // persistent warps: four CTAs of eight warps per SM
 			const uint32_t need = (p.chunkCapacity + CM_THREADS / 32 - 1) / (CM_THREADS / 32);
 			if(gridL > need) gridL = need;
-			cullLargeWarpKernel<<<gridL, CM_THREADS, 0, s>>>(A);
+			cullListWarpKernel<<<gridL, CM_THREADS, 0, s>>>(A);
 		}
 		else {
 			if(!ctx->largeKernelConfigured) {   // per device (a process may hold one context per GPU)

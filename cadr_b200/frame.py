@@ -51,8 +51,6 @@ class DeviceScene:
         self.counters = self._new(self.counters_bytes)
         self.chunk_cap = scene.chunk_capacity
         self.chunk_ws = self._new(max(self.chunk_cap, 1) * 128)   # CADR_CULL_WORK_ITEM_BYTES
-        self.mid_cap = scene.mid_capacity
-        self.mid_ws = self._new(max(self.mid_cap, 1) * 4)
         self.root = self.arena + scene.root_off
         # host staging for the drawable list (the reference keeps it in a mapped HOST_CACHED buffer,
         # Renderer.cpp:513-535) — pinned here so the per-frame copy is a true DMA
@@ -116,7 +114,6 @@ class DeviceScene:
         p.numStateSets, p.stateSetRegions = sc.num_state_sets, self.regions
         p.cmdOut, p.ptrOut, p.tagOut, p.instOut, p.counters = self.cmd_out, self.ptr_out, self.tag_out, self.inst_out, self.counters
         p.chunkWorkspace, p.chunkCapacity = self.chunk_ws, self.chunk_cap
-        p.midWorkspace, p.midCapacity = self.mid_ws, self.mid_cap
         return p
 
     def cull(self, planes: np.ndarray, eye: np.ndarray, stream: int | None = None) -> None:

@@ -72,10 +72,10 @@ class Renderer {
 	std::vector<DrawRange> _drawRanges;
 	std::vector<uint64_t> _rangeInstances;   // worst-case instance count per draw range
 	std::vector<uint64_t> _rangeCommands;
-	uint64_t _rangeChunks = 0, _rangeMids = 0;
+	uint64_t _rangeChunks = 0;
 	CullResult _cull;
-	size_t _cullCmdCapacity = 0, _cullInstCapacity = 0, _cullRangeCapacity = 0, _cullChunkCapacity = 0, _cullMidCapacity = 0;
-	uint64_t _cullRegionsAddress = 0, _cullWorkspaceAddress = 0, _cullMidAddress = 0;
+	size_t _cullCmdCapacity = 0, _cullInstCapacity = 0, _cullRangeCapacity = 0, _cullChunkCapacity = 0;
+	uint64_t _cullRegionsAddress = 0, _cullWorkspaceAddress = 0;
 	bool _collectFrameInfo = false;
 	FrameInfo _inProgress, _completed;
 	uint64_t _countsEpoch = 0;

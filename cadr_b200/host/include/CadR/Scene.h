@@ -184,7 +184,7 @@ class StateSet {                  // src/CadR/StateSet.{h,cpp} (Vulkan pipeline/
 	std::vector<DrawableCullData> _drawableCullList;   // parallel to _drawableDataList
 	std::vector<Drawable*> _drawablePtrList;
 	// worst-case output sizes of the culling extension for this StateSet, recomputed when instance counts change
-	uint64_t _totalsEpoch = ~0ull, _instanceTotal = 0, _commandTotal = 0, _chunkTotal = 0, _midTotal = 0;
+	uint64_t _totalsEpoch = ~0ull, _instanceTotal = 0, _commandTotal = 0, _chunkTotal = 0;
 	void updateCullTotals();
 	// device-resident drawable list: where this StateSet's records were placed the last time they were copied
 	// (one entry per recording of the StateSet in a frame: a StateSet with several parents is recorded several times)

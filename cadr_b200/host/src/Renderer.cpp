@@ -41,7 +41,7 @@ Renderer::~Renderer()
 	_dataStorage.reset();       // handle table and buffers first: they return staging blocks
 	_stagingManager.reset();
 	freeDrawableBuffers();
-	for(uint64_t a : {_cull.commands, _cull.pointers, _cull.tags, _cull.instances, _cull.counters, _cullRegionsAddress, _cullWorkspaceAddress, _cullMidAddress})
+	for(uint64_t a : {_cull.commands, _cull.pointers, _cull.tags, _cull.instances, _cull.counters, _cullRegionsAddress, _cullWorkspaceAddress})
 		if(a) cadr_b200_arena_free(_ctx, a);
 	if(_defaultRenderer == this) _defaultRenderer = nullptr;
 	if(_ownsContext) cadr_b200_destroy(_ctx);
@@ -83,7 +83,6 @@ void Renderer::beginRecording()
 	_rangeInstances.clear();
 	_rangeCommands.clear();
 	_rangeChunks = 0;
-	_rangeMids = 0;
 }
 
 size_t Renderer::prepareSceneRendering(StateSet& stateSetRoot)
@@ -123,19 +122,18 @@ void Renderer::recordDrawableProcessing(size_t numDrawables)
 void StateSet::updateCullTotals()
 {
 	if(_totalsEpoch == _renderer->countsEpoch()) return;
-	_instanceTotal = _commandTotal = _chunkTotal = _midTotal = 0;
+	_instanceTotal = _commandTotal = _chunkTotal = 0;
 	for(size_t i = 0; i < _drawablePtrList.size(); i++) {
 		const uint64_t n = _drawablePtrList[i]->matrixList().numMatrices();
 		const uint64_t lods = _drawableCullList[i].lodCount;
 		_instanceTotal += n;
-		if(n > CADR_CULL_MID_LIST_MAX) {
+		if(n > CADR_CULL_SMALL_LIST_MAX) {    // becomes work items of the list kernel
 			const uint64_t items = (n + CADR_CULL_WORK_ITEM_INSTANCES - 1) / CADR_CULL_WORK_ITEM_INSTANCES;
 			_chunkTotal += items;
 			_commandTotal += lods * items;
 		}
 		else {
 			_commandTotal += n < lods ? n : lods;
-			if(n > CADR_CULL_SMALL_LIST_MAX) _midTotal++;
 		}
 	}
 	_totalsEpoch = _renderer->countsEpoch();
@@ -168,7 +166,6 @@ void Renderer::recordStateSetRange(StateSet& ss, size_t first)
 	_rangeInstances.push_back(ss._instanceTotal);
 	_rangeCommands.push_back(ss._commandTotal);
 	_rangeChunks += ss._chunkTotal;
-	_rangeMids += ss._midTotal;
 }
 
 void Renderer::recordSceneRendering(StateSet& stateSetRoot)
@@ -178,7 +175,6 @@ void Renderer::recordSceneRendering(StateSet& stateSetRoot)
 	_rangeInstances.clear();
 	_rangeCommands.clear();
 	_rangeChunks = 0;
-	_rangeMids = 0;
 	size_t drawableCounter = 0;
 	stateSetRoot.recordToCommandBuffer(drawableCounter);
 	if(drawableCounter != _recordedDrawables && _processingRecorded)
@@ -233,7 +229,6 @@ void Renderer::ensureCullBuffers()
 		_cullRangeCapacity = rangeCap;
 	}
 	grow(_cullWorkspaceAddress, _cullChunkCapacity, size_t(_rangeChunks), CADR_CULL_WORK_ITEM_BYTES, {});
-	grow(_cullMidAddress, _cullMidCapacity, size_t(_rangeMids), sizeof(uint32_t), {});
 }
 
 void Renderer::submit()
@@ -283,8 +278,6 @@ void Renderer::submit()
 		p.counters = _cull.counters;
 		p.chunkWorkspace = _cullWorkspaceAddress;
 		p.chunkCapacity = uint32_t(_rangeChunks);
-		p.midWorkspace = _cullMidAddress;
-		p.midCapacity = uint32_t(_rangeMids);
 		check(cadr_b200_process_and_cull(_ctx, &p, _stream));
 	}
 }

@@ -30,7 +30,6 @@ CULL_BYTES = 48
 ML_HEADER = 64
 MAT_BYTES = 64
 SMALL_MAX = 32       # mirrors cadr_b200/csrc/cull_compact.cu
-MID_MAX = 512
 CHUNK = 1024
 
 
@@ -188,13 +187,8 @@ class Scene:
     @property
     def chunk_capacity(self) -> int:
         c = self.ml_count[self.drawable_ml].astype(np.int64)
-        big = c[c > MID_MAX]
+        big = c[c > SMALL_MAX]
         return int(((big + CHUNK - 1) // CHUNK).sum())
-
-    @property
-    def mid_capacity(self) -> int:
-        c = self.ml_count[self.drawable_ml].astype(np.int64)
-        return int(((c > SMALL_MAX) & (c <= MID_MAX)).sum())
 
     # -- materialisation -----------------------------------------------------------------------------
     def image(self, base: int, with_matrices: bool = True) -> np.ndarray:
@@ -378,7 +372,7 @@ def build_scene(name: str, *, geometries: list[dict] | dict, ml_count: np.ndarra
     # ---- per-StateSet output regions, sized for the worst case -------------------------------------
     S = int(ss.max()) + 1 if n else 1
     cnt = ml_count[dm].astype(np.int64)
-    cmds = np.where(cnt > MID_MAX, 3 * ((cnt + CHUNK - 1) // CHUNK), np.minimum(cnt, 3))
+    cmds = np.where(cnt > SMALL_MAX, 3 * ((cnt + CHUNK - 1) // CHUNK), np.minimum(cnt, 3))
     cmd_cap = np.bincount(ss, weights=cmds, minlength=S).astype(np.int64)
     inst_cap = np.bincount(ss, weights=cnt, minlength=S).astype(np.int64)
     regions = np.zeros((S, 4), dtype=np.uint32)
@@ -514,9 +508,12 @@ def config1(boxes_per_side: int = 100, seed: int = 1) -> Scene:
 
 def random_scene(seed: int, n: int = 300, num_geometries: int = 7, num_lists: int = 50, max_count: int = 70,
                  state_sets: int = 5, first_handle: int = 1, force_level: int = 0, big_lists: int = 0,
-                 with_drawable_data: bool = True, cube: float = 400.0, valid_geometry: bool = False) -> Scene:
+                 with_drawable_data: bool = True, cube: float = 400.0, valid_geometry: bool = False,
+                 list_counts=None) -> Scene:
     """Ragged scene for parity tests: empty lists, shared lists/geometries, 1-3 LODs, empty spheres, several
-    primitive sets per geometry, optional per-drawable data, StateSets of uneven size."""
+    primitive sets per geometry, optional per-drawable data, StateSets of uneven size.  `list_counts` fixes the
+    length of every MatrixList (boundary cases of the small / medium / long-list kernels); drawable k then uses
+    list k mod len(list_counts) so that every list is referenced."""
     rng = np.random.default_rng(seed)
     geos = []
     for g in range(num_geometries):
@@ -538,13 +535,16 @@ def random_scene(seed: int, n: int = 300, num_geometries: int = 7, num_lists: in
     counts[rng.integers(0, num_lists, max(1, num_lists // 5))] = 1             # many single-matrix lists
     for b in range(big_lists):
         counts[int(rng.integers(0, num_lists))] = int(rng.integers(1025, 3500))  # lists spanning several work items
+    if list_counts is not None:
+        counts = np.asarray(list_counts, dtype=np.uint32)
+        num_lists = len(counts)
     total = int(counts.sum())
     pos = (rng.random((total, 3), dtype=np.float32) - np.float32(0.5)) * np.float32(cube)
     q = rng.normal(size=(total, 4)).astype(np.float32)
     q /= np.linalg.norm(q, axis=1, keepdims=True).astype(np.float32)
     mats = trs_matrices(pos, q, (0.25 + 3 * rng.random(total)).astype(np.float32))
     dg = rng.integers(0, num_geometries, n)
-    dm = rng.integers(0, num_lists, n)
+    dm = rng.integers(0, num_lists, n) if list_counts is None else np.arange(n) % num_lists
     nps = np.array([g["primitive_sets"].shape[0] for g in geos])
     pso = (rng.integers(0, 4, n) % nps[dg]) * 8
     lodc = rng.integers(1, 4, n).astype(np.uint32)

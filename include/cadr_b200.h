@@ -40,7 +40,7 @@ extern "C" {
 # define CADR_API __attribute__((visibility("default")))
 #endif
 
-#define CADR_B200_ABI_VERSION 3
+#define CADR_B200_ABI_VERSION 4
 
 /* ---- error codes (src/CadR/Exceptions.h:13-40) ------------------------------------------------- */
 enum {
@@ -128,18 +128,15 @@ typedef struct cadr_command_tag { uint32_t drawableIndex, lod; } cadr_command_ta
 typedef struct cadr_cull_header {
 	uint32_t status;          /* bit 0: a region overflowed, bit 1: chunk workspace overflowed, bit 2: bad range index */
 	uint32_t nearBandCount;   /* instances within 1e-5 of a frustum plane or LOD threshold           */
-	uint32_t chunkCount;      /* internal: work items queued for the large-list kernel               */
-	uint32_t chunkCursor;     /* internal: work items taken                                          */
-	uint32_t midCount;        /* internal: medium lists queued for the per-warp kernel                */
-	uint32_t midCursor;       /* internal: medium lists taken                                         */
-	uint32_t reserved[10];
+	uint32_t chunkCount;      /* internal: work items queued for the list kernel                     */
+	uint32_t chunkCursor;     /* internal: work items claimed                                        */
+	uint32_t reserved[12];
 } cadr_cull_header;           /* 64 B */
 #define CADR_CULL_STATUS_REGION_OVERFLOW 1u
 #define CADR_CULL_STATUS_CHUNK_OVERFLOW  2u
 #define CADR_CULL_STATUS_BAD_RANGE_INDEX 4u     /* a culling record's stateSetIndex >= numStateSets: drawable skipped */
 #define CADR_CULL_WORK_ITEM_BYTES        128u   /* one self-contained descriptor per <= 1024 matrices */
-#define CADR_CULL_SMALL_LIST_MAX         32u    /* lists up to this size are evaluated by one thread  */
-#define CADR_CULL_MID_LIST_MAX           512u   /* lists up to this size by one warp; longer ones become work items */
+#define CADR_CULL_SMALL_LIST_MAX         32u    /* lists up to this size are evaluated by one thread; longer ones become work items */
 #define CADR_CULL_WORK_ITEM_INSTANCES    1024u
 
 #define CADR_MAX_PEERS 8
@@ -167,8 +164,8 @@ typedef struct cadr_cull_params {
 	uint64_t instOut;            /* uint32_t instance indices                                       */
 	uint64_t counters;           /* cadr_cull_header + uint64_t[numStateSets]; zeroed by the call    */
 	/* scratch */
-	uint64_t chunkWorkspace;     /* CADR_CULL_WORK_ITEM_BYTES per work item of the large-list kernel, 16-B aligned */
-	uint32_t chunkCapacity;      /* >= sum over drawables with > CADR_CULL_MID_LIST_MAX matrices of ceil(numMatrices/1024) */
+	uint64_t chunkWorkspace;     /* CADR_CULL_WORK_ITEM_BYTES per work item of the list kernel, 16-B aligned */
+	uint32_t chunkCapacity;      /* >= sum over drawables with > CADR_CULL_SMALL_LIST_MAX matrices of ceil(numMatrices/1024) */
 	uint32_t reserved1;
 	/* Multi-GPU, fused exchange (no reference counterpart).  With exchangeWorld >= 2 the kernels store
 	 * every emitted command / pointers / tag record straight into the gathered arrays of ALL ranks over NVLink peer
@@ -182,10 +179,6 @@ typedef struct cadr_cull_params {
 	uint64_t exchangeCmd[CADR_MAX_PEERS];
 	uint64_t exchangePtr[CADR_MAX_PEERS];
 	uint64_t exchangeTag[CADR_MAX_PEERS];
-	/* scratch for lists of 33..CADR_CULL_MID_LIST_MAX matrices: one u32 per such drawable */
-	uint64_t midWorkspace;
-	uint32_t midCapacity;        /* >= number of drawables whose lists have 33..CADR_CULL_MID_LIST_MAX matrices */
-	uint32_t reserved3;
 } cadr_cull_params;
 
 /* Publishing a rank's per-range counters to its peers and signalling "frame complete" (stream-ordered after the
@@ -337,8 +330,8 @@ CADR_API int  cadr_b200_consume_check_culled(cadr_ctx* ctx, const cadr_cull_para
 
 /* When enabled, process_drawables / cull_compact / upload bracket each kernel with CUDA events.
  * cadr_b200_kernel_times returns, after a sync, the milliseconds of the most recent call:
- * [0] process_drawables, [1] cull small-list kernel, [2] cull large-list kernel,
- * [3] scatter copy, [4] handle patch, [5] cull medium-list kernel.  Unused slots are 0. */
+ * [0] process_drawables, [1] cull small-list kernel (thread per drawable), [2] cull list kernel (work items),
+ * [3] scatter copy, [4] handle patch.  Unused slots are 0. */
 CADR_API int  cadr_b200_set_profiling(cadr_ctx* ctx, int enabled);
 CADR_API int  cadr_b200_kernel_times(cadr_ctx* ctx, float* ms, uint32_t n);
 /* How many kernels of this library the context has launched since creation. */

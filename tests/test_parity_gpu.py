@@ -113,6 +113,37 @@ def test_tier_x_baseline_shapes(ctx, builder, radius, far):
         ds.close()
 
 
+BOUNDARY_COUNTS = [0, 1, 2, 31, 32, 33, 34, 63, 64, 65, 95, 96, 97, 127, 128, 129, 255, 256, 257, 511, 512, 513, 514,
+                   1023, 1024, 1025, 2047, 2048, 2049, 3072]
+
+
+@pytest.mark.parametrize("variant", ["2", "1", "0"], ids=["warp-per-item", "tma-pipeline", "cta-per-item"])
+@pytest.mark.parametrize("fused", [False, True], ids=["two-calls", "fused"])
+def test_tier_x_list_length_boundaries(ctx, monkeypatch, variant, fused):
+    """Every hand-over point between the kernels: thread-per-list (<= 32 matrices), warp-per-list (33..512), work
+    items of 1024 (> 512), full and ragged last steps of 32, full and ragged last work items; for the three
+    long-list kernel variants."""
+    monkeypatch.setenv("CADR_B200_CULL_VARIANT", variant)
+    sc = synth.random_scene(51, n=4 * len(BOUNDARY_COUNTS) + 3, list_counts=BOUNDARY_COUNTS, state_sets=4, first_handle=2030)
+    ds = DeviceScene(ctx, sc)
+    try:
+        for frame in (10, 250):
+            planes, eye = synth.orbit_camera(frame, 250.0, far=500.0)
+            if fused:
+                ds.upload_drawable_list()
+                ds.process_and_cull(planes, eye)
+            else:
+                ds.record_drawable_processing()
+                ds.cull(planes, eye)
+            ctx.sync(ds.stream)
+            got = ds.read_tier_x()
+            _, _, ref = oracle_tier_x(sc, planes, eye, arena_base=ds.arena, list_base=ds.drawable_list)
+            assert_tier_x_equal(got, ref)
+            assert 0 < got["inst_count"].sum() < sc.total_instances
+    finally:
+        ds.close()
+
+
 def test_tier_x_all_visible_none_visible_and_idempotent(ctx):
     sc = synth.random_scene(21, big_lists=2, n=900, num_lists=80)
     big = 1e9
