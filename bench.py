@@ -48,7 +48,7 @@ from cadr_b200 import synth  # noqa: E402
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"])
@@ -107,7 +107,7 @@ class ClockSampler:
     def __init__(self, index: int):
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
@@ -384,7 +384,7 @@ def run_b200(args):
             tier_r.append(ctx.kernel_times()[0])
         ctx.set_profiling(False)
 
-    large_name = {"0": "cullLargeLdgKernel", "1": "cullLargeKernel"}.get(os.environ.get("CADR_B200_CULL_VARIANT", "2"), "cullListWarpKernel")
+    large_name = {"0": "cullLargeLdgKernel", "1": "cullLargeKernel", "3": "cullListRingKernel"}.get(os.environ.get("CADR_B200_CULL_VARIANT", "2"), "cullListWarpKernel")
     kt = np.array(ktimes)
     k_process, k_small, k_large = (float(kt[:, i].mean()) for i in range(3))
     p = float(np.mean(surv)) / inst

@@ -32,6 +32,7 @@ struct cadr_ctx {
 	uint64_t launches = 0;
 	bool profiling = false;
 	bool largeKernelConfigured = false;   // dynamic shared-memory opt-in of cullLargeKernel done on this device
+	bool ringKernelConfigured = false;    // same for cullListRingKernel
 	cudaEvent_t evBegin[cadr::KS_COUNT] = {};
 	cudaEvent_t evEnd[cadr::KS_COUNT] = {};
 	bool evUsed[cadr::KS_COUNT] = {};

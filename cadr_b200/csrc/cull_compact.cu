@@ -74,6 +74,7 @@ struct CullArgs {
 	uint32_t  chunkCapacity;
 	uint32_t  n;
 	uint32_t  numStateSets;
+	uint32_t  diagNoEval;                 // CADR_B200_DIAG_NOEVAL=1: list kernels skip the evaluation (memory-system ceiling of the access structure)
 	float4 plane[6];
 	float4 eye;
 	// fused multi-GPU exchange: gathered arrays of every rank (peer mappings), 0 ranks = write cmdOut/ptrOut/tagOut
@@ -123,13 +124,15 @@ __device__ __forceinline__ int evalInstance(const Mat& m, const LodInfo& L, cons
 
 	bool nonEmpty = b.w >= 0.f;             // radius < 0 (incl. -inf): empty sphere, never visible (:39-43)
 	bool visible = nonEmpty;
-	bool nearP = false;
+	// any_k |dot_k + r| < 1e-5  ==  min_k |dot_k + r| < 1e-5 (fminf skips a NaN term exactly like the comparison would)
+	float nearest = __int_as_float(0x7f800000);
 #pragma unroll
 	for(int k = 0; k < 6; k++) {
 		float dot = __fmaf_rn(plane[k].z, cz, __fmaf_rn(plane[k].y, cy, __fmaf_rn(plane[k].x, cx, plane[k].w)));
 		visible = visible && (dot >= -r);
-		nearP = nearP || (fabsf(__fadd_rn(dot, r)) < 1e-5f);
+		nearest = fminf(nearest, fabsf(__fadd_rn(dot, r)));
 	}
+	const bool nearP = nearest < 1e-5f;
 	float dx = __fadd_rn(cx, -eye.x), dy = __fadd_rn(cy, -eye.y), dz = __fadd_rn(cz, -eye.z);
 	float dist = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
 	int lod = 0;
@@ -224,6 +227,8 @@ __device__ __forceinline__ uint32_t warpInclusiveScan(uint32_t v, int lane)
 	}
 	return v;
 }
+
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
 // command + forwarded pointers + tag of one (drawable, lod[, item])
 __device__ __forceinline__ void writeCommandRecord(const CullArgs& A, uint32_t ci, uint32_t indexCount, uint32_t instanceCount,
@@ -484,13 +489,95 @@ __device__ __forceinline__ uint4 loadItemWord(const CullArgs& A, uint32_t item, 
 	return w;
 }
 
+// shared-memory accessors on 32-bit shared-window addresses (no generic-address conversion in the loops)
+__device__ __forceinline__ uint4 ldsU4(uint32_t addr)
+{
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ float4 ldsF4(uint32_t addr)
+{
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ void stsU4(uint32_t addr, uint4 v)
+{
+	asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// 2-bit code per step in a lane-private 64-bit history (32 steps = one work item): 0 = culled, 1 + lod otherwise
+__device__ __forceinline__ uint32_t histCount(unsigned long long h, uint32_t code)
+{
+	const unsigned long long lo = h & 0x5555555555555555ull, hi = (h >> 1) & 0x5555555555555555ull;
+	const unsigned long long m = (code == 1u) ? (lo & ~hi) : (code == 2u) ? (hi & ~lo) : (lo & hi);
+	return uint32_t(__popcll(m));
+}
+
+// Shared tail of the warp-per-item kernels: per-LOD totals from the lanes' histories, ONE 64-bit atomic to reserve the
+// item's command and index ranges, <= 3 command records (lanes 0..2), then the compacted indices, step by step, from
+// the histories (the matrices are not read again).  `desc` = shared-window address of the item's 128-byte descriptor.
+__device__ __forceinline__ void emitItem(const CullArgs& A, unsigned long long hist, uint32_t steps, uint32_t nb,
+                                         uint32_t desc, const uint4& a0, const uint4& a1, uint32_t lane)
+{
+	const unsigned FULL = 0xffffffffu;
+	const uint32_t lt = (1u << lane) - 1u;
+	const uint32_t t0 = __reduce_add_sync(FULL, histCount(hist, 1u)), t1 = __reduce_add_sync(FULL, histCount(hist, 2u)),
+	               t2 = __reduce_add_sync(FULL, histCount(hist, 3u));
+	if(__any_sync(FULL, nb != 0u)) {
+		nb = __reduce_add_sync(FULL, nb);
+		if(lane == 0) atomicAdd(&A.hdr->nearBandCount, nb);
+	}
+	const uint32_t nInst = t0 + t1 + t2, nCmd = (t0 ? 1u : 0u) + (t1 ? 1u : 0u) + (t2 ? 1u : 0u);
+	if(nInst == 0) return;   // warp-uniform
+	const uint32_t stateSet = a1.y;
+	unsigned long long base = 0;
+	uint4 reg = make_uint4(0, 0, 0, 0);
+	if(lane == 0) {
+		base = atomicAdd(A.counts + stateSet, (unsigned long long)nCmd | ((unsigned long long)nInst << 32));
+		reg = ldg_u4(reinterpret_cast<uint64_t>(A.regions + stateSet));
+	}
+	base = __shfl_sync(FULL, base, 0);
+	reg.x = __shfl_sync(FULL, reg.x, 0); reg.y = __shfl_sync(FULL, reg.y, 0);
+	reg.z = __shfl_sync(FULL, reg.z, 0); reg.w = __shfl_sync(FULL, reg.w, 0);
+	const uint32_t cOff = uint32_t(base), iOff = uint32_t(base >> 32);
+	if(cOff + nCmd > reg.y || iOff + nInst > reg.w) {
+		if(lane == 0) atomicOr(&A.hdr->status, CADR_CULL_STATUS_REGION_OVERFLOW);
+		return;
+	}
+	uint32_t i0 = reg.z + iOff, i1 = i0 + t0, i2 = i1 + t1;
+	if(lane < 3) {
+		const uint32_t tl = (lane == 0) ? t0 : (lane == 1) ? t1 : t2;
+		if(tl) {
+			// PrimitiveSets are words 4 and 5 of the descriptor, the pointers to forward words 6 and 7
+			const uint4 w4 = ldsU4(desc + 64u), w5 = ldsU4(desc + 80u);
+			const uint32_t psCount = (lane == 0) ? w4.x : (lane == 1) ? w4.z : w5.x;
+			const uint32_t psFirst = (lane == 0) ? w4.y : (lane == 1) ? w4.w : w5.y;
+			const uint32_t ci = reg.x + cOff + ((lane > 0 && t0) ? 1u : 0u) + ((lane > 1 && t1) ? 1u : 0u);
+			writeCommandRecord(A, ci, psCount, tl, psFirst, (lane == 0) ? i0 : (lane == 1) ? i1 : i2,
+			                   a1.x, lane, ldsU4(desc + 96u), ldsU4(desc + 112u));
+		}
+	}
+	uint32_t idx = a0.w + lane;     // firstInstance + lane
+	for(uint32_t s = 0; s < steps; s++, idx += 32u, hist >>= 2) {
+		const uint32_t c = uint32_t(hist) & 3u;
+		const unsigned b0 = __ballot_sync(FULL, c == 1u), b1 = __ballot_sync(FULL, c == 2u), b2 = __ballot_sync(FULL, c == 3u);
+		if(c == 1u) A.instOut[i0 + __popc(b0 & lt)] = idx;
+		if(c == 2u) A.instOut[i1 + __popc(b1 & lt)] = idx;
+		if(c == 3u) A.instOut[i2 + __popc(b2 & lt)] = idx;
+		i0 += __popc(b0); i1 += __popc(b1); i2 += __popc(b2);
+	}
+}
+
+constexpr int LW_DESCS = 4;     // descriptor ring per warp: items A, B, C and the slot being refilled
+
 __global__ void __launch_bounds__(CM_THREADS, 4)
 cullListWarpKernel(const __grid_constant__ CullArgs A)
 {
-	__shared__ int8_t sLodStrip[CM_THREADS / 32][CHUNK];
-	const int lane = threadIdx.x & 31;
-	int8_t* strip = sLodStrip[threadIdx.x >> 5];
-	const uint32_t lt = (1u << lane) - 1u;
+	__shared__ __align__(16) uint8_t sDescs[CM_THREADS / 32][LW_DESCS * sizeof(WorkItem)];
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t descs = smemAddr(sDescs[threadIdx.x >> 5]);
 	const unsigned FULL = 0xffffffffu;
 
 	uint32_t total = A.hdr->chunkCount;
@@ -499,8 +586,8 @@ cullListWarpKernel(const __grid_constant__ CullArgs A)
 	uint32_t batch = total / (numWarps * 16u);          // long queues: fewer atomics; short queues: best balance
 	batch = batch < 1u ? 1u : (batch > 8u ? 8u : batch);
 
-	// lane 0 owns the claimed index range [rNext, rEnd)
-	uint32_t rNext = 0, rEnd = 0;
+	// item indices: A (evaluated), B (descriptor in shared memory), C (descriptor in flight in dIn), D (being claimed)
+	uint32_t rNext = 0, rEnd = 0;      // lane 0: claimed index range
 	uint32_t iA, iB, iC;
 	{
 		const uint32_t first = batch < 3u ? 3u : batch;
@@ -509,107 +596,225 @@ cullListWarpKernel(const __grid_constant__ CullArgs A)
 		r = __shfl_sync(FULL, r, 0);
 		iA = r; iB = r + 1u; iC = r + 2u;
 	}
-	uint4 dA = loadItemWord(A, iA, total, lane);
-	uint4 dB = loadItemWord(A, iB, total, lane);
-
+	uint32_t seq = 0;                  // warp-local sequence number of A; its descriptor slot is seq & 3
+	uint4 dIn;
 	Mat cur, nxt;
 	{
-		const uint64_t m = uint64_t(__shfl_sync(FULL, dA.x, 0)) | (uint64_t(__shfl_sync(FULL, dA.y, 0)) << 32);
-		const uint32_t n = __shfl_sync(FULL, dA.z, 0);
-		if(uint32_t(lane) < n) cur = loadMat(reinterpret_cast<const uint8_t*>(m) + 64ull * lane);
+		const uint4 a = loadItemWord(A, iA, total, lane);
+		dIn = loadItemWord(A, iB, total, lane);       // stored to the ring at the top of the first iteration
+		if(lane < 8) stsU4(descs + lane * 16u, a);
+		const uint64_t m = uint64_t(__shfl_sync(FULL, a.x, 0)) | (uint64_t(__shfl_sync(FULL, a.y, 0)) << 32);
+		if(lane < __shfl_sync(FULL, a.z, 0)) cur = loadMat(reinterpret_cast<const uint8_t*>(m) + 64ull * lane);
 	}
 
 	while(iA < total) {
-		// ---- keep the pipeline full: descriptor of C, index of D -------------------------------------
-		const uint4 dC = loadItemWord(A, iC, total, lane);
+		// ---- descriptor pipeline: B has arrived, request C, claim D ------------------------------------
+		if(lane < 8) stsU4(descs + ((seq + 1u) & 3u) * 128u + lane * 16u, dIn);
+		dIn = loadItemWord(A, iC, total, lane);
 		uint32_t iD = 0;
 		if(lane == 0) {
 			if(rNext < rEnd) iD = rNext++;
 			else { iD = atomicAdd(&A.hdr->chunkCursor, batch); rNext = iD + 1u; rEnd = iD + batch; }
 		}
-		// ---- unpack A ----------------------------------------------------------------------------------
-		const uint8_t* matsA = reinterpret_cast<const uint8_t*>(uint64_t(__shfl_sync(FULL, dA.x, 0)) | (uint64_t(__shfl_sync(FULL, dA.y, 0)) << 32));
-		const uint32_t N = __shfl_sync(FULL, dA.z, 0), firstInstance = __shfl_sync(FULL, dA.w, 0);
+		__syncwarp();
+		const uint32_t dA = descs + (seq & 3u) * 128u;
+		const uint4 a0 = ldsU4(dA), a1 = ldsU4(dA + 16u), a2 = ldsU4(dA + 32u), a3 = ldsU4(dA + 48u);
+		const uint4 b0 = ldsU4(descs + ((seq + 1u) & 3u) * 128u);
 		LodInfo L;
-		L.lodCount = __shfl_sync(FULL, dA.z, 1);
-		L.sphere = make_float4(__uint_as_float(__shfl_sync(FULL, dA.x, 2)), __uint_as_float(__shfl_sync(FULL, dA.y, 2)),
-		                       __uint_as_float(__shfl_sync(FULL, dA.z, 2)), __uint_as_float(__shfl_sync(FULL, dA.w, 2)));
-		L.thr0 = __uint_as_float(__shfl_sync(FULL, dA.x, 3)); L.thr1 = __uint_as_float(__shfl_sync(FULL, dA.y, 3));
-		// first step of B (0 matrices when there is no B)
-		const uint8_t* matsB = reinterpret_cast<const uint8_t*>(uint64_t(__shfl_sync(FULL, dB.x, 0)) | (uint64_t(__shfl_sync(FULL, dB.y, 0)) << 32));
-		const uint32_t nB = __shfl_sync(FULL, dB.z, 0);
+		L.lodCount = a1.z;
+		L.sphere = make_float4(__uint_as_float(a2.x), __uint_as_float(a2.y), __uint_as_float(a2.z), __uint_as_float(a2.w));
+		L.thr0 = __uint_as_float(a3.x); L.thr1 = __uint_as_float(a3.y);
 
-		// ---- evaluate A, 32 matrices per step, next step (or B's first step) in flight -----------------
-		uint32_t t0 = 0, t1 = 0, t2 = 0, nb = 0;
-		for(uint32_t j0 = 0; j0 < N; j0 += 32) {
-			const uint32_t j = j0 + lane;
-			if(j0 + 32 < N) { if(j + 32 < N) nxt = loadMat(matsA + 64ull * (j + 32)); }
-			else if(uint32_t(lane) < nB) nxt = loadMat(matsB + 64ull * lane);
-			int lod = -1;
+		// ---- evaluate A, 32 matrices per step; the next step is in flight in registers -----------------
+		unsigned long long hist = 0;       // 2 bits per step, newest at the top
+		uint32_t nb = 0, steps = 1, left = a0.z;
+		const uint8_t* p = reinterpret_cast<const uint8_t*>(uint64_t(a0.x) | (uint64_t(a0.y) << 32)) + 64u * lane;
+		while(left > 32u) {                // full steps that have a successor inside A
+			if(lane + 32u < left) nxt = loadMat(p + 2048);
 			bool nbi = false;
-			if(j < N) lod = evalInstance(cur, L, A.plane, A.eye, nbi);
-			strip[j] = int8_t(lod);
-			t0 += __popc(__ballot_sync(FULL, lod == 0));
-			t1 += __popc(__ballot_sync(FULL, lod == 1));
-			t2 += __popc(__ballot_sync(FULL, lod == 2));
-			nb += __popc(__ballot_sync(FULL, nbi));
+			const int lod = A.diagNoEval ? ((cur.c0.x == 12345.f && cur.c2.x == 1.f) ? 0 : -1) : evalInstance(cur, L, A.plane, A.eye, nbi);
+			nb += nbi ? 1u : 0u;
+			hist = (hist >> 2) | ((unsigned long long)uint32_t(lod + 1) << 62);
+			steps++;
+			cur = nxt; p += 2048; left -= 32u;
+		}
+		{                                  // last step of A: the first step of B goes in flight
+			if(lane < b0.z) nxt = loadMat(reinterpret_cast<const uint8_t*>(uint64_t(b0.x) | (uint64_t(b0.y) << 32)) + 64u * lane);
+			uint32_t code = 0;
+			if(lane < left) {
+				bool nbi = false;
+				const int lod = A.diagNoEval ? ((cur.c0.x == 12345.f && cur.c2.x == 1.f) ? 0 : -1) : evalInstance(cur, L, A.plane, A.eye, nbi);
+				nb += nbi ? 1u : 0u;
+				code = uint32_t(lod + 1);
+			}
+			hist = (hist >> 2) | ((unsigned long long)code << 62);
 			cur = nxt;
 		}
-		if(N == 0 && uint32_t(lane) < nB) cur = loadMat(matsB + 64ull * lane);   // never queued; keeps the pipeline sound
+		hist >>= (64u - 2u * steps);       // step s now sits at bits [2s, 2s + 1]
 
-		// ---- reserve, emit commands, write the compacted indices ---------------------------------------
-		const uint32_t nInst = t0 + t1 + t2, nCmd = (t0 ? 1u : 0u) + (t1 ? 1u : 0u) + (t2 ? 1u : 0u);
-		if(lane == 0 && nb) atomicAdd(&A.hdr->nearBandCount, nb);
-		if(nInst) {   // warp-uniform
-			const uint32_t stateSet = __shfl_sync(FULL, dA.y, 1);
-			unsigned long long base = 0;
-			uint4 reg = make_uint4(0, 0, 0, 0);
-			if(lane == 0) {
-				base = atomicAdd(A.counts + stateSet, (unsigned long long)nCmd | ((unsigned long long)nInst << 32));
-				reg = ldg_u4(reinterpret_cast<uint64_t>(A.regions + stateSet));
-			}
-			base = __shfl_sync(FULL, base, 0);
-			reg.x = __shfl_sync(FULL, reg.x, 0); reg.y = __shfl_sync(FULL, reg.y, 0);
-			reg.z = __shfl_sync(FULL, reg.z, 0); reg.w = __shfl_sync(FULL, reg.w, 0);
-			const uint32_t cOff = uint32_t(base), iOff = uint32_t(base >> 32);
-			if(cOff + nCmd > reg.y || iOff + nInst > reg.w) {
-				if(lane == 0) atomicOr(&A.hdr->status, CADR_CULL_STATUS_REGION_OVERFLOW);
-			}
-			else {
-				uint32_t i0 = reg.z + iOff, i1 = i0 + t0, i2 = i1 + t1;
-				// lane l (< 3) emits the command of LOD l: PrimitiveSets are words 4 and 5, pointers words 6 and 7
-				const uint32_t drawable = __shfl_sync(FULL, dA.x, 1);
-				const uint4 w4 = make_uint4(__shfl_sync(FULL, dA.x, 4), __shfl_sync(FULL, dA.y, 4), __shfl_sync(FULL, dA.z, 4), __shfl_sync(FULL, dA.w, 4));
-				const uint2 w5 = make_uint2(__shfl_sync(FULL, dA.x, 5), __shfl_sync(FULL, dA.y, 5));
-				const uint4 p0 = make_uint4(__shfl_sync(FULL, dA.x, 6), __shfl_sync(FULL, dA.y, 6), __shfl_sync(FULL, dA.z, 6), __shfl_sync(FULL, dA.w, 6));
-				const uint4 p1 = make_uint4(__shfl_sync(FULL, dA.x, 7), __shfl_sync(FULL, dA.y, 7), __shfl_sync(FULL, dA.z, 7), __shfl_sync(FULL, dA.w, 7));
-				if(lane < 3) {
-					const uint32_t tl = (lane == 0) ? t0 : (lane == 1) ? t1 : t2;
-					if(tl) {
-						const uint32_t ci = reg.x + cOff + ((lane > 0 && t0) ? 1u : 0u) + ((lane > 1 && t1) ? 1u : 0u);
-						const uint32_t psCount = (lane == 0) ? w4.x : (lane == 1) ? w4.z : w5.x;
-						const uint32_t psFirst = (lane == 0) ? w4.y : (lane == 1) ? w4.w : w5.y;
-						writeCommandRecord(A, ci, psCount, tl, psFirst, (lane == 0) ? i0 : (lane == 1) ? i1 : i2,
-						                   drawable, uint32_t(lane), p0, p1);
-					}
-				}
-				__syncwarp();   // the strip was written by other lanes
-				for(uint32_t j0 = 0; j0 < N; j0 += 32) {
-					const uint32_t j = j0 + lane;
-					const int lod = (j < N) ? int(strip[j]) : -1;
-					const unsigned b0 = __ballot_sync(FULL, lod == 0), b1 = __ballot_sync(FULL, lod == 1), b2 = __ballot_sync(FULL, lod == 2);
-					if(lod == 0) A.instOut[i0 + __popc(b0 & lt)] = firstInstance + j;
-					if(lod == 1) A.instOut[i1 + __popc(b1 & lt)] = firstInstance + j;
-					if(lod == 2) A.instOut[i2 + __popc(b2 & lt)] = firstInstance + j;
-					i0 += __popc(b0); i1 += __popc(b1); i2 += __popc(b2);
-				}
-			}
-		}
-		__syncwarp();       // the strip is reused by the next item
+		emitItem(A, hist, steps, nb, dA, a0, a1, lane);
+		__syncwarp();       // A's descriptor slot is rewritten three iterations from now; keep the warp together
 
-		// ---- advance the pipeline ------------------------------------------------------------------------
-		dA = dB; dB = dC;
+		// ---- advance the pipeline: B becomes A ---------------------------------------------------------------
+		seq++;
 		iA = iB; iB = iC; iC = __shfl_sync(FULL, iD, 0);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the same stage with a warp-private shared-memory ring: matrices are staged by asynchronous copies
+// ---------------------------------------------------------------------------------------------------
+// cullListWarpKernel keeps ONE step (2 KiB) per warp in flight, in registers; 32 warps x 2 KiB = 64 KiB per SM is only
+// just what Little's law asks for at ~1.2 us of loaded DRAM latency, and a short item cannot look further ahead than
+// its own last step.  Here every warp owns a ring of LW_STAGES x 2 KiB in shared memory, filled with LDGSTS
+// (cp.async.cg, 16 B per lane, 512 contiguous bytes per instruction, no registers held) by a FETCH CURSOR that runs
+// up to LW_STAGES - 1 steps ahead of the evaluation, straight through item boundaries (as far as two items ahead:
+// descriptors A, B, C are unpacked, D is in flight, the index of E is being claimed).
+// Layout of a stage: matrix m occupies bytes [64 m, 64 m + 64); its 16-byte column c sits at slot c ^ ((m >> 1) & 3)
+// (the SWIZZLE_64B pattern), which makes both the asynchronous writes (lane l copies chunk k*32 + l) and the reads
+// (lane m reads its own four columns as LDS.128) hit every bank exactly once per quarter-warp, and needs no
+// un-rotation: the four read offsets of a lane are constants.
+constexpr int    LW_STAGES      = 3;
+constexpr int    LW_STAGE_BYTES = 32 * 64;
+constexpr size_t LW_WARP_BYTES  = LW_STAGES * LW_STAGE_BYTES + LW_DESCS * sizeof(WorkItem);   // 6.5 KiB
+constexpr size_t LW_SMEM_BYTES  = (CM_THREADS / 32) * LW_WARP_BYTES;          // 52 KiB per CTA, four CTAs per SM
+
+__device__ __forceinline__ void cpAsync16(uint32_t dstSmem, const uint8_t* src)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dstSmem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cpAsyncWaitAllBut(uint32_t pending)   // warp-uniform; the operand must be an immediate
+{
+	switch(pending) {
+	case 0:  asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+	case 1:  asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+	default: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+	}
+}
+static_assert(LW_STAGES <= 3, "cpAsyncWaitAllBut covers up to two pending groups");
+
+__global__ void __launch_bounds__(CM_THREADS, 4)
+cullListRingKernel(const __grid_constant__ CullArgs A)
+{
+	extern __shared__ __align__(128) uint8_t lwSmem[];
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t ring = smemAddr(lwSmem) + (threadIdx.x >> 5) * uint32_t(LW_WARP_BYTES);   // shared-window address of my ring
+	const uint32_t ringEnd = ring + LW_STAGES * LW_STAGE_BYTES;
+	const uint32_t descs = ringEnd;                                                         // LW_DESCS x 128 bytes
+	const uint32_t lt = (1u << lane) - 1u;
+	const unsigned FULL = 0xffffffffu;
+	// writer: chunk g = k*32 + lane -> matrix k*8 + (lane >> 2), column lane & 3, swizzle ((lane >> 3) & 3)
+	const uint32_t wrOff = (lane >> 2) * 64u + (((lane & 3u) ^ ((lane >> 3) & 3u)) << 4);
+	// reader: own matrix `lane`; column c sits at slot c ^ ((lane >> 1) & 3), i.e. at address (stage + rdOff) ^ (c << 4)
+	const uint32_t rdOff = lane * 64u + (((lane >> 1) & 3u) << 4);
+
+	uint32_t total = A.hdr->chunkCount;
+	if(total > A.chunkCapacity) total = A.chunkCapacity;
+	const uint32_t numWarps = gridDim.x * (CM_THREADS / 32);
+	uint32_t batch = total / (numWarps * 16u);
+	batch = batch < 1u ? 1u : (batch > 8u ? 8u : batch);
+
+	// item indices: A (evaluated), B, C (descriptors in shared memory), D (descriptor in flight in dIn), E (being claimed)
+	uint32_t rNext = 0, rEnd = 0;      // lane 0: claimed index range
+	uint32_t iA, iB, iC, iD;
+	{
+		const uint32_t first = batch < 4u ? 4u : batch;
+		uint32_t r = 0;
+		if(lane == 0) { r = atomicAdd(&A.hdr->chunkCursor, first); rNext = r + 4u; rEnd = r + first; }
+		r = __shfl_sync(FULL, r, 0);
+		iA = r; iB = r + 1u; iC = r + 2u; iD = r + 3u;
+	}
+	uint32_t seq = 0;                  // warp-local sequence number of A; its descriptor slot is seq & 3
+	{
+		const uint4 a = loadItemWord(A, iA, total, lane), b = loadItemWord(A, iB, total, lane);
+		if(lane < 8) { stsU4(descs + lane * 16u, a); stsU4(descs + 128u + lane * 16u, b); }
+	}
+	uint4 dIn = loadItemWord(A, iC, total, lane);     // stored to the ring at the top of the first iteration
+
+	// fetch cursor: fSeq = item it reads from (seq - 1: none yet), fRemain matrices of it not fetched yet, fSrc this
+	// lane's source of the next step, fDst / eAddr the ring slots written / read next
+	uint32_t fSeq = 0xffffffffu, fRemain = 0, inFlight = 0, fDst = ring, eAddr = ring;
+	const uint8_t* fSrc = nullptr;
+
+	while(iA < total) {
+		// ---- descriptor pipeline: C has arrived, request D, claim E ------------------------------------
+		if(lane < 8) stsU4(descs + ((seq + 2u) & 3u) * 128u + lane * 16u, dIn);
+		dIn = loadItemWord(A, iD, total, lane);
+		uint32_t iE = 0;
+		if(lane == 0) {
+			if(rNext < rEnd) iE = rNext++;
+			else { iE = atomicAdd(&A.hdr->chunkCursor, batch); rNext = iE + 1u; rEnd = iE + batch; }
+		}
+		__syncwarp();
+		const uint32_t dA = descs + (seq & 3u) * 128u;
+		const uint4 a0 = ldsU4(dA), a1 = ldsU4(dA + 16u), a2 = ldsU4(dA + 32u), a3 = ldsU4(dA + 48u);
+		const uint4 b0 = ldsU4(descs + ((seq + 1u) & 3u) * 128u), c0 = ldsU4(descs + ((seq + 2u) & 3u) * 128u);
+		const uint32_t N = a0.z, firstInstance = a0.w;
+		LodInfo L;
+		L.lodCount = a1.z;
+		L.sphere = make_float4(__uint_as_float(a2.x), __uint_as_float(a2.y), __uint_as_float(a2.z), __uint_as_float(a2.w));
+		L.thr0 = __uint_as_float(a3.x); L.thr1 = __uint_as_float(a3.y);
+
+		unsigned long long hist = 0;       // 2 bits per step, newest at the top: 0 = culled, 1 + lod otherwise
+		uint32_t nb = 0, steps = 0;
+		for(uint32_t left = N; left != 0; left = (left > 32u) ? left - 32u : 0u) {
+			// ---- top up the ring: the fetch cursor runs ahead through A, B and C -------------------------
+			while(inFlight < uint32_t(LW_STAGES)) {
+				if(fRemain == 0) {                              // (rare) move the cursor to the next item
+					const uint32_t which = fSeq + 1u - seq;     // 0 = A, 1 = B, 2 = C
+					if(which > 2u) break;                       // beyond C: not known yet
+					const uint4 w = (which == 0u) ? a0 : (which == 1u) ? b0 : c0;
+					if(w.z == 0u) break;                        // there is no further item
+					fSeq++; fRemain = w.z;
+					fSrc = reinterpret_cast<const uint8_t*>(uint64_t(w.x) | (uint64_t(w.y) << 32)) + 16u * lane;
+				}
+				const uint32_t dst = fDst + wrOff;
+				if(fRemain >= 32u) {
+					cpAsync16(dst, fSrc); cpAsync16(dst + 512u, fSrc + 512); cpAsync16(dst + 1024u, fSrc + 1024); cpAsync16(dst + 1536u, fSrc + 1536);
+					fRemain -= 32u;
+				}
+				else {
+					const uint32_t chunks = fRemain * 4u;       // 16-byte chunks of a ragged last step
+#pragma unroll
+					for(uint32_t k = 0; k < 4; k++)
+						if(k * 32u + lane < chunks) cpAsync16(dst + k * 512u, fSrc + k * 512u);
+					fRemain = 0;
+				}
+				cpAsyncCommit();
+				fSrc += LW_STAGE_BYTES;
+				fDst += LW_STAGE_BYTES; if(fDst == ringEnd) fDst = ring;
+				inFlight++;
+			}
+			// ---- the oldest stage in flight is this step ----------------------------------------------
+			if(inFlight == 3u)      asm volatile("cp.async.wait_group 2;" ::: "memory");
+			else if(inFlight == 2u) asm volatile("cp.async.wait_group 1;" ::: "memory");
+			else                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+			__syncwarp();                      // chunks of my matrix were copied by other lanes
+			uint32_t code = 0;
+			if(lane < left) {
+				const uint32_t ma = eAddr + rdOff;
+				Mat m;
+				m.c0 = ldsF4(ma); m.c1 = ldsF4(ma ^ 16u); m.c2 = ldsF4(ma ^ 32u); m.c3 = ldsF4(ma ^ 48u);
+				bool nbi = false;
+				const int lod = A.diagNoEval ? ((m.c0.x == 12345.f && m.c2.x == 1.f) ? 0 : -1) : evalInstance(m, L, A.plane, A.eye, nbi);
+				code = uint32_t(lod + 1);
+				nb += nbi ? 1u : 0u;
+			}
+			hist = (hist >> 2) | ((unsigned long long)code << 62);
+			steps++;
+			__syncwarp();                      // every lane has read the slot before any lane refills it
+			eAddr += LW_STAGE_BYTES; if(eAddr == ringEnd) eAddr = ring;
+			inFlight--;
+		}
+		if(steps) hist >>= (64u - 2u * steps);      // step s now sits at bits [2s, 2s + 1]
+
+		emitItem(A, hist, steps, nb, dA, a0, a1, lane);
+		__syncwarp();       // A's descriptor slot is rewritten two iterations from now; keep the warp together
+
+		// ---- advance the pipeline: B becomes A ---------------------------------------------------------------
+		seq++;
+		iA = iB; iB = iC; iC = iD; iD = __shfl_sync(FULL, iE, 0);
 	}
 }
 
@@ -635,7 +840,6 @@ static_assert(sizeof(TpStage) % 128 == 0, "stage alignment");
 constexpr size_t TP_SMEM_BYTES = TP_STAGES * sizeof(TpStage) + 2 * TP_STAGES * sizeof(uint64_t);
 static_assert(TP_SMEM_BYTES <= 227 * 1024, "shared memory budget of one CTA");
 
-__device__ __forceinline__ uint32_t smemAddr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count)
 {
 	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smemAddr(bar)), "r"(count) : "memory");
@@ -967,7 +1171,8 @@ cullLargeLdgKernel(const __grid_constant__ CullArgs A)
 static int cullVariant()
 {
 	const char* v = std::getenv("CADR_B200_CULL_VARIANT");
-	return v ? std::atoi(v) : 2;   // 2 = warp per work item (default), 1 = TMA pipeline, 0 = first direct-load version
+	return v ? std::atoi(v) : 2;   // 2 = warp per item, register prefetch (default); 3 = warp per item, shared-memory ring;
+	                               // 1 = CTA-wide TMA pipeline; 0 = first direct-load version
 }
 
 int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, bool fused)
@@ -1020,6 +1225,7 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 	A.numStateSets = p.numStateSets;
 	for(int k = 0; k < 6; k++) A.plane[k] = make_float4(p.planes[k][0], p.planes[k][1], p.planes[k][2], p.planes[k][3]);
 	A.eye = make_float4(p.eye[0], p.eye[1], p.eye[2], 0.f);
+	{ const char* dg = std::getenv("CADR_B200_DIAG_NOEVAL"); A.diagNoEval = (dg && dg[0] == '1') ? 1u : 0u; }
 	A.xWorld = exchange ? p.exchangeWorld : 0;
 	A.xSlotBase = exchange ? p.exchangeRank * p.exchangeCmdCapacity : 0;
 	for(uint32_t r = 0; r < CADR_MAX_PEERS; r++) {
@@ -1061,6 +1267,16 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 			const uint32_t need = (p.chunkCapacity + CM_THREADS / 32 - 1) / (CM_THREADS / 32);
 			if(gridL > need) gridL = need;
 			cullListWarpKernel<<<gridL, CM_THREADS, 0, s>>>(A);
+		}
+		else if(variant == 3) {
+			if(!ctx->ringKernelConfigured) {
+				CADR_CUDA(cudaFuncSetAttribute(cullListRingKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LW_SMEM_BYTES)));
+				ctx->ringKernelConfigured = true;
+			}
+			uint32_t gridL = uint32_t(ctx->smCount) * 4u;   // persistent warps: four CTAs of eight warps (52 KiB of rings each) per SM
+			const uint32_t need = (p.chunkCapacity + CM_THREADS / 32 - 1) / (CM_THREADS / 32);
+			if(gridL > need) gridL = need;
+			cullListRingKernel<<<gridL, CM_THREADS, LW_SMEM_BYTES, s>>>(A);
 		}
 		else {
 			if(!ctx->largeKernelConfigured) {   // per device (a process may hold one context per GPU)
