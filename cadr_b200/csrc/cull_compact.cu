@@ -16,6 +16,8 @@
 //                       the last 32-matrix step of an item already loads the first step of the next one, so no
 //                       dependent load and no atomic round trip is ever waited for in front of a matrix load.
 //                       Default for every list longer than 32 matrices.
+//   cullListRingKernel  the same with a warp-private shared-memory ring filled by asynchronous copies (LDGSTS) three
+//                       steps ahead (CADR_B200_CULL_VARIANT=3): higher memory-side ceiling, but issue-bound.
 //   cullLargeKernel     the same stage as a warp-specialised TMA pipeline (CADR_B200_CULL_VARIANT=1): persistent,
 //                       one CTA per SM; a producer lane streams each item's descriptor + up to 64 KiB of matrices
 //                       into a 3-stage shared-memory ring with TMA bulk copies (cp.async.bulk ...
@@ -39,7 +41,7 @@ constexpr uint32_t SMALL_MAX  = CADR_CULL_SMALL_LIST_MAX;        // lists up to 
 constexpr uint32_t CHUNK      = CADR_CULL_WORK_ITEM_INSTANCES;   // instances per work item of the list kernels
 constexpr int      CS_THREADS = 256;
 
-// Self-contained work item of the large-list kernel: 128 bytes, written by cullSmallKernel.
+// Self-contained work item of the list kernels: 128 bytes, written by cullSmallKernel.
 struct __align__(16) WorkItem {
 	uint64_t matrices;        // device address of the item's first matrix
 	uint32_t count;           // 1..CHUNK matrices (0xffffffff in shared memory: end of work)
@@ -466,20 +468,24 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 // ---------------------------------------------------------------------------------------------------
 // lists longer than 32 matrices: persistent warps, one work item per warp at a time, pipelined across items
 // ---------------------------------------------------------------------------------------------------
-// Per step a warp reads 32 consecutive matrices as 256-bit loads (2 KiB, full 32-byte sectors) and already has the
-// next step in flight; LODs are parked in a warp-private shared-memory strip; per-LOD counts come from
-// __ballot_sync/__popc; ONE 64-bit atomic per item reserves both output ranges; a second pass over the strip (not
-// over the matrices) writes the compacted indices coalesced.
+// Per step a warp reads 32 consecutive matrices as 256-bit loads (LDG.E.256: 2 KiB, full 32-byte sectors) and already
+// has the next step in flight in registers.  A lane records what it decided for its matrix of each step as a 2-bit
+// code in a private 64-bit history (32 steps = one work item), so the step loop has no shared-memory traffic and no
+// votes; per-LOD totals come from population counts of the histories + one warp reduction per item; ONE 64-bit atomic
+// per item reserves both output ranges; a second pass over the histories (not over the matrices) writes the compacted
+// indices coalesced.
 //
-// What keeps short items (33..200 matrices) at bandwidth is the pipeline ACROSS items.  Each warp always knows
+// What keeps short items (33..200 matrices) near bandwidth is the pipeline ACROSS items.  Each warp always knows
 //   item A  being evaluated (its first step was loaded during the previous item),
-//   item B  descriptor in registers (requested one item ago): the LAST step of A issues B's first matrix loads, so
-//           they are in flight while A's atomic, command records and index write-out happen,
-//   item C  descriptor just requested,   item D  index being claimed (atomic issued, consumed next iteration),
+//   item B  descriptor in the warp's shared-memory ring (requested one item ago): the LAST step of A issues B's first
+//           matrix loads, so they are in flight while A's atomic, command records and index write-out happen,
+//   item C  descriptor requested (one 16-byte word per lane, lanes 0..7),   item D  index being claimed,
 // so neither the queue atomic, nor the descriptor fetch, nor the output reservation sits in front of a matrix load.
-// A descriptor lives as ONE 16-byte word per lane (lanes 0..7 hold words 0..7 of the 128-byte item) and is unpacked
-// with shuffles.  Items are claimed in batches (1..8 per atomic, more when the queue is long) so that a queue of
-// millions of short items is not limited by same-address atomic throughput.
+// Items are claimed in batches (1..8 per atomic, more when the queue is long) so that a queue of millions of short
+// items is not limited by same-address atomic throughput.
+// Measured (100 M instances, one B200, G instances/s for the whole frame), lists of 33 / 64 / 100 / 200 / 500 / 1000:
+// 46 / 76 / 81 / 92 / 97 / 99; the two-queue predecessor (cullMidKernel + cullLargeWarpKernel) did 31 / 29 / - / 83 /
+// 95 / 100.
 constexpr int CM_THREADS = 256;
 
 __device__ __forceinline__ uint4 loadItemWord(const CullArgs& A, uint32_t item, uint32_t total, int lane)
@@ -669,11 +675,15 @@ cullListWarpKernel(const __grid_constant__ CullArgs A)
 // its own last step.  Here every warp owns a ring of LW_STAGES x 2 KiB in shared memory, filled with LDGSTS
 // (cp.async.cg, 16 B per lane, 512 contiguous bytes per instruction, no registers held) by a FETCH CURSOR that runs
 // up to LW_STAGES - 1 steps ahead of the evaluation, straight through item boundaries (as far as two items ahead:
-// descriptors A, B, C are unpacked, D is in flight, the index of E is being claimed).
+// descriptors A, B, C are in shared memory, D is in flight, the index of E is being claimed).
 // Layout of a stage: matrix m occupies bytes [64 m, 64 m + 64); its 16-byte column c sits at slot c ^ ((m >> 1) & 3)
 // (the SWIZZLE_64B pattern), which makes both the asynchronous writes (lane l copies chunk k*32 + l) and the reads
 // (lane m reads its own four columns as LDS.128) hit every bank exactly once per quarter-warp, and needs no
-// un-rotation: the four read offsets of a lane are constants.
+// un-rotation: a lane's four read addresses are (stage + constant) ^ (c << 4).
+// Measured: with the evaluation stubbed out (CADR_B200_DIAG_NOEVAL=1) this structure streams C3 in 0.91 ms (7.1 TB/s,
+// the register kernel: 0.96-0.98 ms), but the copies and shared-memory reads cost ~45 more instructions per step and
+// the full kernel becomes issue-bound (ncu: issue slots 73 % busy vs 51 %): 1.00-1.01 ms against 0.99 ms.  Selectable
+// with CADR_B200_CULL_VARIANT=3; not the default.
 constexpr int    LW_STAGES      = 3;
 constexpr int    LW_STAGE_BYTES = 32 * 64;
 constexpr size_t LW_WARP_BYTES  = LW_STAGES * LW_STAGE_BYTES + LW_DESCS * sizeof(WorkItem);   // 6.5 KiB
