@@ -132,6 +132,10 @@ SYMBOLS = {
     "cadr_b200_ipc_export": (C.c_int, [_P, C.c_uint64, C.c_char_p]),
     "cadr_b200_ipc_import": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_uint64)]),
     "cadr_b200_ipc_close": (C.c_int, [_P, C.c_uint64]),
+    "cadr_b200_external_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_size_t)]),
+    "cadr_b200_external_export_fd": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_int)]),
+    "cadr_b200_external_import_fd": (C.c_int, [_P, C.c_int, C.c_size_t, C.POINTER(C.c_uint64)]),
+    "cadr_b200_external_free": (C.c_int, [_P, C.c_uint64]),
     "cadr_b200_exchange_publish": (C.c_int, [_P, C.POINTER(ExchangeSync), _P]),
     "cadr_b200_exchange_wait": (C.c_int, [_P, C.POINTER(ExchangeSync), _P]),
     "cadr_b200_consume_check": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
@@ -303,6 +307,26 @@ class Context:
 
     def ipc_close(self, addr: int) -> None:
         check(self._l.cadr_b200_ipc_close(self._h, addr))
+
+    # -- export to a Vulkan consumer / another process
+    def external_alloc(self, nbytes: int) -> tuple[int, int]:
+        """-> (device address, allocated bytes): a buffer that can be exported as a POSIX fd."""
+        a, n = C.c_uint64(), C.c_size_t()
+        check(self._l.cadr_b200_external_alloc(self._h, nbytes, C.byref(a), C.byref(n)))
+        return a.value, n.value
+
+    def external_export_fd(self, addr: int) -> int:
+        fd = C.c_int(-1)
+        check(self._l.cadr_b200_external_export_fd(self._h, addr, C.byref(fd)))
+        return fd.value
+
+    def external_import_fd(self, fd: int, allocated_bytes: int) -> int:
+        a = C.c_uint64()
+        check(self._l.cadr_b200_external_import_fd(self._h, fd, allocated_bytes, C.byref(a)))
+        return a.value
+
+    def external_free(self, addr: int) -> None:
+        check(self._l.cadr_b200_external_free(self._h, addr))
 
     def exchange_publish(self, sync: "ExchangeSync", stream: int = 0) -> None:
         check(self._l.cadr_b200_exchange_publish(self._h, C.byref(sync), _P(stream)))

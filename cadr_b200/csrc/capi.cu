@@ -118,6 +118,7 @@ void cadr_b200_destroy(cadr_ctx* ctx)
 	if(ctx->device >= 0) {
 		cudaSetDevice(ctx->device);
 		cudaStreamSynchronize(ctx->stream);
+		while(!ctx->externals.empty()) cadr_b200_external_free(ctx, ctx->externals.begin()->first);
 		for(auto& a : ctx->arenas) cudaFree(reinterpret_cast<void*>(a.first));
 		for(auto& h : ctx->hostBlocks) cudaFreeHost(h.first);
 		if(ctx->devScratch) cudaFree(ctx->devScratch);

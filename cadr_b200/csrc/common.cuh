@@ -41,6 +41,10 @@ struct cadr_ctx {
 	std::map<uint64_t, size_t> arenas;
 	uint64_t fakeNext = 0x7f0000000000ull;  // address-space-only bump pointer
 
+	// exportable buffers of external.cu (address -> driver allocation handle, mapped size)
+	struct External { unsigned long long handle; size_t bytes; };
+	std::map<uint64_t, External> externals;
+
 	// pinned host blocks (ptr -> size)
 	std::map<void*, size_t> hostBlocks;
 

@@ -307,6 +307,24 @@ CADR_API int  cadr_b200_exchange_publish(cadr_ctx* ctx, const cadr_exchange_sync
 /* Block the stream (not the host) until every peer's flag in the LOCAL flag array has reached frameSeq. */
 CADR_API int  cadr_b200_exchange_wait(cadr_ctx* ctx, const cadr_exchange_sync* sync, cadr_stream stream);
 
+/* ---- export to a Vulkan consumer or another process (optional in north_star) ------------------- */
+
+/* A device buffer whose memory can be handed out as a POSIX file descriptor (CUDA virtual-memory API: cuMemCreate with
+ * an exportable handle type, mapped read/write on the context's device).  Usable wherever an arena_alloc address is
+ * (e.g. as cmdOut / instOut / counters of cadr_b200_cull_compact).  allocatedBytes (>= bytes, a multiple of the
+ * allocation granularity, 2 MiB on B200) is the size the importer has to state.
+ * Counterpart in the reference: the opaque-fd sharing of examples/OpenGLInteroperability/main.cpp:644-651 (export)
+ * and :1488-1490 (import), in the other direction: a Vulkan consumer imports the descriptor with
+ * VkImportMemoryFdInfoKHR{ handleType = VK_EXTERNAL_MEMORY_HANDLE_TYPE_OPAQUE_FD_BIT, fd } + VkMemoryAllocateInfo{
+ * allocationSize = allocatedBytes } and binds a VkBuffer (INDIRECT_BUFFER | STORAGE_BUFFER | SHADER_DEVICE_ADDRESS). */
+CADR_API int  cadr_b200_external_alloc(cadr_ctx* ctx, size_t bytes, uint64_t* devAddr, size_t* allocatedBytes);
+/* A new descriptor for the buffer; the caller owns it (a successful Vulkan import takes ownership, otherwise close()). */
+CADR_API int  cadr_b200_external_export_fd(cadr_ctx* ctx, uint64_t devAddr, int* fd);
+/* Map a buffer exported by another context or process (a CUDA consumer; also what the tests use, since no Vulkan ICD
+ * exists on the test machines).  The descriptor stays the caller's.  Release with cadr_b200_external_free. */
+CADR_API int  cadr_b200_external_import_fd(cadr_ctx* ctx, int fd, size_t allocatedBytes, uint64_t* devAddr);
+CADR_API int  cadr_b200_external_free(cadr_ctx* ctx, uint64_t devAddr);
+
 /* Size of the counters buffer for `numStateSets` StateSets. */
 CADR_API size_t cadr_b200_cull_counters_bytes(uint32_t numStateSets);
 

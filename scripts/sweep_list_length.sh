@@ -1,11 +1,11 @@
 #!/bin/bash
 # Frame rate as a function of MatrixList length at a fixed 100 M instances (one bench.py line per length).
-# usage: scripts/sweep_list_length.sh <tag> [lengths...]   -> gpurun_out/sweep_<tag>.jsonl
+# usage: [TOTAL=instances] scripts/sweep_list_length.sh <tag> [lengths...]   -> gpurun_out/sweep_<tag>.jsonl
 tag=$1; shift
 lens=${@:-"2 8 16 32 33 48 64 100 200 500 1000 5000"}
 out=gpurun_out/sweep_$tag.jsonl; : > $out
 for n in $lens; do
-  d=$(( 100000000 / n ))
+  d=$(( ${TOTAL:-100000000} / n ))
   python bench.py --workload c3 --instances $n --drawables $d --steps 30 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 >> $out
 done
 python - "$out" <<'PY'
