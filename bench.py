@@ -7,10 +7,11 @@ VkDrawIndexedIndirectCommand lists (Tier X), through the C ABI of libcadr_b200.s
 
   value     device-resident: drawable list, matrices, tables already in HBM; CUDA events on the launching
             stream around exactly K steps; max over ranks.
-  e2e       the same frame through the host-buffer entry point (cadr_b200_record_drawable_processing: DMA of the
-            48 B/drawable list from pinned host memory every frame, as Renderer::recordDrawableProcessing does)
-            plus a device->host read of the per-StateSet counters every frame.
-  roofline  dominant kernel (cullLargeKernel for C3, cullSmallKernel for C2): algorithmic bytes per launch
+  e2e       the same frame with host buffers: DMA of the 48 B/drawable list from pinned host memory every frame (what
+            Renderer::recordDrawableProcessing does, Renderer.cpp:635-644; double-buffered, so frame k+1's list crosses
+            PCIe while frame k is culled), the fused process+cull call, and a device->host read of the per-StateSet
+            counters that the host waits for every frame.
+  roofline  dominant kernel (cullListWarpKernel for C3, cullSmallKernel for C2): algorithmic bytes per launch
             ((64 + 4p) B per instance, SURVEY §8d / DESIGN.md) / mean launch duration from CUDA events
             recorded around that kernel inside the library, against MEASURED_PEAKS.json:hbm_gbs.
   cpu_baseline / --impl reference
@@ -174,7 +175,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
+    steps, warmup = max(1, min(args.steps, 1000)), max(1, min(args.warmup, 10))      # ~16 ms of 16 cores per step
     value, desc, threads, sec = cpu_sample_run(args, steps, warmup)
     line = {
         "impl": "reference", "metric": "culled+emitted instances/sec", "value": round(value / 1e6, 3), "unit": "M instances/s",
@@ -308,10 +309,23 @@ def run_b200(args):
     counters_host = torch.empty(ds.counters_bytes, dtype=torch.uint8).pin_memory()
     counters_dev = arena.tensor(ds.counters)
 
+    # e2e: every frame DMAs the 48 B/drawable list from pinned host memory (Renderer.cpp:635-644), culls, and reads the
+    # counters back.  Frames are pipelined the way a renderer with two frames in flight does it: the list of frame k+1
+    # crosses PCIe on a copy stream into the other of two device buffers while frame k is being culled.
+    copy_t = torch.cuda.Stream(device=dev)
+    lists = [ds.drawable_list, arena.alloc(ds.capacity * 48)]
+    list_ready = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def upload_list(k):
+        ctx.memcpy_h2d(lists[k % 2], ds.host_list_ptr, scene.n * 48, stream=copy_t.cuda_stream)
+        list_ready[k % 2].record(copy_t)
+
     def step_e2e(k):
+        stream_t.wait_event(list_ready[k % 2])
+        ds.drawable_list = lists[k % 2]
+        upload_list(k + 1)             # frame k-1, the last reader of that buffer, was synchronised below
         if rewrite is not None:        # Renderer::executeCopyOperations: pinned host staging -> device ranges (PCIe)
             ctx.upload(rewrite["regions"][k % 16], rewrite["stage_host"], stream=stream)
-        ds.upload_drawable_list()                 # pinned host list -> device, 48 B/drawable (Renderer.cpp:635-644)
         run_cull(k, True)
         counters_host.copy_(counters_dev, non_blocking=True)
         stream_t.synchronize()                    # the host consumes the counts every frame
@@ -357,10 +371,15 @@ def run_b200(args):
 
         ms_cull_only = timed(lambda k: step_device(k, with_exchange=False), args.steps) if world > 1 else ms_total
 
+        upload_list(0)
         for k in range(3):
             step_e2e(k)
         e2e_steps = args.steps if rewrite is None else min(args.steps, 50)    # c4 moves 640 MB over PCIe per step
+        copy_t.synchronize()
+        upload_list(args.warmup)       # timed() numbers its steps from args.warmup
         ms_e2e = timed(step_e2e, e2e_steps)
+        copy_t.synchronize()
+        ds.drawable_list = lists[0]    # lists[0] is the buffer DeviceScene owns (and the one the kernel profile below reads)
 
         # per-kernel durations (CUDA events recorded by the library around each of its kernels)
         ctx.set_profiling(True)
@@ -455,7 +474,7 @@ def run_b200(args):
         line["exchange"] = ("fused: cull kernels store records into every rank's gathered arrays over NVLink peer mappings (no collective call)"
                             if px is not None else f"NCCL all_gather_into_tensor of {ex.bytes_per_rank} padded bytes per rank after the cull")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, desc, threads, _ = cpu_sample_run(args, 5, 1)
+        v, desc, threads, _ = cpu_sample_run(args, 40, 2)
         line["cpu_baseline"] = {"value": round(v / 1e6, 3), "unit": "M instances/s", "cores": threads, "kind": "port", "sample": desc}
     if rank == 0:
         print(json.dumps(line))
@@ -463,6 +482,7 @@ def run_b200(args):
         px.close()
     if rewrite is not None:
         ctx.host_free(rewrite["stage_host"])
+    arena.free(lists[1])
     ds.close()
     ctx.close()
     if world > 1:

@@ -147,7 +147,7 @@ __device__ __forceinline__ int evalInstance(const Mat& m, const LodInfo& L, cons
 
 // Two instances at once with Blackwell's packed fp32 pipe (FFMA2 / FADD2 / FMUL2, sm_100): every component of a
 // packed operation is the same IEEE-754 operation evalInstance() performs, so results are bit-identical; the FP
-// instruction count per instance halves.  Used by the large-list kernel, where each lane owns two instances.
+// instruction count per instance halves.  Used by the TMA pipeline kernel (cullLargeKernel), where each lane owns two instances.
 __device__ __forceinline__ void evalInstancePair(const Mat& a, const Mat& b, const LodInfo& L, const float4 (&plane)[6],
                                                  const float4& eye, int& lodA, int& lodB, bool& nearA, bool& nearB)
 {
