@@ -306,29 +306,35 @@ def run_b200(args):
             ctx.scatter_copy(rewrite["regions"][k % 16], rewrite["stage_dev"], stream=stream)
         run_cull(k, with_exchange)
 
-    counters_host = torch.empty(ds.counters_bytes, dtype=torch.uint8).pin_memory()
     counters_dev = arena.tensor(ds.counters)
 
     # e2e: every frame DMAs the 48 B/drawable list from pinned host memory (Renderer.cpp:635-644), culls, and reads the
-    # counters back.  Frames are pipelined the way a renderer with two frames in flight does it: the list of frame k+1
-    # crosses PCIe on a copy stream into the other of two device buffers while frame k is being culled.
+    # counters back to the host.  Two frames are in flight, as in a renderer that records frame k while frame k-1
+    # executes: the list of frame k+1 crosses PCIe on a copy stream into the other of two device buffers while frame k
+    # is culled, and the host waits for (and consumes) the counters of frame k-1 after it has queued frame k.
     copy_t = torch.cuda.Stream(device=dev)
     lists = [ds.drawable_list, arena.alloc(ds.capacity * 48)]
     list_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    frame_done = [torch.cuda.Event(), torch.cuda.Event()]
+    counters_host = [torch.empty(ds.counters_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    consumed = [0]
 
     def upload_list(k):
+        copy_t.wait_event(frame_done[k % 2])      # frame k-2 was the last reader of this buffer
         ctx.memcpy_h2d(lists[k % 2], ds.host_list_ptr, scene.n * 48, stream=copy_t.cuda_stream)
         list_ready[k % 2].record(copy_t)
 
     def step_e2e(k):
         stream_t.wait_event(list_ready[k % 2])
         ds.drawable_list = lists[k % 2]
-        upload_list(k + 1)             # frame k-1, the last reader of that buffer, was synchronised below
         if rewrite is not None:        # Renderer::executeCopyOperations: pinned host staging -> device ranges (PCIe)
             ctx.upload(rewrite["regions"][k % 16], rewrite["stage_host"], stream=stream)
         run_cull(k, True)
-        counters_host.copy_(counters_dev, non_blocking=True)
-        stream_t.synchronize()                    # the host consumes the counts every frame
+        counters_host[k % 2].copy_(counters_dev, non_blocking=True)
+        frame_done[k % 2].record(stream_t)
+        upload_list(k + 1)
+        frame_done[(k + 1) % 2].synchronize()     # frame k-1: the host consumes its counts now
+        consumed[0] += int(counters_host[(k + 1) % 2][0])   # status word of that frame (0 when nothing overflowed)
 
     def barrier():
         torch.cuda.synchronize()
