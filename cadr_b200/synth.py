@@ -506,6 +506,37 @@ def config1(boxes_per_side: int = 100, seed: int = 1) -> Scene:
                        lod_threshold=np.zeros((n, 2), np.float32), matrices=mats, seed=seed, gen=dict(kind="c1"))
 
 
+def config1_instanced(boxes_per_side: int = 100, seed: int = 1) -> Scene:
+    """RenderingPerformance InstancedBoxesScene (Tests.cpp:863-880, generateBoxesScene with instanced = singleGeometry =
+    true): ONE drawable, one geometry, one MatrixList holding every box transform (100^3 = 1 M matrices) — the
+    instancing extreme next to config1.  The matrices are the same grid as config1's."""
+    m = boxes_per_side
+    n = m ** 3
+    dist = np.float32(9.72)
+    origin = -dist * np.float32(m - 1) / 2
+    idx = np.arange(n)
+    i, j, k = idx % m, (idx // m) % m, idx // (m * m)
+    pos = np.stack([origin + i * dist, origin + j * dist, origin + k * dist], axis=1).astype(np.float32)
+    mats = trs_matrices(pos, None, np.ones(n, np.float32))
+    geo = dict(count=1, **_box_geometry(False))
+    sphere = np.array([[0, 0, 0, BOX_SPHERE_RADIUS]], dtype=np.float32)
+    return build_scene(f"C1-instanced:{m}^3", geometries=geo, ml_count=np.array([n], np.uint32), drawable_geom=np.zeros(1, np.int64),
+                       drawable_ml=np.zeros(1, np.int64), drawable_ps_offset=np.zeros(1, np.uint64), state_set=np.zeros(1, np.uint32),
+                       sphere=sphere, lod_count=np.ones(1, np.uint32), lod_ps_offset=np.zeros((1, 3), np.uint32),
+                       lod_threshold=np.zeros((1, 2), np.float32), matrices=mats, seed=seed, gen=dict(kind="c1i"))
+
+
+def reference_camera(frame: int):
+    """The camera of examples/RenderingPerformance (main.cpp:936-946,1416-1421): orthographic LH, depth 0..1,
+    l/r = -/+960, b/t = -/+540, near 0.5, far 100, eye (x, 0, -50) looking at (x, 0, 0), up (0, -1, 0), x alternating
+    1, 0 with the frame number.  -> (planes, eye)"""
+    x = float(frame & 1)
+    eye = np.array([x, 0.0, -50.0])
+    view = look_at_lh(eye, (x, 0.0, 0.0), (0.0, -1.0, 0.0))
+    proj = ortho_lh_zo(-960.0, 960.0, -540.0, 540.0, 0.5, 100.0)
+    return frustum_planes(proj, view), eye.astype(np.float32)
+
+
 def random_scene(seed: int, n: int = 300, num_geometries: int = 7, num_lists: int = 50, max_count: int = 70,
                  state_sets: int = 5, first_handle: int = 1, force_level: int = 0, big_lists: int = 0,
                  with_drawable_data: bool = True, cube: float = 400.0, valid_geometry: bool = False,

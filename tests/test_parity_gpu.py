@@ -144,6 +144,31 @@ def test_tier_x_list_length_boundaries(ctx, monkeypatch, variant, fused):
         ds.close()
 
 
+@pytest.mark.parametrize("side", [36, 100], ids=["46k", "1M-as-in-the-reference"])
+def test_reference_instanced_boxes_scene_and_camera(ctx, side):
+    """RenderingPerformance InstancedBoxesScene (one drawable, one list of side^3 matrices; 100^3 in the reference)
+    under the example's own orthographic camera: Tier R record + culled result against the oracle; the list spans
+    46 / 977 work items."""
+    sc = synth.config1_instanced(side)
+    ds = DeviceScene(ctx, sc)
+    try:
+        for frame in (0, 1):
+            planes, eye = synth.reference_camera(frame)
+            ds.record_drawable_processing()
+            ds.cull(planes, eye)
+            ctx.sync(ds.stream)
+            ind, ptr = ds.read_tier_r()
+            got = ds.read_tier_x()
+            e_ind, e_ptr, ref = oracle_tier_x(sc, planes, eye, arena_base=ds.arena, list_base=ds.drawable_list)
+            assert np.array_equal(ind, e_ind) and np.array_equal(ptr, e_ptr)
+            assert ind[0, 1] == side ** 3 and ind[0, 0] == 36                # instanceCount, vertexCount of the box
+            assert_tier_x_equal(got, ref)
+            # the ortho volume is 100 deep and the grid 340 wide: a slab of the boxes survives
+            assert 0 < got["inst_count"].sum() < sc.total_instances
+    finally:
+        ds.close()
+
+
 def test_tier_x_all_visible_none_visible_and_idempotent(ctx):
     sc = synth.random_scene(21, big_lists=2, n=900, num_lists=80)
     big = 1e9
