@@ -155,3 +155,33 @@ def test_c2_full_size_10m_drawables(ctx):
             assert sample_check(ctx, ds, arena, scene, planes, eye, a, sample) >= 300
     finally:
         ds.close()
+
+
+def test_c1_full_size_independent_boxes_tier_r_and_cull(ctx):
+    """BASELINE configs[0] at the reference's size: RenderingPerformance IndependentBoxesScene, 100^3 = 1 M drawables,
+    1 M geometries, 1 M one-matrix lists, 4 000 000 handles (level 2), the example's orthographic camera.  Tier R is
+    compared record by record with the oracle (all 1 M); the culled frame through counts and index checksums."""
+    from helpers import oracle_tier_x
+    sc = synth.config1(100)
+    assert sc.n == 1_000_000 and sc.handle_level == 2 and sc.num_handles == 4_000_000
+    ds = DeviceScene(ctx, sc)
+    try:
+        planes, eye = synth.reference_camera(1)
+        ds.upload_drawable_list()
+        ds.process_and_cull(planes, eye)
+        ctx.sync(ds.stream)
+        ind, ptr = ds.read_tier_r()
+        e_ind, e_ptr, ref = oracle_tier_x(sc, planes, eye, arena_base=ds.arena, list_base=ds.drawable_list)
+        assert np.array_equal(ind, e_ind) and np.array_equal(ptr, e_ptr)
+        got = ds.read_counters()
+        assert got["status"] == 0 and ref["status"] == 0
+        assert np.array_equal(got["inst_count"], ref["inst_count"]) and np.array_equal(got["cmd_count"], ref["cmd_count"])
+        assert got["near_band"] == ref["near_band"]
+        # every drawable has one matrix: the set of surviving drawables is the set of command tags
+        n_cmd = int(got["cmd_count"][0])
+        tags = ds._read(ds.tag_out, n_cmd * 8, np.uint32).reshape(-1, 2)
+        ref_tags = ref["tag"][:n_cmd]
+        assert np.array_equal(np.sort(tags[:, 0]), np.sort(ref_tags[:, 0])) and not tags[:, 1].any()
+        assert 0 < n_cmd < sc.n
+    finally:
+        ds.close()
