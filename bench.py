@@ -23,7 +23,9 @@ Workloads (BASELINE.json configs): c3 = configs[2], 100k geometries x 1000-insta
 64 StateSets, 3 LODs — the configuration north_star's target is quoted on, and the default; c2 = configs[1], 10 M
 drawables x 1 matrix; c4 = configs[3], c3 with 10 % of the MatrixLists rewritten every frame through the upload path
 (device-resident: staging already in HBM, scatter kernel + cull; e2e: cadr_b200_upload from pinned host staging,
-640 MB over PCIe per frame, + cull); c5 = configs[4], the c3 shape at 125 M instances per GPU (8 GPUs = 1 B).
+640 MB over PCIe per frame, + cull); c5 = configs[4], the c3 shape at 125 M instances per GPU (8 GPUs = 1 B);
+c1 = configs[0], the reference's RenderingPerformance IndependentBoxesScene (100^3 drawables with their own geometry
+and one-matrix list, the example's orthographic camera).
 Multi-GPU (torchrun): every rank culls its own shard (weak scaling); the compacted command lists and per-StateSet
 counters of all ranks end up in one buffer on every rank — stored there by the cull kernels themselves over NVLink
 peer mappings (default), or all-gathered with NCCL after the cull (--exchange nccl, the baseline).
@@ -52,7 +54,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5", "c1"])
     ap.add_argument("--drawables", type=int, default=0, help="override the drawable count (debug)")
     ap.add_argument("--instances", type=int, default=1000, help="matrices per list for c3")
     ap.add_argument("--state-sets", type=int, default=64, help="StateSets for c3 (debug: 1 makes drawable order == list order)")
@@ -76,11 +78,16 @@ def make_scene(args, rank: int, host_matrices: bool, drawables: int | None = Non
     if args.workload in C3_SHAPED:
         n = drawables or c3_drawables(args)
         return synth.config3(n, args.instances, state_sets=args.state_sets, seed=0xC0FFEE03 + rank, host_matrices=host_matrices)
+    if args.workload == "c1":
+        side = round((drawables or args.drawables or 1_000_000) ** (1 / 3))
+        return synth.config1(side, seed=1 + rank)          # small enough to build with its matrices on the host
     n = drawables or args.drawables or 10_000_000
     return synth.config2(n, seed=0xC0FFEE02 + rank, host_matrices=host_matrices)
 
 
 def camera(args, frame: int):
+    if args.workload == "c1":
+        return synth.reference_camera(frame)                # the example's orthographic camera, eye x alternating 1, 0
     far = 3000.0 if args.workload in C3_SHAPED else 1500.0
     return synth.orbit_camera(frame, 1500.0, far=far)
 
@@ -93,39 +100,55 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(kernel: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture, if any."""
+def recorded_traffic(workload: str, kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture of this
+    workload (profiles/traffic.json), if there is one."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(kernel)
+            return json.load(f).get(workload, {}).get(kernel)
     except Exception:
         return None
 
 
 class ClockSampler:
+    """nvidia-smi in loop mode (20 ms), read by a thread that time-stamps every sample; stop() reports the samples that
+    fall inside the marked windows (the timed regions)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        self.p = None
+        import threading
+        self.samples, self.windows, self.p = [], [], None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
-            self.p = None
+            return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.samples.append((time.monotonic(), line))
+
+    def wait_first(self, timeout=3.0):
+        t0 = time.monotonic()
+        while self.p is not None and not self.samples and time.monotonic() - t0 < timeout:
+            time.sleep(0.01)
+
+    def window(self, t0: float, t1: float):
+        self.windows.append((t0, t1))
 
     def stop(self) -> dict:
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.p.terminate()
-        try:
-            out, _ = self.p.communicate(timeout=5)
-        except Exception:
-            self.p.kill()
-            out = ""
+        self.t.join(timeout=2)
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
+        for ts, line in list(self.samples):
+            if not any(a <= ts <= b for a, b in self.windows):
+                continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
@@ -133,11 +156,11 @@ class ClockSampler:
                 sm.append(float(f[0])); mx.append(float(f[1]))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[3:7]):
+            for nm, v in zip(self.NAMES, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "window": "timed regions (device-resident and e2e loops)"}
 
 
 # -----------------------------------------------------------------------------------------------------
@@ -149,7 +172,7 @@ def cpu_sample_run(args, steps: int, warmup: int, sample_drawables: int | None =
     from oracle import binding as ob
     threads = ob.max_threads()
     if sample_drawables is None:
-        sample_drawables = args.cpu_sample or (8000 if args.workload in C3_SHAPED else 4_000_000)
+        sample_drawables = args.cpu_sample or (8000 if args.workload in C3_SHAPED else 1_000_000 if args.workload == "c1" else 4_000_000)
     sc = make_scene(args, 0, host_matrices=True, drawables=sample_drawables)
     base, lst = 0x7F1200000000, 0x7F2000000000
     img = sc.image(base)
@@ -207,6 +230,12 @@ def workload_config(args, n_gpus: int) -> dict:
                 "per_gpu_instances": n * args.instances, "gpus": n_gpus,
                 "l2": f"inputs ({n * args.instances * 64 / 1e9:.1f} GB of matrices per GPU) are far larger than the 126 MB L2; no flush needed",
                 "multi_gpu": mg}
+    if args.workload == "c1":
+        side = round((args.drawables or 1_000_000) ** (1 / 3))
+        return {"workload": f"BASELINE configs[0]: examples/RenderingPerformance IndependentBoxesScene, {side}^3 = {side ** 3} drawables, one geometry and "
+                            f"one 1-matrix list each ({4 * side ** 3} handles), single StateSet, the example's orthographic camera",
+                "per_gpu_instances": side ** 3, "gpus": n_gpus,
+                "l2": "inputs (0.13 GB matrix lists + 0.29 GB geometry + 0.05 GB drawable list + 0.03 GB handle tables) are larger than the 126 MB L2"}
     n = args.drawables or 10_000_000
     return {"workload": f"BASELINE configs[1]: {n} drawables x 1 matrix, single StateSet, orbiting camera", "per_gpu_instances": n,
             "gpus": n_gpus, "l2": "inputs (1.3 GB matrix lists + 0.5 GB drawable list per GPU) are far larger than the 126 MB L2"}
@@ -239,8 +268,11 @@ def run_b200(args):
     arena = TorchArena(dev)
     with torch.cuda.stream(stream_t):
         ds = DeviceScene(ctx, scene, alloc=arena.alloc, free=arena.free, upload=False, stream=stream)
-        ds.upload_static(with_matrices=False)
-        fill_matrix_lists(scene, arena.tensor(ds.arena))
+        if scene.matrices is not None:
+            ds.upload_static(with_matrices=True)
+        else:
+            ds.upload_static(with_matrices=False)
+            fill_matrix_lists(scene, arena.tensor(ds.arena))
     torch.cuda.synchronize()
     inst = scene.total_instances
     cams = [camera(args, k) for k in range(360)]
@@ -342,9 +374,12 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None     # started early: nvidia-smi needs ~0.1 s to deliver its first sample
+
     def timed(fn, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        t_begin = time.monotonic()
         torch.cuda.nvtx.range_push("timed")      # ncu --nvtx --nvtx-include "timed/" lists exactly these launches
         e0.record(stream_t)
         for k in range(steps):
@@ -353,6 +388,8 @@ def run_b200(args):
         barrier()
         torch.cuda.nvtx.range_pop()
         ms = e0.elapsed_time(e1)
+        if sampler is not None:
+            sampler.window(t_begin, time.monotonic())
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -369,11 +406,11 @@ def run_b200(args):
         if status:
             raise SystemExit(f"bench.py: cull_compact reported overflow status {status}")
 
-        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler is not None:
+            sampler.wait_first()
         l0 = ctx.launch_count
         ms_total = timed(step_device, args.steps)
         launches = ctx.launch_count - l0
-        clocks = sampler.stop() if sampler else None
 
         ms_cull_only = timed(lambda k: step_device(k, with_exchange=False), args.steps) if world > 1 else ms_total
 
@@ -386,6 +423,8 @@ def run_b200(args):
         ms_e2e = timed(step_e2e, e2e_steps)
         copy_t.synchronize()
         ds.drawable_list = lists[0]    # lists[0] is the buffer DeviceScene owns (and the one the kernel profile below reads)
+        clocks = sampler.stop() if sampler is not None else None
+        sampler = None
 
         # per-kernel durations (CUDA events recorded by the library around each of its kernels)
         ctx.set_profiling(True)
@@ -432,13 +471,19 @@ def run_b200(args):
         # what DRAM must move at this layout: a B200 L2 miss fetches the whole 128-B line (scripts/l2gran.cu), so the 4-byte
         # numMatrices + 64-byte matrix of a one-matrix MatrixList block cost 128 B, not 68
         line_granular = (48 + 8 + 128 + 48 + 48 + 64.0 * p) * inst
+        if args.workload == "c1":
+            # every drawable has its own geometry: four distinct handles (32 B of leaf entries) and its own PrimitiveSet
+            alg_bytes = (48 + 32 + 8 + 4 + 64 + 48 + 48 + 64.0 * p) * inst
+            alg_note = ("per drawable: 204 B read (list 48, four leaf entries 32, PrimitiveSet 8, numMatrices 4, matrix 64, cull record 48) "
+                        "+ 48 B Tier R records + 64p B written")
+            line_granular = (48 + 32 + 128 + 128 + 48 + 48 + 64.0 * p) * inst       # PrimitiveSet and MatrixList each cost a 128-B line
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
     total_inst = inst * world
     value = total_inst * args.steps / (ms_total * 1e-3)
     e2e_value = total_inst * e2e_steps / (ms_e2e * 1e-3)
     tier_r_ms = float(np.median(tier_r[2:]))
-    tier_r_bytes = 140 if args.workload in C3_SHAPED else 108
+    tier_r_bytes = 108 if args.workload == "c2" else 140        # shared geometry (c2) / own geometry per drawable
 
     line = {
         "metric": "culled+emitted instances/sec", "value": round(value / 1e6, 1), "unit": "M instances/s",
@@ -454,7 +499,7 @@ def run_b200(args):
                        large_name: round(k_large, 4)},
         "entry": "cadr_b200_process_drawables + cadr_b200_cull_compact" if args.unfused else "cadr_b200_process_and_cull",
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": recorded_traffic(dom_name), "peak_source": peak_src,
+                     "frac": round(achieved / peak, 4), "traffic": recorded_traffic({"c4": "c3"}.get(args.workload, args.workload) if not args.drawables and args.instances == 1000 else "", dom_name), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(alg_bytes), "algorithmic_bytes": alg_note, "launch_ms": round(dom_ms, 4)},
         "clocks": clocks,
         "tier_r": {"kernel": "processDrawablesKernel", "drawables": scene.n, "launch_ms": round(tier_r_ms, 4),
@@ -466,7 +511,8 @@ def run_b200(args):
         line["roofline"]["dram_line_granular_bytes_per_launch"] = int(line_granular)
         line["roofline"]["frac_of_line_granular_floor"] = round(line_granular / (dom_ms * 1e-3) / 1e9 / peak, 4)
         # Tier R alone on this shape: 48 list + 8 leaf + 128 (line holding numMatrices) read, 48 written
-        line["tier_r"]["frac_of_line_granular_floor"] = round(232 * scene.n / (tier_r_ms * 1e-3) / 1e9 / peak, 4)
+        tr_lines = 232 if args.workload == "c2" else 48 + 32 + 128 + 128 + 48
+        line["tier_r"]["frac_of_line_granular_floor"] = round(tr_lines * scene.n / (tier_r_ms * 1e-3) / 1e9 / peak, 4)
     if rewrite is not None:
         sc_ms = float(np.median(scatter_ms[2:]))
         line["upload"] = {"rewritten_lists_per_step": rewrite["lists"], "bytes_per_step": rewrite["bytes"], "kernel": "scatterCopyKernel",
