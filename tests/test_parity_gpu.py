@@ -208,6 +208,35 @@ def test_tier_x_region_overflow_is_reported(ctx):
         ds.close()
 
 
+def test_tier_x_work_item_queue_overflow_is_reported(ctx):
+    """A work-item workspace smaller than the scene needs: status bit 1, the items that did not fit are dropped, the
+    ones that did are still complete and correct (never a write past the workspace)."""
+    sc = synth.random_scene(24, n=300, list_counts=[40, 700, 1500, 2500, 90, 33], state_sets=3)
+    big = 1e9
+    all_in = np.array([[1, 0, 0, big], [-1, 0, 0, big], [0, 1, 0, big], [0, -1, 0, big], [0, 0, 1, big], [0, 0, -1, big]], np.float32)
+    ds = DeviceScene(ctx, sc)
+    try:
+        need = ds.chunk_cap
+        assert need > 40
+        guard = ctx.arena_alloc(128)                       # poison right behind a deliberately small workspace
+        ds.chunk_cap = need // 3
+        small_ws = ctx.arena_alloc(ds.chunk_cap * 128 + 256)
+        ctx.memset(small_ws, 0xAB, ds.chunk_cap * 128 + 256)
+        ds.chunk_ws = small_ws
+        ds.record_drawable_processing()
+        ds.cull(all_in, np.zeros(3, np.float32)); ctx.sync(ds.stream)
+        c = ds.read_counters()
+        assert c["status"] == 2
+        tail = np.empty(256, np.uint8); ctx.memcpy_d2h(tail, small_ws + ds.chunk_cap * 128); ctx.sync()
+        assert (tail == 0xAB).all()
+        cnt = sc.ml_count[sc.drawable_ml].astype(np.int64)
+        nonempty = sc.cull[:, 3].view(np.float32) >= 0
+        assert 0 < c["inst_count"].sum() < int(cnt[nonempty].sum())     # some items were dropped, the rest were emitted
+        ctx.arena_free(small_ws); ctx.arena_free(guard)
+    finally:
+        ds.close()
+
+
 def test_tier_x_bad_range_index_is_reported_not_followed(ctx):
     sc = synth.random_scene(23, n=400, num_lists=40)
     sc.cull = sc.cull.copy()
