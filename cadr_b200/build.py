@@ -16,7 +16,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--cudart", "static", "-shared",
 ]
-CUDA_SOURCES = ["capi.cu", "process_drawables.cu", "cull_compact.cu", "upload.cu", "exchange.cu", "consume_check.cu", "external.cu"]
+CUDA_SOURCES = ["capi.cu", "process_drawables.cu", "cull_compact.cu", "cull_variants.cu", "upload.cu", "exchange.cu", "consume_check.cu", "external.cu"]
 
 
 def _run(cmd, **kw):
@@ -46,7 +46,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     out = os.path.join(LIBDIR, "libcadr_b200.so")
     srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
-    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "cadr_b200.h")]
+    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "cull_common.cuh"), os.path.join(ROOT, "include", "cadr_b200.h")]
     if force or _stale(out, deps):
         flags = NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
         log = _run([nvcc()] + flags + ["-o", out] + srcs)

@@ -18,12 +18,9 @@
 //                       Default for every list longer than 32 matrices.
 //   cullListRingKernel  the same with a warp-private shared-memory ring filled by asynchronous copies (LDGSTS) three
 //                       steps ahead (CADR_B200_CULL_VARIANT=3): higher memory-side ceiling, but issue-bound.
-//   cullLargeKernel     the same stage as a warp-specialised TMA pipeline (CADR_B200_CULL_VARIANT=1): persistent,
-//                       one CTA per SM; a producer lane streams each item's descriptor + up to 64 KiB of matrices
-//                       into a 3-stage shared-memory ring with TMA bulk copies (cp.async.bulk ...
-//                       mbarrier::complete_tx::bytes); 16 consumer warps evaluate from shared memory.  Measured
-//                       slower than the warp-per-item kernel (0.93 vs 1.02 of the copy peak); kept for A/B.
-//   cullLargeLdgKernel  the first version (CTA per item, direct loads, CTA barriers; CADR_B200_CULL_VARIANT=0).
+//   cull_variants.cu    two earlier versions of the long-list stage, kept for A/B measurements: cullLargeKernel, a
+//                       CTA-wide warp-specialised TMA pipeline (CADR_B200_CULL_VARIANT=1; 0.93 of the copy peak
+//                       against 1.00 here), and cullLargeLdgKernel, CTA per item with direct loads (=0).
 //
 // No per-instance global atomics anywhere.  Emission order of commands inside a StateSet and of instance
 // indices inside a run depends on arrival order, so comparisons canonicalise: merge by (drawableIndex, lod),
@@ -32,230 +29,10 @@
 // Algorithmic bytes per instance: 64 R (mat4) + 4*p W (u32 index of a survivor) + per-drawable
 // overhead / N.
 
-#include "common.cuh"
+#include "cull_common.cuh"
 #include <cstdlib>
 
 namespace cadr {
-
-constexpr uint32_t SMALL_MAX  = CADR_CULL_SMALL_LIST_MAX;        // lists up to this many matrices are handled by one thread
-constexpr uint32_t CHUNK      = CADR_CULL_WORK_ITEM_INSTANCES;   // instances per work item of the list kernels
-constexpr int      CS_THREADS = 256;
-
-// Self-contained work item of the list kernels: 128 bytes, written by cullSmallKernel.
-struct __align__(16) WorkItem {
-	uint64_t matrices;        // device address of the item's first matrix
-	uint32_t count;           // 1..CHUNK matrices (0xffffffff in shared memory: end of work)
-	uint32_t firstInstance;   // index of the first matrix inside its MatrixList
-	uint32_t drawable;
-	uint32_t stateSet;
-	uint32_t lodCount;        // 1..3
-	uint32_t pad0;
-	float    sphere[4];
-	float    thr0, thr1;
-	uint32_t pad1[2];
-	uint32_t ps[3][2];        // {indexCount, firstIndex} of each LOD's PrimitiveSet
-	uint32_t pad2[2];
-	uint4    ptr0, ptr1;      // DrawablePointers to forward
-};
-static_assert(sizeof(WorkItem) == 128, "WorkItem must be 128 bytes");
-
-struct CullArgs {
-	uint64_t root;
-	const uint8_t* drawableList;
-	const uint4*   indirect;
-	const uint4*   pointers;
-	const uint4*   cullData;
-	const uint4*   regions;
-	uint8_t*  cmdOut;
-	uint4*    ptrOut;
-	uint2*    tagOut;
-	uint32_t* instOut;
-	cadr_cull_header* hdr;
-	unsigned long long* counts;
-	WorkItem* items;
-	uint32_t  chunkCapacity;
-	uint32_t  n;
-	uint32_t  numStateSets;
-	uint32_t  diagNoEval;                 // CADR_B200_DIAG_NOEVAL=1: list kernels skip the evaluation (memory-system ceiling of the access structure)
-	float4 plane[6];
-	float4 eye;
-	// fused multi-GPU exchange: gathered arrays of every rank (peer mappings), 0 ranks = write cmdOut/ptrOut/tagOut
-	uint32_t  xWorld, xSlotBase;          // xSlotBase = rank * capacity
-	uint8_t*  xCmd[CADR_MAX_PEERS];
-	uint4*    xPtr[CADR_MAX_PEERS];
-	uint2*    xTag[CADR_MAX_PEERS];
-};
-
-struct Mat { float4 c0, c1, c2, c3; };  // column-major mat4
-
-__device__ __forceinline__ Mat loadMat(const uint8_t* p)
-{
-	// two 256-bit streaming loads: each pulls one full 32-byte sector (LDG.E.256, new on sm_100)
-	Mat m;
-	asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-	             : "=f"(m.c0.x), "=f"(m.c0.y), "=f"(m.c0.z), "=f"(m.c0.w),
-	               "=f"(m.c1.x), "=f"(m.c1.y), "=f"(m.c1.z), "=f"(m.c1.w) : "l"(p));
-	asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-	             : "=f"(m.c2.x), "=f"(m.c2.y), "=f"(m.c2.z), "=f"(m.c2.w),
-	               "=f"(m.c3.x), "=f"(m.c3.y), "=f"(m.c3.z), "=f"(m.c3.w) : "l"(p + 32));
-	return m;
-}
-
-struct LodInfo { float4 sphere; uint32_t lodCount; float thr0, thr1; };
-
-// Per-instance evaluation.  Operation order is normative (DESIGN.md "Tier X"): every multiply-add below is ONE
-// IEEE-754 fusedMultiplyAdd (__fmaf_rn == C fmaf), every other product/sum/sqrt a separately rounded fp32
-// operation, so the result is bit-identical to the C oracle (built with -ffp-contract=off, explicit fmaf).
-// Returns the LOD (0..2) of a visible instance or -1; `nearBand` reports a sphere within 1e-5 of a plane or
-// of an LOD threshold.
-__device__ __forceinline__ int evalInstance(const Mat& m, const LodInfo& L, const float4 (&plane)[6],
-                                            const float4& eye, bool& nearBand)
-{
-	const float4 b = L.sphere;
-	// centre = mat3(M)*c + M[3].xyz                                   BoundingSphere.h:73
-	float cx = __fmaf_rn(m.c2.x, b.z, __fmaf_rn(m.c1.x, b.y, __fmaf_rn(m.c0.x, b.x, m.c3.x)));
-	float cy = __fmaf_rn(m.c2.y, b.z, __fmaf_rn(m.c1.y, b.y, __fmaf_rn(m.c0.y, b.x, m.c3.y)));
-	float cz = __fmaf_rn(m.c2.z, b.z, __fmaf_rn(m.c1.z, b.y, __fmaf_rn(m.c0.z, b.x, m.c3.z)));
-	// radius = sqrt(max squared column length) * r                    BoundingSphere.h:76-85
-	float s0 = __fmaf_rn(m.c0.z, m.c0.z, __fmaf_rn(m.c0.y, m.c0.y, __fmul_rn(m.c0.x, m.c0.x)));
-	float s1 = __fmaf_rn(m.c1.z, m.c1.z, __fmaf_rn(m.c1.y, m.c1.y, __fmul_rn(m.c1.x, m.c1.x)));
-	float s2 = __fmaf_rn(m.c2.z, m.c2.z, __fmaf_rn(m.c2.y, m.c2.y, __fmul_rn(m.c2.x, m.c2.x)));
-	float s01 = (s0 < s1) ? s1 : s0;        // std::max
-	float s = (s01 < s2) ? s2 : s01;
-	float r = __fmul_rn(__fsqrt_rn(s), b.w);
-
-	bool nonEmpty = b.w >= 0.f;             // radius < 0 (incl. -inf): empty sphere, never visible (:39-43)
-	bool visible = nonEmpty;
-	// any_k |dot_k + r| < 1e-5  ==  min_k |dot_k + r| < 1e-5 (fminf skips a NaN term exactly like the comparison would)
-	float nearest = __int_as_float(0x7f800000);
-#pragma unroll
-	for(int k = 0; k < 6; k++) {
-		float dot = __fmaf_rn(plane[k].z, cz, __fmaf_rn(plane[k].y, cy, __fmaf_rn(plane[k].x, cx, plane[k].w)));
-		visible = visible && (dot >= -r);
-		nearest = fminf(nearest, fabsf(__fadd_rn(dot, r)));
-	}
-	const bool nearP = nearest < 1e-5f;
-	float dx = __fadd_rn(cx, -eye.x), dy = __fadd_rn(cy, -eye.y), dz = __fadd_rn(cz, -eye.z);
-	float dist = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
-	int lod = 0;
-	bool nearT = false;
-	if(L.lodCount > 1) { lod += (L.thr0 <= dist) ? 1 : 0; nearT = nearT || (fabsf(__fadd_rn(dist, -L.thr0)) < 1e-5f); }
-	if(L.lodCount > 2) { lod += (L.thr1 <= dist) ? 1 : 0; nearT = nearT || (fabsf(__fadd_rn(dist, -L.thr1)) < 1e-5f); }
-	nearBand = nonEmpty && (nearP || (visible && nearT));
-	return visible ? lod : -1;
-}
-
-// Two instances at once with Blackwell's packed fp32 pipe (FFMA2 / FADD2 / FMUL2, sm_100): every component of a
-// packed operation is the same IEEE-754 operation evalInstance() performs, so results are bit-identical; the FP
-// instruction count per instance halves.  Used by the TMA pipeline kernel (cullLargeKernel), where each lane owns two instances.
-__device__ __forceinline__ void evalInstancePair(const Mat& a, const Mat& b, const LodInfo& L, const float4 (&plane)[6],
-                                                 const float4& eye, int& lodA, int& lodB, bool& nearA, bool& nearB)
-{
-#define CADR_P2(u, v) make_float2((u), (v))
-#define CADR_D2(u) make_float2((u), (u))
-	const float4 sp = L.sphere;
-	const float2 bx = CADR_D2(sp.x), by = CADR_D2(sp.y), bz = CADR_D2(sp.z);
-	const float2 cx = __ffma2_rn(CADR_P2(a.c2.x, b.c2.x), bz, __ffma2_rn(CADR_P2(a.c1.x, b.c1.x), by, __ffma2_rn(CADR_P2(a.c0.x, b.c0.x), bx, CADR_P2(a.c3.x, b.c3.x))));
-	const float2 cy = __ffma2_rn(CADR_P2(a.c2.y, b.c2.y), bz, __ffma2_rn(CADR_P2(a.c1.y, b.c1.y), by, __ffma2_rn(CADR_P2(a.c0.y, b.c0.y), bx, CADR_P2(a.c3.y, b.c3.y))));
-	const float2 cz = __ffma2_rn(CADR_P2(a.c2.z, b.c2.z), bz, __ffma2_rn(CADR_P2(a.c1.z, b.c1.z), by, __ffma2_rn(CADR_P2(a.c0.z, b.c0.z), bx, CADR_P2(a.c3.z, b.c3.z))));
-	auto sq = [](float ax, float ay, float az, float bx_, float by_, float bz_) {
-		const float2 x = CADR_P2(ax, bx_), y = CADR_P2(ay, by_), z = CADR_P2(az, bz_);
-		return __ffma2_rn(z, z, __ffma2_rn(y, y, __fmul2_rn(x, x)));
-	};
-	const float2 s0 = sq(a.c0.x, a.c0.y, a.c0.z, b.c0.x, b.c0.y, b.c0.z);
-	const float2 s1 = sq(a.c1.x, a.c1.y, a.c1.z, b.c1.x, b.c1.y, b.c1.z);
-	const float2 s2 = sq(a.c2.x, a.c2.y, a.c2.z, b.c2.x, b.c2.y, b.c2.z);
-	const float sA01 = (s0.x < s1.x) ? s1.x : s0.x, sA = (sA01 < s2.x) ? s2.x : sA01;
-	const float sB01 = (s0.y < s1.y) ? s1.y : s0.y, sB = (sB01 < s2.y) ? s2.y : sB01;
-	const float2 r = __fmul2_rn(CADR_P2(__fsqrt_rn(sA), __fsqrt_rn(sB)), CADR_D2(sp.w));
-
-	const bool nonEmpty = sp.w >= 0.f;
-	bool visA = nonEmpty, visB = nonEmpty, npA = false, npB = false;
-#pragma unroll
-	for(int k = 0; k < 6; k++) {
-		const float2 dot = __ffma2_rn(CADR_D2(plane[k].z), cz, __ffma2_rn(CADR_D2(plane[k].y), cy, __ffma2_rn(CADR_D2(plane[k].x), cx, CADR_D2(plane[k].w))));
-		const float2 t = __fadd2_rn(dot, r);
-		visA = visA && (dot.x >= -r.x); visB = visB && (dot.y >= -r.y);
-		npA = npA || (fabsf(t.x) < 1e-5f); npB = npB || (fabsf(t.y) < 1e-5f);
-	}
-	const float2 dx = __fadd2_rn(cx, CADR_D2(-eye.x)), dy = __fadd2_rn(cy, CADR_D2(-eye.y)), dz = __fadd2_rn(cz, CADR_D2(-eye.z));
-	const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-	const float distA = __fsqrt_rn(d2.x), distB = __fsqrt_rn(d2.y);
-	int la = 0, lb = 0;
-	bool ntA = false, ntB = false;
-	if(L.lodCount > 1) {
-		la += (L.thr0 <= distA) ? 1 : 0; lb += (L.thr0 <= distB) ? 1 : 0;
-		const float2 e = __fadd2_rn(CADR_P2(distA, distB), CADR_D2(-L.thr0));
-		ntA = ntA || (fabsf(e.x) < 1e-5f); ntB = ntB || (fabsf(e.y) < 1e-5f);
-	}
-	if(L.lodCount > 2) {
-		la += (L.thr1 <= distA) ? 1 : 0; lb += (L.thr1 <= distB) ? 1 : 0;
-		const float2 e = __fadd2_rn(CADR_P2(distA, distB), CADR_D2(-L.thr1));
-		ntA = ntA || (fabsf(e.x) < 1e-5f); ntB = ntB || (fabsf(e.y) < 1e-5f);
-	}
-	nearA = nonEmpty && (npA || (visA && ntA));
-	nearB = nonEmpty && (npB || (visB && ntB));
-	lodA = visA ? la : -1;
-	lodB = visB ? lb : -1;
-#undef CADR_P2
-#undef CADR_D2
-}
-
-__device__ __forceinline__ LodInfo unpackLod(uint4 a, uint4 b, uint4 c, uint32_t (&psOff)[3], uint32_t& stateSet)
-{
-	LodInfo L;
-	L.sphere = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
-	uint32_t lc = b.x;
-	L.lodCount = lc < 1 ? 1 : (lc > 3 ? 3 : lc);
-	psOff[0] = b.y; psOff[1] = b.z; psOff[2] = b.w;
-	L.thr0 = __uint_as_float(c.x); L.thr1 = __uint_as_float(c.y);
-	stateSet = c.z;
-	return L;
-}
-
-template<int LEVEL>
-__device__ __forceinline__ uint64_t primitiveSetBase(const CullArgs& A, uint32_t d)
-{
-	uint64_t h = ldg_u64(reinterpret_cast<uint64_t>(A.drawableList) + 48ull * d + 32);
-	return lookupHandle<LEVEL>(A.root, h);
-}
-
-__device__ __forceinline__ uint32_t warpInclusiveScan(uint32_t v, int lane)
-{
-#pragma unroll
-	for(int o = 1; o < 32; o <<= 1) {
-		uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-		if(lane >= o) v += t;
-	}
-	return v;
-}
-
-__device__ __forceinline__ uint32_t smemAddr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
-
-// command + forwarded pointers + tag of one (drawable, lod[, item])
-__device__ __forceinline__ void writeCommandRecord(const CullArgs& A, uint32_t ci, uint32_t indexCount, uint32_t instanceCount,
-                                                   uint32_t firstIndex, uint32_t firstInstance, uint32_t d, uint32_t lod,
-                                                   uint4 p0, uint4 p1)
-{
-	if(A.xWorld > 1) {
-		// fused exchange: the record goes to slot (rank * capacity + ci) of EVERY rank's gathered arrays over NVLink
-		// peer mappings while the cull is still running (the local copy is one of them)
-		const uint64_t slot = uint64_t(A.xSlotBase) + ci;
-		for(uint32_t r = 0; r < A.xWorld; r++) {
-			uint32_t* c = reinterpret_cast<uint32_t*>(A.xCmd[r] + 20ull * slot);
-			c[0] = indexCount; c[1] = instanceCount; c[2] = firstIndex; c[3] = 0u; c[4] = firstInstance;
-			A.xPtr[r][2ull * slot] = p0;
-			A.xPtr[r][2ull * slot + 1] = p1;
-			A.xTag[r][slot] = make_uint2(d, lod);
-		}
-		return;
-	}
-	uint32_t* c = reinterpret_cast<uint32_t*>(A.cmdOut + 20ull * ci);
-	c[0] = indexCount; c[1] = instanceCount; c[2] = firstIndex; c[3] = 0u; c[4] = firstInstance;
-	A.ptrOut[2ull * ci] = p0;
-	A.ptrOut[2ull * ci + 1] = p1;
-	A.tagOut[ci] = make_uint2(d, lod);
-}
 
 // ---------------------------------------------------------------------------------------------------
 // small lists + work-item queueing: one thread per drawable
@@ -828,356 +605,6 @@ cullListRingKernel(const __grid_constant__ CullArgs A)
 	}
 }
 
-// ---------------------------------------------------------------------------------------------------
-// long lists, TMA pipeline: persistent CTAs, producer warp + 16 consumer warps, 3-stage smem ring
-// ---------------------------------------------------------------------------------------------------
-constexpr int TP_STAGES         = 3;
-constexpr int TP_CONSUMER_WARPS = 16;
-constexpr int TP_THREADS        = (TP_CONSUMER_WARPS + 1) * 32;     // 544
-constexpr int TP_PER_WARP       = CHUNK / TP_CONSUMER_WARPS;        // 64 instances per warp per item
-constexpr int TP_BATCHES        = TP_PER_WARP / 32;                 // 2
-
-struct __align__(128) TpStage {
-	uint8_t  mats[CHUNK * 64];       // 64 KiB, filled by TMA
-	WorkItem item;                   // 128 B, filled by TMA
-	uint16_t stash[3][CHUNK];        // survivors' local indices per LOD
-	uint32_t cnt[3];                 // survivors per LOD so far (smem atomics)
-	uint32_t done;                   // consumer warps finished with this item
-	uint32_t nearBand;
-	uint32_t pad[27];
-};
-static_assert(sizeof(TpStage) % 128 == 0, "stage alignment");
-constexpr size_t TP_SMEM_BYTES = TP_STAGES * sizeof(TpStage) + 2 * TP_STAGES * sizeof(uint64_t);
-static_assert(TP_SMEM_BYTES <= 227 * 1024, "shared memory budget of one CTA");
-
-__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smemAddr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbarArrive(uint64_t* bar)
-{
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smemAddr(bar)) : "memory");
-}
-__device__ __forceinline__ void mbarArriveExpectTx(uint64_t* bar, uint32_t bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smemAddr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity)
-{
-	asm volatile(
-		"{\n\t.reg .pred p;\n\t"
-		"MBAR_WAIT_%=:\n\t"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-		"@p bra MBAR_DONE_%=;\n\t"
-		"bra MBAR_WAIT_%=;\n\t"
-		"MBAR_DONE_%=:\n\t}"
-		:: "r"(smemAddr(bar)), "r"(parity) : "memory");
-}
-// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tmaLoad(void* dstSmem, uint64_t srcGlobal, uint32_t bytes, uint64_t* bar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-	             :: "r"(smemAddr(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar)) : "memory");
-}
-
-// Read matrix `jj` of the stage.  A lane's matrix is 64 contiguous bytes, so lanes l and l+2 of a quarter-warp
-// would hit the same banks; each lane therefore reads its four 16-byte columns in a rotated order (column
-// (k + rot) & 3 in step k, rot = (lane >> 1) & 3), which makes every LDS.128 cover all 32 banks exactly once,
-// and un-rotates in registers with two select levels.
-__device__ __forceinline__ Mat loadMatSmem(const uint8_t* mats, uint32_t jj, int lane)
-{
-	const uint8_t* mp = mats + 64u * jj;
-	const uint32_t rot = (uint32_t(lane) >> 1) & 3u;
-	float4 q0 = *reinterpret_cast<const float4*>(mp + (((0u + rot) & 3u) << 4));
-	float4 q1 = *reinterpret_cast<const float4*>(mp + (((1u + rot) & 3u) << 4));
-	float4 q2 = *reinterpret_cast<const float4*>(mp + (((2u + rot) & 3u) << 4));
-	float4 q3 = *reinterpret_cast<const float4*>(mp + (((3u + rot) & 3u) << 4));
-	// q[k] = column (k + rot) & 3  =>  column c = q[(c - rot) & 3] = q[(c + back) & 3], back = (4 - rot) & 3
-	const uint32_t back = (4u - rot) & 3u;
-	const bool b2 = back & 2u, b1 = back & 1u;
-	auto sel = [](bool c, const float4& a, const float4& b) { return make_float4(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z, c ? a.w : b.w); };
-	float4 t0 = sel(b2, q2, q0), t1 = sel(b2, q3, q1), t2 = sel(b2, q0, q2), t3 = sel(b2, q1, q3);  // t[c] = q[(c + (back&2)) & 3]
-	Mat m;
-	m.c0 = sel(b1, t1, t0); m.c1 = sel(b1, t2, t1); m.c2 = sel(b1, t3, t2); m.c3 = sel(b1, t0, t3);
-	return m;
-}
-
-__global__ void __launch_bounds__(TP_THREADS, 1)
-cullLargeKernel(const __grid_constant__ CullArgs A)
-{
-	extern __shared__ __align__(128) uint8_t smem[];
-	TpStage* stages = reinterpret_cast<TpStage*>(smem);
-	uint64_t* full = reinterpret_cast<uint64_t*>(smem + TP_STAGES * sizeof(TpStage));
-	uint64_t* empty = full + TP_STAGES;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-	if(tid == 0) {
-#pragma unroll
-		for(int s = 0; s < TP_STAGES; s++) { mbarInit(&full[s], 1); mbarInit(&empty[s], TP_CONSUMER_WARPS); }
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-	__syncthreads();
-
-	uint32_t total = A.hdr->chunkCount;
-	if(total > A.chunkCapacity) total = A.chunkCapacity;
-
-	if(warp == TP_CONSUMER_WARPS) {
-		// ===== producer: one elected lane =====
-		if(lane == 0) {
-			uint32_t next = atomicAdd(&A.hdr->chunkCursor, 1u);
-			for(uint32_t it = 0;; it++) {
-				const uint32_t s = it % TP_STAGES, ph = (it / TP_STAGES) & 1u;
-				const uint32_t item = next;
-				const bool end = item >= total;
-				uint4 head = make_uint4(0, 0, 0, 0);
-				if(!end) {
-					head = *reinterpret_cast<const uint4*>(A.items + item);   // {matrices lo, hi, count, firstInstance}
-					next = atomicAdd(&A.hdr->chunkCursor, 1u);                // prefetch the next item index
-				}
-				TpStage& st = stages[s];
-				mbarWait(&empty[s], ph ^ 1u);                                 // all consumers released the stage
-				st.cnt[0] = 0; st.cnt[1] = 0; st.cnt[2] = 0; st.done = 0; st.nearBand = 0;
-				if(end) {
-					st.item.count = 0xffffffffu;
-					mbarArrive(&full[s]);
-					break;
-				}
-				const uint32_t bytes = head.z * 64u;
-				mbarArriveExpectTx(&full[s], bytes + uint32_t(sizeof(WorkItem)));
-				tmaLoad(&st.item, reinterpret_cast<uint64_t>(A.items + item), uint32_t(sizeof(WorkItem)), &full[s]);
-				tmaLoad(st.mats, uint64_t(head.x) | (uint64_t(head.y) << 32), bytes, &full[s]);
-			}
-		}
-		return;
-	}
-
-	// ===== consumers =====
-	const uint32_t lt = (1u << lane) - 1u;
-	for(uint32_t it = 0;; it++) {
-		const uint32_t s = it % TP_STAGES, ph = (it / TP_STAGES) & 1u;
-		TpStage& st = stages[s];
-		mbarWait(&full[s], ph);
-		const uint32_t cnt = st.item.count;
-		if(cnt == 0xffffffffu) break;
-
-		LodInfo L;
-		L.sphere = make_float4(st.item.sphere[0], st.item.sphere[1], st.item.sphere[2], st.item.sphere[3]);
-		L.lodCount = st.item.lodCount; L.thr0 = st.item.thr0; L.thr1 = st.item.thr1;
-
-		int lod[TP_BATCHES];
-		bool nbv[TP_BATCHES];
-		uint32_t bal[TP_BATCHES][3];
-		uint32_t wc[3] = {0, 0, 0}, nearCnt = 0;
-		const uint32_t jw = warp * TP_PER_WARP + lane;
-		// branch-free evaluation of both batches (index clamped, result masked) so that the two independent
-		// instruction streams interleave; a tail item re-evaluates its last matrix in the idle lanes
-		static_assert(TP_BATCHES == 2, "the packed evaluation pairs the lane's two instances");
-		{
-			const Mat m0 = loadMatSmem(st.mats, min(jw, cnt - 1u), lane);
-			const Mat m1 = loadMatSmem(st.mats, min(jw + 32u, cnt - 1u), lane);
-			int l0, l1;
-			bool n0, n1;
-			evalInstancePair(m0, m1, L, A.plane, A.eye, l0, l1, n0, n1);
-			lod[0] = (jw < cnt) ? l0 : -1;        nbv[0] = n0 && (jw < cnt);
-			lod[1] = (jw + 32u < cnt) ? l1 : -1;  nbv[1] = n1 && (jw + 32u < cnt);
-		}
-#pragma unroll
-		for(int b = 0; b < TP_BATCHES; b++) {
-			const bool nb = nbv[b];
-			bal[b][0] = __ballot_sync(0xffffffffu, lod[b] == 0);
-			bal[b][1] = __ballot_sync(0xffffffffu, lod[b] == 1);
-			bal[b][2] = __ballot_sync(0xffffffffu, lod[b] == 2);
-			nearCnt += __popc(__ballot_sync(0xffffffffu, nb));
-			wc[0] += __popc(bal[b][0]); wc[1] += __popc(bal[b][1]); wc[2] += __popc(bal[b][2]);
-		}
-		// rank of this warp's survivors inside the item's per-LOD stash: one smem atomic per (warp, LOD)
-		uint32_t rank = 0;
-		if(lane < 3) {
-			uint32_t mine = (lane == 0) ? wc[0] : (lane == 1) ? wc[1] : wc[2];
-			if(mine) rank = atomicAdd(&st.cnt[lane], mine);
-		}
-		else if(lane == 3 && nearCnt) atomicAdd(&st.nearBand, nearCnt);
-		uint32_t r0 = __shfl_sync(0xffffffffu, rank, 0), r1 = __shfl_sync(0xffffffffu, rank, 1), r2 = __shfl_sync(0xffffffffu, rank, 2);
-#pragma unroll
-		for(int b = 0; b < TP_BATCHES; b++) {
-			const uint32_t jj = jw + b * 32;
-			if(lod[b] == 0) st.stash[0][r0 + __popc(bal[b][0] & lt)] = uint16_t(jj);
-			if(lod[b] == 1) st.stash[1][r1 + __popc(bal[b][1] & lt)] = uint16_t(jj);
-			if(lod[b] == 2) st.stash[2][r2 + __popc(bal[b][2] & lt)] = uint16_t(jj);
-			r0 += __popc(bal[b][0]); r1 += __popc(bal[b][1]); r2 += __popc(bal[b][2]);
-		}
-		__syncwarp();
-		uint32_t arrived = 0;
-		if(lane == 0) {
-			__threadfence_block();                         // stash writes before the arrival count
-			arrived = atomicAdd(&st.done, 1u);
-		}
-		arrived = __shfl_sync(0xffffffffu, arrived, 0);
-		if(arrived == TP_CONSUMER_WARPS - 1) {
-			// ---- last warp of the item: reserve, emit commands, copy the stash out -------------------
-			__threadfence_block();
-			const uint32_t t0 = *reinterpret_cast<volatile uint32_t*>(&st.cnt[0]);
-			const uint32_t t1 = *reinterpret_cast<volatile uint32_t*>(&st.cnt[1]);
-			const uint32_t t2 = *reinterpret_cast<volatile uint32_t*>(&st.cnt[2]);
-			const uint32_t nInst = t0 + t1 + t2;
-			if(nInst) {
-				const uint32_t nCmd = (t0 ? 1u : 0u) + (t1 ? 1u : 0u) + (t2 ? 1u : 0u);
-				const uint32_t stateSet = st.item.stateSet;
-				unsigned long long base = 0;
-				uint4 reg = make_uint4(0, 0, 0, 0);
-				if(lane == 0) {
-					base = atomicAdd(A.counts + stateSet, (unsigned long long)nCmd | ((unsigned long long)nInst << 32));
-					reg = ldg_u4(reinterpret_cast<uint64_t>(A.regions + stateSet));
-					uint32_t nbTot = *reinterpret_cast<volatile uint32_t*>(&st.nearBand);
-					if(nbTot) atomicAdd(&A.hdr->nearBandCount, nbTot);
-				}
-				base = __shfl_sync(0xffffffffu, base, 0);
-				reg.x = __shfl_sync(0xffffffffu, reg.x, 0); reg.y = __shfl_sync(0xffffffffu, reg.y, 0);
-				reg.z = __shfl_sync(0xffffffffu, reg.z, 0); reg.w = __shfl_sync(0xffffffffu, reg.w, 0);
-				const uint32_t cmdOff = uint32_t(base), instOff = uint32_t(base >> 32);
-				if(cmdOff + nCmd > reg.y || instOff + nInst > reg.w) {
-					if(lane == 0) atomicOr(&A.hdr->status, CADR_CULL_STATUS_REGION_OVERFLOW);
-				}
-				else {
-					const uint32_t i0 = reg.z + instOff, i1 = i0 + t0, i2 = i1 + t1;
-					const uint32_t j0 = st.item.firstInstance, d = st.item.drawable;
-					if(lane < 3) {
-						const uint32_t tl = (lane == 0) ? t0 : (lane == 1) ? t1 : t2;
-						if(tl) {
-							uint32_t ci = reg.x + cmdOff + ((lane > 0 && t0) ? 1u : 0u) + ((lane > 1 && t1) ? 1u : 0u);
-							writeCommandRecord(A, ci, st.item.ps[lane][0], tl, st.item.ps[lane][1],
-							                   (lane == 0) ? i0 : (lane == 1) ? i1 : i2, d, uint32_t(lane), st.item.ptr0, st.item.ptr1);
-						}
-					}
-					for(uint32_t i = lane; i < t0; i += 32) A.instOut[i0 + i] = j0 + st.stash[0][i];
-					for(uint32_t i = lane; i < t1; i += 32) A.instOut[i1 + i] = j0 + st.stash[1][i];
-					for(uint32_t i = lane; i < t2; i += 32) A.instOut[i2 + i] = j0 + st.stash[2][i];
-				}
-			}
-			else if(lane == 0) {
-				uint32_t nbTot = *reinterpret_cast<volatile uint32_t*>(&st.nearBand);
-				if(nbTot) atomicAdd(&A.hdr->nearBandCount, nbTot);
-			}
-		}
-		__syncwarp();
-		if(lane == 0) mbarArrive(&empty[s]);   // this warp no longer touches the stage
-	}
-}
-
-// ---------------------------------------------------------------------------------------------------
-// long lists, first version: direct 256-bit global loads, CTA barriers (kept for A/B measurements)
-// ---------------------------------------------------------------------------------------------------
-constexpr int      CL_THREADS  = 256;
-constexpr int      CL_WARPS    = CL_THREADS / 32;
-constexpr uint32_t CL_PER_WARP = CHUNK / CL_WARPS;   // 128 instances per warp per item
-constexpr int      CL_BATCHES  = CL_PER_WARP / 32;   // 4 batches of 32
-
-__global__ void __launch_bounds__(CL_THREADS, 2)
-cullLargeLdgKernel(const __grid_constant__ CullArgs A)
-{
-	__shared__ uint32_t sItem[2];
-	__shared__ uint32_t sWarpCnt[CL_WARPS][4];   // [warp][lod], 4th = near-band count
-	__shared__ uint32_t sLodStart[3];            // absolute index into instOut of each LOD's run, or 0xffffffff
-	__shared__ uint32_t sCmdBase;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-	uint32_t total = A.hdr->chunkCount;
-	if(total > A.chunkCapacity) total = A.chunkCapacity;
-	if(tid == 0) sItem[0] = atomicAdd(&A.hdr->chunkCursor, 1u);
-	__syncthreads();
-
-	for(int it = 0;; it++) {
-		const uint32_t item = sItem[it & 1];
-		if(item >= total) break;
-		uint32_t nextItem = 0;
-		if(tid == 0) nextItem = atomicAdd(&A.hdr->chunkCursor, 1u);
-
-		const uint4* w = reinterpret_cast<const uint4*>(A.items + item);
-		const uint4 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
-		const uint8_t* mats = reinterpret_cast<const uint8_t*>(uint64_t(w0.x) | (uint64_t(w0.y) << 32));
-		const uint32_t cnt = w0.z, j0 = w0.w, d = w1.x, stateSet = w1.y;
-		LodInfo L;
-		L.sphere = make_float4(__uint_as_float(w2.x), __uint_as_float(w2.y), __uint_as_float(w2.z), __uint_as_float(w2.w));
-		L.lodCount = w1.z; L.thr0 = __uint_as_float(w3.x); L.thr1 = __uint_as_float(w3.y);
-
-		Mat m[CL_BATCHES];
-		const uint32_t jw = warp * CL_PER_WARP + lane;
-#pragma unroll
-		for(int k = 0; k < CL_BATCHES; k++) {
-			uint32_t jj = jw + k * 32;
-			if(jj < cnt) m[k] = loadMat(mats + 64ull * jj);
-		}
-		int lod[CL_BATCHES];
-		uint32_t bal[CL_BATCHES][3];
-		uint32_t wc0 = 0, wc1 = 0, wc2 = 0, nearCnt = 0;
-#pragma unroll
-		for(int k = 0; k < CL_BATCHES; k++) {
-			uint32_t jj = jw + k * 32;
-			bool nb = false;
-			lod[k] = -1;
-			if(jj < cnt) lod[k] = evalInstance(m[k], L, A.plane, A.eye, nb);
-			bal[k][0] = __ballot_sync(0xffffffffu, lod[k] == 0);
-			bal[k][1] = __ballot_sync(0xffffffffu, lod[k] == 1);
-			bal[k][2] = __ballot_sync(0xffffffffu, lod[k] == 2);
-			nearCnt += __popc(__ballot_sync(0xffffffffu, nb));
-			wc0 += __popc(bal[k][0]); wc1 += __popc(bal[k][1]); wc2 += __popc(bal[k][2]);
-		}
-		if(lane == 0) { sWarpCnt[warp][0] = wc0; sWarpCnt[warp][1] = wc1; sWarpCnt[warp][2] = wc2; sWarpCnt[warp][3] = nearCnt; }
-		if(tid == 0) sItem[(it + 1) & 1] = nextItem;
-		__syncthreads();
-
-		if(tid == 0) {
-			uint32_t t0 = 0, t1 = 0, t2 = 0, nb = 0;
-#pragma unroll
-			for(int q = 0; q < CL_WARPS; q++) { t0 += sWarpCnt[q][0]; t1 += sWarpCnt[q][1]; t2 += sWarpCnt[q][2]; nb += sWarpCnt[q][3]; }
-			uint32_t nCmd = (t0 ? 1u : 0u) + (t1 ? 1u : 0u) + (t2 ? 1u : 0u), nInst = t0 + t1 + t2;
-			uint32_t s0 = 0xffffffffu, s1 = 0xffffffffu, s2 = 0xffffffffu;
-			if(nb) atomicAdd(&A.hdr->nearBandCount, nb);
-			if(nInst) {
-				unsigned long long base = atomicAdd(A.counts + stateSet, (unsigned long long)nCmd | ((unsigned long long)nInst << 32));
-				uint4 reg = ldg_u4(reinterpret_cast<uint64_t>(A.regions + stateSet));
-				uint32_t cmdOff = uint32_t(base), instOff = uint32_t(base >> 32);
-				if(cmdOff + nCmd > reg.y || instOff + nInst > reg.w)
-					atomicOr(&A.hdr->status, CADR_CULL_STATUS_REGION_OVERFLOW);
-				else {
-					s0 = reg.z + instOff; s1 = s0 + t0; s2 = s1 + t1;
-					sCmdBase = reg.x + cmdOff;
-				}
-			}
-			sLodStart[0] = s0; sLodStart[1] = s1; sLodStart[2] = s2;
-		}
-		__syncthreads();
-
-		if(sLodStart[0] != 0xffffffffu) {
-			uint32_t t0 = 0, t1 = 0, t2 = 0;
-#pragma unroll
-			for(int q = 0; q < CL_WARPS; q++) { t0 += sWarpCnt[q][0]; t1 += sWarpCnt[q][1]; t2 += sWarpCnt[q][2]; }
-			if(tid < 3) {
-				const uint32_t tl = (tid == 0) ? t0 : (tid == 1) ? t1 : t2;
-				if(tl) {
-					uint32_t ci = sCmdBase + ((tid > 0 && t0) ? 1u : 0u) + ((tid > 1 && t1) ? 1u : 0u);
-					const uint4 w4 = w[4], w5 = w[5];
-					const uint32_t ic = (tid == 0) ? w4.x : (tid == 1) ? w4.z : w5.x;
-					const uint32_t fi = (tid == 0) ? w4.y : (tid == 1) ? w4.w : w5.y;
-					writeCommandRecord(A, ci, ic, tl, fi, sLodStart[tid], d, uint32_t(tid), w[6], w[7]);
-				}
-			}
-			uint32_t pre0 = sLodStart[0], pre1 = sLodStart[1], pre2 = sLodStart[2];
-			for(int q = 0; q < warp; q++) { pre0 += sWarpCnt[q][0]; pre1 += sWarpCnt[q][1]; pre2 += sWarpCnt[q][2]; }
-			const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-			for(int k = 0; k < CL_BATCHES; k++) {
-				uint32_t j = j0 + jw + k * 32;
-				if(lod[k] == 0) A.instOut[pre0 + __popc(bal[k][0] & lt)] = j;
-				if(lod[k] == 1) A.instOut[pre1 + __popc(bal[k][1] & lt)] = j;
-				if(lod[k] == 2) A.instOut[pre2 + __popc(bal[k][2] & lt)] = j;
-				pre0 += __popc(bal[k][0]); pre1 += __popc(bal[k][1]); pre2 += __popc(bal[k][2]);
-			}
-		}
-		__syncthreads();
-	}
-}
-
 static int cullVariant()
 {
 	const char* v = std::getenv("CADR_B200_CULL_VARIANT");
@@ -1267,19 +694,8 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 	if(p.chunkCapacity) {
 		const int variant = cullVariant();
 		ctx->timeBegin(KS_CULL_LARGE, s);
-		if(variant == 0) {
-			uint32_t gridL = uint32_t(ctx->smCount) * 2u;   // two CTAs per SM (launch bounds)
-			if(gridL > p.chunkCapacity) gridL = p.chunkCapacity;
-			cullLargeLdgKernel<<<gridL, CL_THREADS, 0, s>>>(A);
-		}
-		else if(variant == 2) {
-			uint32_t gridL = uint32_t(ctx->smCount) * 4u;   // persistent warps: four CTAs of eight warps per SM
-			const uint32_t need = (p.chunkCapacity + CM_THREADS / 32 - 1) / (CM_THREADS / 32);
-			if(gridL > need) gridL = need;
-			cullListWarpKernel<<<gridL, CM_THREADS, 0, s>>>(A);
-		}
-		else if(variant == 3) {
-			if(!ctx->ringKernelConfigured) {
+		if(variant == 3) {
+			if(!ctx->ringKernelConfigured) {   // per device (a process may hold one context per GPU)
 				CADR_CUDA(cudaFuncSetAttribute(cullListRingKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LW_SMEM_BYTES)));
 				ctx->ringKernelConfigured = true;
 			}
@@ -1288,14 +704,14 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 			if(gridL > need) gridL = need;
 			cullListRingKernel<<<gridL, CM_THREADS, LW_SMEM_BYTES, s>>>(A);
 		}
+		else if(variant == 0 || variant == 1) {
+			if(int r = launchCullVariant(ctx, A, variant, p.chunkCapacity, s)) return r;
+		}
 		else {
-			if(!ctx->largeKernelConfigured) {   // per device (a process may hold one context per GPU)
-				CADR_CUDA(cudaFuncSetAttribute(cullLargeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TP_SMEM_BYTES)));
-				ctx->largeKernelConfigured = true;
-			}
-			uint32_t gridL = uint32_t(ctx->smCount);       // persistent: one CTA per SM (215 KB of shared memory each)
-			if(gridL > p.chunkCapacity) gridL = p.chunkCapacity;
-			cullLargeKernel<<<gridL, TP_THREADS, TP_SMEM_BYTES, s>>>(A);
+			uint32_t gridL = uint32_t(ctx->smCount) * 4u;   // persistent warps: four CTAs of eight warps per SM
+			const uint32_t need = (p.chunkCapacity + CM_THREADS / 32 - 1) / (CM_THREADS / 32);
+			if(gridL > need) gridL = need;
+			cullListWarpKernel<<<gridL, CM_THREADS, 0, s>>>(A);
 		}
 		ctx->timeEnd(KS_CULL_LARGE, s);
 		ctx->launches++;
