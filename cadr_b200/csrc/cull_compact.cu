@@ -489,7 +489,6 @@ cullListRingKernel(const __grid_constant__ CullArgs A)
 	const uint32_t ring = smemAddr(lwSmem) + (threadIdx.x >> 5) * uint32_t(LW_WARP_BYTES);   // shared-window address of my ring
 	const uint32_t ringEnd = ring + LW_STAGES * LW_STAGE_BYTES;
 	const uint32_t descs = ringEnd;                                                         // LW_DESCS x 128 bytes
-	const uint32_t lt = (1u << lane) - 1u;
 	const unsigned FULL = 0xffffffffu;
 	// writer: chunk g = k*32 + lane -> matrix k*8 + (lane >> 2), column lane & 3, swizzle ((lane >> 3) & 3)
 	const uint32_t wrOff = (lane >> 2) * 64u + (((lane & 3u) ^ ((lane >> 3) & 3u)) << 4);
@@ -537,7 +536,7 @@ cullListRingKernel(const __grid_constant__ CullArgs A)
 		const uint32_t dA = descs + (seq & 3u) * 128u;
 		const uint4 a0 = ldsU4(dA), a1 = ldsU4(dA + 16u), a2 = ldsU4(dA + 32u), a3 = ldsU4(dA + 48u);
 		const uint4 b0 = ldsU4(descs + ((seq + 1u) & 3u) * 128u), c0 = ldsU4(descs + ((seq + 2u) & 3u) * 128u);
-		const uint32_t N = a0.z, firstInstance = a0.w;
+		const uint32_t N = a0.z;
 		LodInfo L;
 		L.lodCount = a1.z;
 		L.sphere = make_float4(__uint_as_float(a2.x), __uint_as_float(a2.y), __uint_as_float(a2.z), __uint_as_float(a2.w));
