@@ -89,6 +89,8 @@ class CullParams(C.Structure):
         ("exchangeCmd", C.c_uint64 * 8),
         ("exchangePtr", C.c_uint64 * 8),
         ("exchangeTag", C.c_uint64 * 8),
+        ("drawableBounds", C.c_uint64),
+        ("reserved3", C.c_uint64),
     ]
 
 
@@ -129,6 +131,7 @@ SYMBOLS = {
     "cadr_b200_record_drawable_processing": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
     "cadr_b200_cull_compact": (C.c_int, [_P, C.POINTER(CullParams), _P]),
     "cadr_b200_process_and_cull": (C.c_int, [_P, C.POINTER(CullParams), _P]),
+    "cadr_b200_compute_drawable_bounds": (C.c_int, [_P, C.POINTER(CullParams), C.c_uint64, C.c_uint64, C.c_uint32, _P]),
     "cadr_b200_ipc_export": (C.c_int, [_P, C.c_uint64, C.c_char_p]),
     "cadr_b200_ipc_import": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_uint64)]),
     "cadr_b200_ipc_close": (C.c_int, [_P, C.c_uint64]),
@@ -162,7 +165,7 @@ def lib() -> C.CDLL:
             f = getattr(l, name)  # AttributeError if the library does not export a declared symbol
             f.restype = res
             f.argtypes = args
-        if l.cadr_b200_abi_version() != 4:
+        if l.cadr_b200_abi_version() != 5:
             raise ImportError("libcadr_b200.so ABI version mismatch")
         _lib = l
     return _lib
@@ -286,6 +289,9 @@ class Context:
 
     def process_and_cull(self, params: CullParams, stream: int = 0) -> None:
         check(self._l.cadr_b200_process_and_cull(self._h, C.byref(params), _P(stream)))
+
+    def compute_drawable_bounds(self, params: CullParams, bounds_out: int, count: int, indices: int = 0, stream: int = 0) -> None:
+        check(self._l.cadr_b200_compute_drawable_bounds(self._h, C.byref(params), bounds_out, indices, count, _P(stream)))
 
     # -- consumer-side contract check
     def consume_check(self, indirect: int, pointers: int, first: int, n: int, digest_out: int, stream: int = 0) -> None:

@@ -16,7 +16,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--cudart", "static", "-shared",
 ]
-CUDA_SOURCES = ["capi.cu", "process_drawables.cu", "cull_compact.cu", "cull_variants.cu", "upload.cu", "exchange.cu", "consume_check.cu", "external.cu"]
+CUDA_SOURCES = ["capi.cu", "process_drawables.cu", "cull_compact.cu", "cull_variants.cu", "cull_bounds.cu", "upload.cu", "exchange.cu", "consume_check.cu", "external.cu"]
 
 
 def _run(cmd, **kw):

@@ -331,6 +331,14 @@ int cadr_b200_process_and_cull(cadr_ctx* ctx, const cadr_cull_params* params, ca
 	return launchCullCompact(ctx, *params, ctx->pick(stream), true);
 }
 
+int cadr_b200_compute_drawable_bounds(cadr_ctx* ctx, const cadr_cull_params* params, uint64_t boundsOut,
+                                      uint64_t drawableIndices, uint32_t count, cadr_stream stream)
+{
+	REQUIRE_DEVICE(ctx);
+	if(!params) return setError(CADR_E_LOGIC, "compute_drawable_bounds: null params");
+	return launchComputeBounds(ctx, *params, boundsOut, drawableIndices, count, ctx->pick(stream));
+}
+
 size_t cadr_b200_cull_counters_bytes(uint32_t numStateSets)
 {
 	return sizeof(cadr_cull_header) + size_t(numStateSets) * sizeof(uint64_t);

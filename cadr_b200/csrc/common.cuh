@@ -118,6 +118,7 @@ __device__ __forceinline__ uint64_t lookupHandle(uint64_t root, uint64_t handle)
 int launchProcessDrawables(cadr_ctx* ctx, uint64_t root, uint32_t level, uint64_t drawableList,
                            uint64_t indirectOut, uint64_t pointersOut, uint64_t n, cudaStream_t s);
 int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, bool fused);
+int launchComputeBounds(cadr_ctx* ctx, const cadr_cull_params& p, uint64_t boundsOut, uint64_t indices, uint32_t count, cudaStream_t s);
 int launchScatterCopy(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n, uint64_t stagingDevAddr, cudaStream_t s);
 int launchPatchHandles(cadr_ctx* ctx, uint64_t root, uint32_t level, const cadr_handle_patch* patches, uint32_t n, cudaStream_t s);
 

@@ -44,6 +44,7 @@ struct CullArgs {
 	unsigned long long* counts;
 	WorkItem* items;
 	uint32_t  chunkCapacity;
+	const float4* bounds;                 // optional cadr_drawable_bound[n] = 2 x float4 each (pre-test of long lists), or nullptr
 	uint32_t  n;
 	uint32_t  numStateSets;
 	uint32_t  diagNoEval;                 // CADR_B200_DIAG_NOEVAL=1: list kernels skip the evaluation (memory-system ceiling of the access structure)

@@ -101,6 +101,27 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 	}
 	const uint64_t matrixList = uint64_t(p1.x) | (uint64_t(p1.y) << 32);
 
+	// ---- optional pre-test of a long list: its bound lies outside one plane by more than the margin ----------
+	// margin = twice the near band + 32 ulps of every magnitude that enters either test (the per-instance dot products
+	// round three times each, this one four times; cull_bounds.cu inflates the bound itself), so a dropped drawable has
+	// no visible and no near-band instance: the frame's result does not depend on the table.
+	if(A.bounds != nullptr && N > SMALL_MAX) {
+		const float4 B = __ldg(A.bounds + 2ull * d), H = __ldg(A.bounds + 2ull * d + 1);   // centre + valid, half extents
+		if(B.w >= 0.f) {
+			bool outside = false;
+#pragma unroll
+			for(int k = 0; k < 6; k++) {
+				const float4 n = A.plane[k];
+				// the box corner furthest along the plane normal
+				const float reach = fabsf(n.x) * H.x + fabsf(n.y) * H.y + fabsf(n.z) * H.z;
+				const float t = __fmaf_rn(n.z, B.z, __fmaf_rn(n.y, B.y, __fmaf_rn(n.x, B.x, n.w))) + reach;
+				const float mag = fabsf(n.x * B.x) + fabsf(n.y * B.y) + fabsf(n.z * B.z) + fabsf(n.w) + reach;
+				outside = outside || (t < -(2e-5f + 3.8146973e-6f * mag));
+			}
+			if(outside) N = 0;
+		}
+	}
+
 	// ---- number of work items this drawable needs in the large-list queue --------------------------
 	uint32_t nChunks = (N > SMALL_MAX) ? (N + CHUNK - 1) / CHUNK : 0;
 	uint32_t chunkIncl = warpInclusiveScan(nChunks, lane);
@@ -639,6 +660,8 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 		return setError(CADR_E_LOGIC, "cull_compact: output buffers misaligned");
 	if(p.numStateSets == 0)
 		return setError(CADR_E_LOGIC, "cull_compact: numStateSets must be > 0");
+	if(p.drawableBounds & 31)
+		return setError(CADR_E_LOGIC, "cull_compact: drawableBounds must be 32-byte aligned");
 	if(p.chunkCapacity && !p.chunkWorkspace)
 		return setError(CADR_E_LOGIC, "cull_compact: chunkCapacity > 0 but no chunkWorkspace");
 
@@ -657,6 +680,7 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 	A.counts = reinterpret_cast<unsigned long long*>(p.counters + sizeof(cadr_cull_header));
 	A.items = reinterpret_cast<WorkItem*>(p.chunkWorkspace);
 	A.chunkCapacity = p.chunkCapacity;
+	A.bounds = reinterpret_cast<const float4*>(p.drawableBounds);
 	A.n = p.numDrawables;
 	A.numStateSets = p.numStateSets;
 	for(int k = 0; k < 6; k++) A.plane[k] = make_float4(p.planes[k][0], p.planes[k][1], p.planes[k][2], p.planes[k][3]);

@@ -52,6 +52,7 @@ class DeviceScene:
         self.chunk_cap = scene.chunk_capacity
         self.chunk_ws = self._new(max(self.chunk_cap, 1) * 128)   # CADR_CULL_WORK_ITEM_BYTES
         self.root = self.arena + scene.root_off
+        self.bounds = 0               # optional cadr_drawable_bound[n], see compute_bounds()
         # host staging for the drawable list (the reference keeps it in a mapped HOST_CACHED buffer,
         # Renderer.cpp:513-535) — pinned here so the per-frame copy is a true DMA
         self.host_list_ptr = ctx.host_alloc(cap * 48) if ctx.device >= 0 else 0
@@ -114,7 +115,18 @@ class DeviceScene:
         p.numStateSets, p.stateSetRegions = sc.num_state_sets, self.regions
         p.cmdOut, p.ptrOut, p.tagOut, p.instOut, p.counters = self.cmd_out, self.ptr_out, self.tag_out, self.inst_out, self.counters
         p.chunkWorkspace, p.chunkCapacity = self.chunk_ws, self.chunk_cap
+        p.drawableBounds = self.bounds
         return p
+
+    def compute_bounds(self, indices: int = 0, count: int | None = None, stream: int | None = None) -> None:
+        """Optional pre-test: (re)compute the per-drawable bounds from the current matrices (needs the Tier R outputs of
+        the current scene state: run record_drawable_processing / process_drawables first).  Later frames drop long
+        lists that lie outside the frustum without reading their matrices."""
+        s = self.stream if stream is None else stream
+        if not self.bounds:
+            self.bounds = self._new(max(self.scene.n, 1) * 32)
+        p = self.cull_params(np.zeros((6, 4), np.float32), np.zeros(3, np.float32))
+        self.ctx.compute_drawable_bounds(p, self.bounds, self.scene.n if count is None else count, indices, stream=s)
 
     def cull(self, planes: np.ndarray, eye: np.ndarray, stream: int | None = None) -> None:
         s = self.stream if stream is None else stream

@@ -40,7 +40,7 @@ extern "C" {
 # define CADR_API __attribute__((visibility("default")))
 #endif
 
-#define CADR_B200_ABI_VERSION 4
+#define CADR_B200_ABI_VERSION 5
 
 /* ---- error codes (src/CadR/Exceptions.h:13-40) ------------------------------------------------- */
 enum {
@@ -179,7 +179,18 @@ typedef struct cadr_cull_params {
 	uint64_t exchangeCmd[CADR_MAX_PEERS];
 	uint64_t exchangePtr[CADR_MAX_PEERS];
 	uint64_t exchangeTag[CADR_MAX_PEERS];
+	/* Optional pre-test (no reference counterpart): cadr_drawable_bound[numDrawables] written by
+	 * cadr_b200_compute_drawable_bounds, or 0.  A drawable with more than CADR_CULL_SMALL_LIST_MAX matrices whose bound
+	 * lies outside one frustum plane by more than a rounding-safe margin is dropped before any of its matrices is read;
+	 * the result of the frame is identical with and without the table. */
+	uint64_t drawableBounds;
+	uint64_t reserved3;
 } cadr_cull_params;
+
+/* World-space axis-aligned box that encloses the bounding spheres of ALL instances of a drawable (the drawable's
+ * model-space sphere under every matrix of its MatrixList), slightly inflated; valid < 0: no bound (never used to
+ * skip).  Must be recomputed when the drawable's matrices, MatrixList or model-space sphere change. */
+typedef struct cadr_drawable_bound { float center[3]; float valid; float halfExtent[3]; float reserved; } cadr_drawable_bound;  /* 32 B */
 
 /* Publishing a rank's per-range counters to its peers and signalling "frame complete" (stream-ordered after the
  * cull kernels), and waiting until every peer has done the same.  Flags are monotonically increasing frame
@@ -287,6 +298,14 @@ CADR_API int  cadr_b200_record_drawable_processing(cadr_ctx* ctx, const cadr_dra
 
 /* No reference counterpart.  Specification: DESIGN.md "Tier X". */
 CADR_API int  cadr_b200_cull_compact(cadr_ctx* ctx, const cadr_cull_params* params, cadr_stream stream);
+
+/* Fill bounds[d] for the `count` drawables listed in drawableIndices (device array of uint32_t), or for drawables
+ * [0, count) when drawableIndices is 0.  Reads params->indirectData / drawablePointers (Tier R outputs of the current
+ * scene state: numMatrices, matrix list address), params->cullData (model-space spheres) and every matrix of the
+ * listed drawables once; lists of <= CADR_CULL_SMALL_LIST_MAX matrices get radius -1 (their thread evaluates them
+ * directly).  One warp per drawable. */
+CADR_API int  cadr_b200_compute_drawable_bounds(cadr_ctx* ctx, const cadr_cull_params* params, uint64_t boundsOut,
+                                                uint64_t drawableIndices, uint32_t count, cadr_stream stream);
 
 /* cadr_b200_process_drawables + cadr_b200_cull_compact in ONE pass over the drawable list: the first kernel also
  * resolves the handles and writes params->indirectData / params->drawablePointers (which are OUTPUTS here, with

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     l = ctypes.CDLL(cadr_b200.LIB_PATH)
     for name in declared_symbols():
         assert hasattr(l, name), name
-    assert cadr_b200.lib().cadr_b200_abi_version() == 4
+    assert cadr_b200.lib().cadr_b200_abi_version() == 5
 
 
 def test_struct_sizes_match_header():
@@ -39,7 +39,8 @@ def test_struct_sizes_match_header():
     assert _capi.CullParams.stateSetRegions.offset == 168
     assert _capi.CullParams.exchangeWorld.offset == 232
     assert _capi.CullParams.exchangeTag.offset == 232 + 16 + 2 * 64
-    assert ctypes.sizeof(_capi.CullParams) == 232 + 16 + 3 * 64
+    assert _capi.CullParams.drawableBounds.offset == 232 + 16 + 3 * 64
+    assert ctypes.sizeof(_capi.CullParams) == 232 + 16 + 3 * 64 + 16
     assert ctypes.sizeof(_capi.ExchangeSync) == 32 + 2 * 64
     assert cadr_b200.lib().cadr_b200_cull_counters_bytes(64) == 64 + 64 * 8
 
