@@ -304,7 +304,21 @@ def run_b200(args):
             return np.stack([np.uint64(ds.arena) + scene.ml_off[lists] + np.uint64(64), src, size], axis=1)
 
         rewrite = dict(regions=[regions_of(f) for f in range(16)], stage_dev=stage_dev, stage_host=stage_host,
-                       bytes=rw_lists * blk, lists=rw_lists)
+                       bytes=rw_lists * blk, lists=rw_lists, touched=None)
+        if args.list_bounds:
+            # the drawables whose bounds go stale with each frame's rewrite (device index lists, built once)
+            drawable_of_list = np.argsort(scene.drawable_ml).astype(np.uint32)
+            touched = []
+            for f in range(16):
+                lists = (f * 10007 + np.arange(rw_lists, dtype=np.int64) * 7919) % scene.n
+                t = torch.from_numpy(drawable_of_list[lists].astype(np.int32)).to(dev)
+                touched.append(t)
+            rewrite["touched"] = touched
+
+    def refresh_bounds(k):
+        if rewrite is not None and rewrite["touched"] is not None:
+            t = rewrite["touched"][k % 16]
+            ds.compute_bounds(indices=t.data_ptr(), count=t.numel())
 
     # multi-GPU exchange: every rank ends up with all ranks' compacted command lists and per-range counters
     ex = px = None
@@ -339,6 +353,7 @@ def run_b200(args):
     def step_device(k, with_exchange=True):
         if rewrite is not None:        # staged bytes already in HBM: scatter kernel only
             ctx.scatter_copy(rewrite["regions"][k % 16], rewrite["stage_dev"], stream=stream)
+            refresh_bounds(k)
         run_cull(k, with_exchange)
 
     counters_dev = arena.tensor(ds.counters)
@@ -364,6 +379,7 @@ def run_b200(args):
         ds.drawable_list = lists[k % 2]
         if rewrite is not None:        # Renderer::executeCopyOperations: pinned host staging -> device ranges (PCIe)
             ctx.upload(rewrite["regions"][k % 16], rewrite["stage_host"], stream=stream)
+            refresh_bounds(k)
         run_cull(k, True)
         counters_host[k % 2].copy_(counters_dev, non_blocking=True)
         frame_done[k % 2].record(stream_t)
