@@ -79,6 +79,11 @@ class Renderer {
 	bool _collectFrameInfo = false;
 	FrameInfo _inProgress, _completed;
 	uint64_t _countsEpoch = 0;
+	// optional pre-test of the culling pass (cadr_b200_compute_drawable_bounds): one box per flattened drawable,
+	// recomputed by submit() whenever anything it depends on changed since it was last computed
+	bool _useDrawableBounds = false;
+	uint64_t _boundsAddress = 0, _boundsInputsEpoch = 0, _boundsComputedEpoch = ~uint64_t(0);
+	size_t _boundsCapacity = 0;
 	// device-resident drawable list: only ranges whose records changed since they were last copied are
 	// written to the staging list and DMA'd; the reference re-copies the whole list every frame (Renderer.cpp:635-644)
 	bool _incrementalList = true, _residentValid = false;
@@ -118,6 +123,12 @@ public:
 
 	void notifyInstanceCountsChanged() noexcept { _countsEpoch++; }   ///< drawables / matrix-list sizes / LOD tables changed
 	uint64_t countsEpoch() const { return _countsEpoch; }
+	/// Anything the per-drawable bounds depend on changed: matrices, MatrixList of a drawable, model-space sphere,
+	/// the set or order of drawables.
+	void notifyBoundsInputsChanged() noexcept { _boundsInputsEpoch++; }
+	/// Extension, off by default: let the culling pass drop long MatrixLists that lie outside the frustum before their
+	/// matrices are read.  Results are identical; a frame after a scene change pays one extra pass over the matrices.
+	void setDrawableBounds(bool on) { _useDrawableBounds = on; _boundsComputedEpoch = ~uint64_t(0); }
 	bool hasDevice() const;
 	/// Off: copy the whole flattened list every frame exactly like the reference.  On (default): copy what changed.
 	void setIncrementalDrawableUpload(bool on) { _incrementalList = on; _residentValid = false; }

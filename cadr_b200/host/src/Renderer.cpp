@@ -41,7 +41,7 @@ Renderer::~Renderer()
 	_dataStorage.reset();       // handle table and buffers first: they return staging blocks
 	_stagingManager.reset();
 	freeDrawableBuffers();
-	for(uint64_t a : {_cull.commands, _cull.pointers, _cull.tags, _cull.instances, _cull.counters, _cullRegionsAddress, _cullWorkspaceAddress})
+	for(uint64_t a : {_cull.commands, _cull.pointers, _cull.tags, _cull.instances, _cull.counters, _cullRegionsAddress, _cullWorkspaceAddress, _boundsAddress})
 		if(a) cadr_b200_arena_free(_ctx, a);
 	if(_defaultRenderer == this) _defaultRenderer = nullptr;
 	if(_ownsContext) cadr_b200_destroy(_ctx);
@@ -278,7 +278,32 @@ void Renderer::submit()
 		p.counters = _cull.counters;
 		p.chunkWorkspace = _cullWorkspaceAddress;
 		p.chunkCapacity = uint32_t(_rangeChunks);
-		check(cadr_b200_process_and_cull(_ctx, &p, _stream));
+		if(!_useDrawableBounds) {
+			check(cadr_b200_process_and_cull(_ctx, &p, _stream));
+			return;
+		}
+		// bounds are indexed by flattened drawable: every change of the list, of a MatrixList or of a sphere makes them stale
+		const uint64_t epoch = _boundsInputsEpoch + _countsEpoch;
+		if(_boundsCapacity < _recordedDrawables || !_boundsAddress) {
+			if(_boundsAddress) check(cadr_b200_arena_free(_ctx, _boundsAddress));
+			_boundsAddress = 0;
+			_boundsCapacity = std::max<size_t>(size_t(double(_recordedDrawables) * 1.2), 128);
+			check(cadr_b200_arena_alloc(_ctx, _boundsCapacity * sizeof(cadr_drawable_bound), &_boundsAddress));
+			_boundsComputedEpoch = ~uint64_t(0);
+		}
+		if(_boundsComputedEpoch != epoch || _lastListUploadBytes != 0) {
+			// two-call form: the bounds pass needs this frame's Tier R records (matrix list addresses, counts)
+			check(cadr_b200_process_drawables(_ctx, p.handleTableRoot, p.handleLevel, p.drawableList, p.indirectData, p.drawablePointers,
+			                                  _recordedDrawables, _stream));
+			check(cadr_b200_compute_drawable_bounds(_ctx, &p, _boundsAddress, 0, uint32_t(_recordedDrawables), _stream));
+			_boundsComputedEpoch = epoch;
+			p.drawableBounds = _boundsAddress;
+			check(cadr_b200_cull_compact(_ctx, &p, _stream));
+		}
+		else {
+			p.drawableBounds = _boundsAddress;
+			check(cadr_b200_process_and_cull(_ctx, &p, _stream));
+		}
 	}
 }
 

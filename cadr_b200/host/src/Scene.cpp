@@ -30,6 +30,7 @@ mat4* MatrixList::editNewContent(size_t numMatrices)
 	StagingData sd = _matrixList.alloc(sizeof(mat4) * numMatrices + sizeof(mat4));
 	mat4* m = sd.data<mat4>();
 	initHeader(m, numMatrices);
+	_matrixList.renderer().notifyBoundsInputsChanged();
 	if(numMatrices != _numMatrices) {
 		_numMatrices = numMatrices;
 		_matrixList.renderer().notifyInstanceCountsChanged();
@@ -144,6 +145,7 @@ void Drawable::setCullData(const BoundingSphere& bs, uint32_t lodCount, const ui
 		c.lodThreshold[l] = lodThresholds ? lodThresholds[l] : 0.f;
 	_stateSet->_modCount++;
 	_stateSet->renderer().notifyInstanceCountsChanged();
+	_stateSet->renderer().notifyBoundsInputsChanged();
 }
 
 // ---- StateSet ---------------------------------------------------------------------------------------

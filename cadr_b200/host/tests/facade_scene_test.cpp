@@ -39,13 +39,14 @@ struct Geo { std::unique_ptr<Geometry> g; std::vector<PrimitiveSet> ps; };
 
 int main(int argc, char** argv)
 {
-	if(argc < 3) { fprintf(stderr, "usage: %s <device|-1> <dump> [frames]\n", argv[0]); return 2; }
+	if(argc < 3) { fprintf(stderr, "usage: %s <device|-1> <dump> [frames] [bounds]\n", argv[0]); return 2; }
 	const int device = atoi(argv[1]);
 	const int frames = argc > 3 ? atoi(argv[3]) : 4;
 	g_out = fopen(argv[2], "wb");
 	if(!g_out) return 2;
 	try {
 		Renderer r(device);
+		if(argc > 4 && std::string(argv[4]) == "bounds") r.setDrawableBounds(true);
 		Shadow shadow;
 		r.dataStorage().uploadObserver = [&](const cadr_copy_region* regs, size_t n) { shadow.sync(r.dataStorage()); shadow.apply(regs, n); };
 		std::mt19937 rng(1234);

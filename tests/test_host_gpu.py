@@ -25,10 +25,12 @@ def test_reference_data_allocation_scenarios_on_device():
     assert r.returncode == 0, r.stderr
 
 
-@pytest.fixture(scope="module")
-def gpu_frames(tmp_path_factory):
+@pytest.fixture(scope="module", params=["plain", "bounds"])
+def gpu_frames(tmp_path_factory, request):
+    """`bounds`: the same scene with Renderer::setDrawableBounds(true) — the pre-test must not change any result."""
     out = str(tmp_path_factory.mktemp("facade") / "scene.bin")
-    r = subprocess.run([os.path.join(BIN, "facade_scene_test"), "0", out, "5"], capture_output=True, text=True)
+    r = subprocess.run([os.path.join(BIN, "facade_scene_test"), "0", out, "5"] + (["bounds"] if request.param == "bounds" else []),
+                       capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     frames = parse(out)
     os.remove(out)
