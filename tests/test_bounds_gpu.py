@@ -151,3 +151,26 @@ def test_c3_full_size_with_bounds_equals_without(ctx):
         assert qa == 100_000 and qb < 0.6 * qa
     finally:
         ds.close()
+
+
+def test_bounds_api_misuse_is_a_logic_error(ctx):
+    import cadr_b200
+    sc = synth.random_scene(75, n=50, list_counts=[100] * 5, state_sets=1)
+    ds = DeviceScene(ctx, sc)
+    try:
+        ds.record_drawable_processing(); ctx.sync(ds.stream)
+        p = ds.cull_params(np.zeros((6, 4), np.float32), np.zeros(3, np.float32))
+        buf = ctx.arena_alloc(50 * 32 + 64)
+        with pytest.raises(cadr_b200.LogicError):
+            ctx.compute_drawable_bounds(p, buf + 16, 50)            # 32-byte alignment
+        with pytest.raises(cadr_b200.LogicError):
+            ctx.compute_drawable_bounds(p, buf, 51)                 # more than numDrawables without an index list
+        with pytest.raises(cadr_b200.LogicError):
+            ctx.compute_drawable_bounds(p, 0, 50)
+        p.drawableBounds = buf + 16
+        with pytest.raises(cadr_b200.LogicError):
+            ctx.cull_compact(p)
+        ctx.compute_drawable_bounds(p, buf, 0)                      # nothing to do is fine
+        ctx.arena_free(buf)
+    finally:
+        ds.close()
