@@ -24,7 +24,7 @@ computeBoundsKernel(const uint4* __restrict__ indirect, const uint4* __restrict_
 		const uint4 p1 = ldg_u4(reinterpret_cast<uint64_t>(pointers + 2ull * d + 1));
 		const uint4 sb = ldg_u4(reinterpret_cast<uint64_t>(cullData + 3ull * d));
 		const float4 b = make_float4(__uint_as_float(sb.x), __uint_as_float(sb.y), __uint_as_float(sb.z), __uint_as_float(sb.w));
-		if(N <= SMALL_MAX || !(b.w >= 0.f)) {       // evaluated by its own thread / empty sphere: no bound needed
+		if(N < CADR_CULL_BOUNDS_MIN_LIST || !(b.w >= 0.f)) {       // too short to be worth a pre-test / empty sphere
 			if(lane == 0) { bounds[2ull * d] = make_float4(0.f, 0.f, 0.f, -1.f); bounds[2ull * d + 1] = make_float4(0.f, 0.f, 0.f, 0.f); }
 			continue;
 		}

@@ -101,11 +101,11 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 	}
 	const uint64_t matrixList = uint64_t(p1.x) | (uint64_t(p1.y) << 32);
 
-	// ---- optional pre-test of a long list: its bound lies outside one plane by more than the margin ----------
+	// ---- optional pre-test of a list: its bound lies outside one plane by more than the margin ------------------
 	// margin = twice the near band + 32 ulps of every magnitude that enters either test (the per-instance dot products
 	// round three times each, this one four times; cull_bounds.cu inflates the bound itself), so a dropped drawable has
 	// no visible and no near-band instance: the frame's result does not depend on the table.
-	if(A.bounds != nullptr && N > SMALL_MAX) {
+	if(A.bounds != nullptr && N >= CADR_CULL_BOUNDS_MIN_LIST) {
 		const float4 B = __ldg(A.bounds + 2ull * d), H = __ldg(A.bounds + 2ull * d + 1);   // centre + valid, half extents
 		if(B.w >= 0.f) {
 			bool outside = false;

@@ -138,6 +138,7 @@ typedef struct cadr_cull_header {
 #define CADR_CULL_WORK_ITEM_BYTES        128u   /* one self-contained descriptor per <= 1024 matrices */
 #define CADR_CULL_SMALL_LIST_MAX         32u    /* lists up to this size are evaluated by one thread; longer ones become work items */
 #define CADR_CULL_WORK_ITEM_INSTANCES    1024u
+#define CADR_CULL_BOUNDS_MIN_LIST         4u     /* the optional bounds pre-test applies to lists of at least this many matrices */
 
 #define CADR_MAX_PEERS 8
 
@@ -180,7 +181,7 @@ typedef struct cadr_cull_params {
 	uint64_t exchangePtr[CADR_MAX_PEERS];
 	uint64_t exchangeTag[CADR_MAX_PEERS];
 	/* Optional pre-test (no reference counterpart): cadr_drawable_bound[numDrawables] written by
-	 * cadr_b200_compute_drawable_bounds, or 0.  A drawable with more than CADR_CULL_SMALL_LIST_MAX matrices whose bound
+	 * cadr_b200_compute_drawable_bounds, or 0.  A drawable with at least CADR_CULL_BOUNDS_MIN_LIST matrices whose bound
 	 * lies outside one frustum plane by more than a rounding-safe margin is dropped before any of its matrices is read;
 	 * the result of the frame is identical with and without the table. */
 	uint64_t drawableBounds;
@@ -302,8 +303,8 @@ CADR_API int  cadr_b200_cull_compact(cadr_ctx* ctx, const cadr_cull_params* para
 /* Fill bounds[d] for the `count` drawables listed in drawableIndices (device array of uint32_t), or for drawables
  * [0, count) when drawableIndices is 0.  Reads params->indirectData / drawablePointers (Tier R outputs of the current
  * scene state: numMatrices, matrix list address), params->cullData (model-space spheres) and every matrix of the
- * listed drawables once; lists of <= CADR_CULL_SMALL_LIST_MAX matrices get radius -1 (their thread evaluates them
- * directly).  One warp per drawable. */
+ * listed drawables once; lists shorter than CADR_CULL_BOUNDS_MIN_LIST get valid = -1 (testing the bound would cost what
+ * evaluating them costs).  One warp per drawable. */
 CADR_API int  cadr_b200_compute_drawable_bounds(cadr_ctx* ctx, const cadr_cull_params* params, uint64_t boundsOut,
                                                 uint64_t drawableIndices, uint32_t count, cadr_stream stream);
 

@@ -36,8 +36,9 @@ def clusterise(sc, seed, cube=400.0, sigma=6.0):
 
 
 @pytest.mark.parametrize("kw", [dict(seed=71, n=500, num_lists=60, max_count=300, state_sets=4, big_lists=4),
-                                dict(seed=72, n=300, list_counts=[33, 64, 100, 700, 1500, 2500, 40, 5, 0], state_sets=3, first_handle=2040)],
-                         ids=["ragged", "boundaries"])
+                                dict(seed=72, n=300, list_counts=[33, 64, 100, 700, 1500, 2500, 40, 5, 0], state_sets=3, first_handle=2040),
+                                dict(seed=76, n=900, list_counts=[4, 8, 16, 32, 5, 31, 3, 1, 2, 0], state_sets=3)],
+                         ids=["ragged", "boundaries", "short-lists-only"])
 @pytest.mark.parametrize("fused", [True, False], ids=["fused", "two-calls"])
 def test_result_is_identical_with_bounds_and_work_items_are_dropped(ctx, kw, fused):
     sc = synth.random_scene(**kw)
@@ -59,7 +60,7 @@ def test_result_is_identical_with_bounds_and_work_items_are_dropped(ctx, kw, fus
             assert_tier_x_equal(got, ref)
             assert got["chunk_count"] <= queued_without[f]
             dropped += queued_without[f] - got["chunk_count"]
-        assert dropped > 0
+        assert dropped > 0 or not (sc.ml_count > 32).any()      # short lists are dropped by their own thread, not from the queue
     finally:
         ds.close()
 
