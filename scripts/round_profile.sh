@@ -4,11 +4,13 @@
 tag=${1:-r01h}
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-for w in c3 c2 c4 c5; do
-  python bench.py --workload $w --steps 100 $([ $w = c3 ] || echo --no-cpu-baseline) > gpurun_out/${tag}_bench_$w.json 2> gpurun_out/${tag}_bench_$w.err
+for w in c3 c1 c2 c4 c5; do
+  python bench.py --workload $w $([ $w = c3 ] || echo --no-cpu-baseline) > gpurun_out/${tag}_bench_$w.json 2> gpurun_out/${tag}_bench_$w.err
   tail -c 400 gpurun_out/${tag}_bench_$w.json
 done
 python bench.py --impl reference > gpurun_out/${tag}_bench_reference.json 2>/dev/null
+python bench.py --list-bounds --no-cpu-baseline > gpurun_out/${tag}_bench_c3_list_bounds.json 2>/dev/null
+python bench.py --workload c4 --list-bounds --no-cpu-baseline > gpurun_out/${tag}_bench_c4_list_bounds.json 2>/dev/null
 for w in c3 c2; do
   ncu --nvtx --nvtx-include "timed/" --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches_$w.csv \
       python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_launches_$w.log 2>&1
