@@ -173,7 +173,8 @@ def cpu_sample_run(args, steps: int, warmup: int, sample_drawables: int | None =
     """Time the oracle (Tier R + Tier X evaluation, OpenMP) on the first `sample` drawables of the workload.
     -> (instances/s, description, threads, seconds per step)"""
     from oracle import binding as ob
-    threads = ob.max_threads()
+    # every host core this process may run on; not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its ranks
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or ob.max_threads())
     if sample_drawables is None:
         sample_drawables = args.cpu_sample or (8000 if args.workload in C3_SHAPED else 1_000_000 if args.workload == "c1" else 4_000_000)
     sc = make_scene(args, 0, host_matrices=True, drawables=sample_drawables)
