@@ -97,15 +97,16 @@ __device__ __forceinline__ int evalInstance(const Mat& m, const LodInfo& L, cons
 
 	bool nonEmpty = b.w >= 0.f;             // radius < 0 (incl. -inf): empty sphere, never visible (:39-43)
 	bool visible = nonEmpty;
-	// any_k |dot_k + r| < 1e-5  ==  min_k |dot_k + r| < 1e-5 (fminf skips a NaN term exactly like the comparison would)
-	float nearest = __int_as_float(0x7f800000);
+	// near a plane = the MOST violated plane (smallest dot_k + r; fminf skips a NaN term) lies within 1e-5: the test
+	// that decides the instance is in the band.  Clearly outside one plane and touching the extension of another is not near.
+	float worst = __int_as_float(0x7f800000);
 #pragma unroll
 	for(int k = 0; k < 6; k++) {
 		float dot = __fmaf_rn(plane[k].z, cz, __fmaf_rn(plane[k].y, cy, __fmaf_rn(plane[k].x, cx, plane[k].w)));
 		visible = visible && (dot >= -r);
-		nearest = fminf(nearest, fabsf(__fadd_rn(dot, r)));
+		worst = fminf(worst, __fadd_rn(dot, r));
 	}
-	const bool nearP = nearest < 1e-5f;
+	const bool nearP = fabsf(worst) < 1e-5f;
 	float dx = __fadd_rn(cx, -eye.x), dy = __fadd_rn(cy, -eye.y), dz = __fadd_rn(cz, -eye.z);
 	float dist = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
 	int lod = 0;
@@ -141,13 +142,14 @@ __device__ __forceinline__ void evalInstancePair(const Mat& a, const Mat& b, con
 	const float2 r = __fmul2_rn(CADR_P2(__fsqrt_rn(sA), __fsqrt_rn(sB)), CADR_D2(sp.w));
 
 	const bool nonEmpty = sp.w >= 0.f;
-	bool visA = nonEmpty, visB = nonEmpty, npA = false, npB = false;
+	bool visA = nonEmpty, visB = nonEmpty;
+	float worstA = __int_as_float(0x7f800000), worstB = worstA;      // smallest dot_k + r, see evalInstance
 #pragma unroll
 	for(int k = 0; k < 6; k++) {
 		const float2 dot = __ffma2_rn(CADR_D2(plane[k].z), cz, __ffma2_rn(CADR_D2(plane[k].y), cy, __ffma2_rn(CADR_D2(plane[k].x), cx, CADR_D2(plane[k].w))));
 		const float2 t = __fadd2_rn(dot, r);
 		visA = visA && (dot.x >= -r.x); visB = visB && (dot.y >= -r.y);
-		npA = npA || (fabsf(t.x) < 1e-5f); npB = npB || (fabsf(t.y) < 1e-5f);
+		worstA = fminf(worstA, t.x); worstB = fminf(worstB, t.y);
 	}
 	const float2 dx = __fadd2_rn(cx, CADR_D2(-eye.x)), dy = __fadd2_rn(cy, CADR_D2(-eye.y)), dz = __fadd2_rn(cz, CADR_D2(-eye.z));
 	const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
@@ -164,8 +166,8 @@ __device__ __forceinline__ void evalInstancePair(const Mat& a, const Mat& b, con
 		const float2 e = __fadd2_rn(CADR_P2(distA, distB), CADR_D2(-L.thr1));
 		ntA = ntA || (fabsf(e.x) < 1e-5f); ntB = ntB || (fabsf(e.y) < 1e-5f);
 	}
-	nearA = nonEmpty && (npA || (visA && ntA));
-	nearB = nonEmpty && (npB || (visB && ntB));
+	nearA = nonEmpty && (fabsf(worstA) < 1e-5f || (visA && ntA));
+	nearB = nonEmpty && (fabsf(worstB) < 1e-5f || (visB && ntB));
 	lodA = visA ? la : -1;
 	lodB = visB ? lb : -1;
 #undef CADR_P2

@@ -127,7 +127,7 @@ typedef struct cadr_command_tag { uint32_t drawableIndex, lod; } cadr_command_ta
  *   high 32 bits = number of instance indices emitted for the StateSet. */
 typedef struct cadr_cull_header {
 	uint32_t status;          /* bit 0: a region overflowed, bit 1: chunk workspace overflowed, bit 2: bad range index */
-	uint32_t nearBandCount;   /* instances within 1e-5 of a frustum plane or LOD threshold           */
+	uint32_t nearBandCount;   /* instances whose deciding plane test, or LOD threshold, is within 1e-5 */
 	uint32_t chunkCount;      /* internal: work items queued for the list kernel                     */
 	uint32_t chunkCursor;     /* internal: work items claimed                                        */
 	uint32_t reserved[12];

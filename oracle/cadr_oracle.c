@@ -161,12 +161,16 @@ static inline int eval_instance(const float* M /* 16 floats, column-major */, co
 
 	int nonEmpty = bs[3] >= 0.f;           /* BoundingSphere.h:39-43: radius -inf (or < 0) == empty */
 	int visible = nonEmpty;
-	int nearP = 0;
+	/* near a plane = the plane test that decides the instance is within 1e-5: the MOST violated plane (smallest
+	 * dot_k + r; fminf skips a NaN term) lies in the band.  An instance clearly outside one plane is not "near"
+	 * because it also touches the extension of another one: its classification cannot flip. */
+	float worst = INFINITY;
 	for(int k = 0; k < 6; k++) {
 		float dot = fmaf(planes[k][2], cz, fmaf(planes[k][1], cy, fmaf(planes[k][0], cx, planes[k][3])));
 		visible = visible && (dot >= -r);
-		nearP = nearP || (fabsf(dot + r) < 1e-5f);
+		worst = fminf(worst, dot + r);
 	}
+	int nearP = fabsf(worst) < 1e-5f;
 	float dx = cx - eye[0], dy = cy - eye[1], dz = cz - eye[2];
 	float dist = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
 	int lod = 0, nearT = 0;

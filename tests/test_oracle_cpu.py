@@ -148,6 +148,36 @@ def test_tier_x_oracle_against_numpy(kw, frame):
     assert res["num_instances"] < sc.total_instances  # the camera really culls something
 
 
+def test_near_band_counts_only_instances_whose_classification_could_flip():
+    """The near-band definition (Tier X): |min_k(dot_k + r)| < 1e-5, or a visible instance on an LOD threshold.
+    Unit spheres against the planes x >= 0 and z <= 10 (the others far away): touching x = 0 counts, touching x = 0
+    while far beyond z = 10 does not, clearly in / out do not; a visible instance exactly at threshold distance counts."""
+    pos = np.array([[-1.0, 0, 0],            # touches x >= 0 from outside, inside everything else      -> near, visible (dot == -r)
+                    [-1.0 - 4e-6, 0, 0],     # 4e-6 outside                                               -> near, invisible
+                    [-1.0 + 4e-6, 5, 0],     # 4e-6 inside, 5.1 from the eye                              -> near, visible, lod 1
+                    [-1.0, 0, 500.0],        # touches x = 0 but 489 units beyond z <= 10                 -> NOT near
+                    [-1.5, 0, 0],            # clearly outside                                            -> not near
+                    [3.0, 0, 0],             # clearly inside, at distance 3 = threshold                  -> near (threshold), lod 1
+                    [3.0, 0, 500.0]],        # at the threshold distance from nothing visible             -> not near
+                   np.float32)
+    sc = synth.random_scene(90, n=1, list_counts=[len(pos)], state_sets=1, with_drawable_data=False)
+    m = np.zeros((len(pos), 16), np.float32)
+    m[:, 0] = m[:, 5] = m[:, 10] = m[:, 15] = 1.0
+    m[:, 12:15] = pos
+    sc.matrices[:] = m
+    sc.cull[:, 0:3] = 0
+    sc.cull[:, 3] = np.float32(1.0).view(np.uint32)
+    sc.cull[:, 4] = 2                                                     # two LODs, threshold 3.0
+    sc.cull[:, 8] = np.float32(3.0).view(np.uint32)
+    big = 1e9
+    planes = np.array([[1, 0, 0, 0], [-1, 0, 0, big], [0, 1, 0, big], [0, -1, 0, big], [0, 0, 1, big], [0, 0, -1, 10]], np.float32)
+    eye = np.zeros(3, np.float32)
+    _, _, res = oracle_tier_x(sc, planes, eye)
+    assert res["near_band"] == 4
+    canon = canonicalise(res)[0]
+    assert {(d, lod): inst.tolist() for (d, lod, *_x, inst) in canon} == {(0, 0): [0], (0, 1): [2, 5]}
+
+
 def test_tier_x_everything_and_nothing_visible():
     sc = synth.random_scene(21, big_lists=1)
     big = 1e9
