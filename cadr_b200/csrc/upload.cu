@@ -134,9 +134,12 @@ constexpr uint64_t UPLOAD_DMA_THRESHOLD = 1u << 20;
 int launchUpload(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n, const void* stagingBase, cudaStream_t s)
 {
 	const uint8_t* base = static_cast<const uint8_t*>(stagingBase);
-	std::vector<cadr_copy_region> small;   // srcOffset rewritten below to the offset inside the device mirror
-	std::vector<uint32_t> smallIdx;
-	uint64_t lo = ~0ull, hi = 0, sum = 0;
+	// Small regions are grouped by the host block their source lies in: a span may only be shipped whole when every byte
+	// of it is known to be readable.  With a staging base the caller's block covers all offsets by contract; with absolute
+	// addresses (base == nullptr) the blocks handed out by cadr_b200_host_alloc are known, anything else is packed.
+	struct Group { uint64_t lo = ~0ull, hi = 0, sum = 0; std::vector<uint32_t> idx; };
+	std::map<uintptr_t, Group> groups;      // key: start of the containing host block, 0 = the caller's staging block
+	Group loose;                            // sources outside every known block
 	for(uint32_t i = 0; i < n; i++) {
 		const cadr_copy_region& r = regions[i];
 		if(r.bytes == 0) continue;
@@ -148,40 +151,67 @@ int launchUpload(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n, con
 			CADR_CUDA(cudaMemcpyAsync(reinterpret_cast<void*>(r.dstAddr), base + r.srcOffset, r.bytes, cudaMemcpyHostToDevice, s));
 			continue;
 		}
-		small.push_back(r);
-		smallIdx.push_back(i);
-		lo = r.srcOffset < lo ? r.srcOffset : lo;
-		hi = r.srcOffset + r.bytes > hi ? r.srcOffset + r.bytes : hi;
-		sum += r.bytes;
+		Group* g = &loose;
+		if(base != nullptr) g = &groups[0];
+		else {
+			void* src = reinterpret_cast<void*>(uintptr_t(r.srcOffset));
+			auto it = ctx->hostBlocks.upper_bound(src);
+			if(it != ctx->hostBlocks.begin()) {
+				--it;
+				const uintptr_t b0 = reinterpret_cast<uintptr_t>(it->first);
+				if(uintptr_t(r.srcOffset) + r.bytes <= b0 + it->second) g = &groups[b0];
+			}
+		}
+		g->idx.push_back(i);
+		g->lo = r.srcOffset < g->lo ? r.srcOffset : g->lo;
+		g->hi = r.srcOffset + r.bytes > g->hi ? r.srcOffset + r.bytes : g->hi;
+		g->sum += r.bytes;
 	}
+	// dense groups (sources cover >= half of the span) go out as ONE DMA of the span each; everything else is packed on
+	// the host into the pinned scratch (16-B aligned slots keep the scatter kernel's fast path) and goes out as one DMA
+	std::vector<cadr_copy_region> small;     // srcOffset rewritten to the offset inside the device mirror
+	struct Span { uint64_t lo, bytes, mirrorOff; };
+	std::vector<Span> spans;
+	std::vector<uint32_t> packIdx = std::move(loose.idx);
+	uint64_t mirrorBytes = 0;
+	for(auto& [key, g] : groups) {
+		if(g.idx.empty()) continue;
+		const uint64_t lo = g.lo & ~uint64_t(15);                 // keep the 16-byte phase
+		if(g.sum * 2 >= g.hi - lo) {
+			spans.push_back(Span{lo, g.hi - lo, mirrorBytes});
+			for(uint32_t i : g.idx) { cadr_copy_region q = regions[i]; q.srcOffset = mirrorBytes + (q.srcOffset - lo); small.push_back(q); }
+			mirrorBytes += (g.hi - lo + 255) & ~uint64_t(255);
+		}
+		else packIdx.insert(packIdx.end(), g.idx.begin(), g.idx.end());
+	}
+	const uint64_t packBase = mirrorBytes;
+	uint64_t packedBytes = 0;
+	for(uint32_t i : packIdx) { cadr_copy_region q = regions[i]; q.srcOffset = packBase + packedBytes; small.push_back(q); packedBytes += (q.bytes + 15) & ~uint64_t(15); }
+	mirrorBytes += packedBytes;
 	if(small.empty())
 		return CADR_OK;
+
 	const size_t numUnits = countUnits(small.data(), uint32_t(small.size()));
+	if(numUnits > 0x7fffffffull)
+		return setError(CADR_E_LOGIC, "upload: too many copy units");
 	const size_t unitBytes = (numUnits * sizeof(CopyUnit) + 255) & ~size_t(255);
 	CADR_CUDA(cudaEventSynchronize(ctx->hostScratchFree));
 	if(int r = ctx->ensureDevScratch(unitBytes)) return r;
-
-	lo &= ~uint64_t(15);                                   // keep 16-byte phase: the scatter kernel's fast path
-	const uint64_t span = hi - lo;
-	if(sum * 2 >= span) {
-		// dense: one DMA of the span, regions keep their relative positions
-		if(int r = ctx->ensureHostScratch(unitBytes)) return r;
-		if(int r = ctx->ensureDevMirror(span)) return r;
-		for(auto& q : small) q.srcOffset -= lo;
-		fillUnits(static_cast<CopyUnit*>(ctx->hostScratch), small.data(), uint32_t(small.size()), reinterpret_cast<uint64_t>(ctx->devMirror));
-		CADR_CUDA(cudaMemcpyAsync(ctx->devMirror, base + lo, span, cudaMemcpyHostToDevice, s));
-		return shipUnitsAndLaunch(ctx, numUnits, s);
-	}
-	// sparse: pack on the host (16-B aligned slots keep the fast path)
-	size_t packedBytes = 0;
-	for(auto& q : small) { uint64_t b = q.bytes; q.srcOffset = packedBytes; packedBytes += (b + 15) & ~uint64_t(15); }
 	if(int r = ctx->ensureHostScratch(unitBytes + packedBytes)) return r;
-	if(int r = ctx->ensureDevMirror(packedBytes)) return r;
+	if(int r = ctx->ensureDevMirror(mirrorBytes)) return r;
 	fillUnits(static_cast<CopyUnit*>(ctx->hostScratch), small.data(), uint32_t(small.size()), reinterpret_cast<uint64_t>(ctx->devMirror));
-	uint8_t* pack = static_cast<uint8_t*>(ctx->hostScratch) + unitBytes;
-	for(size_t k = 0; k < small.size(); k++)
-		std::memcpy(pack + small[k].srcOffset, base + regions[smallIdx[k]].srcOffset, small[k].bytes);
-	CADR_CUDA(cudaMemcpyAsync(ctx->devMirror, pack, packedBytes, cudaMemcpyHostToDevice, s));
+	uint8_t* mirror = static_cast<uint8_t*>(ctx->devMirror);
+	for(const Span& sp : spans)
+		CADR_CUDA(cudaMemcpyAsync(mirror + sp.mirrorOff, base + sp.lo, sp.bytes, cudaMemcpyHostToDevice, s));
+	if(packedBytes) {
+		uint8_t* pack = static_cast<uint8_t*>(ctx->hostScratch) + unitBytes;
+		uint64_t off = 0;
+		for(uint32_t i : packIdx) {
+			std::memcpy(pack + off, base + regions[i].srcOffset, regions[i].bytes);
+			off += (regions[i].bytes + 15) & ~uint64_t(15);
+		}
+		CADR_CUDA(cudaMemcpyAsync(mirror + packBase, pack, packedBytes, cudaMemcpyHostToDevice, s));
+	}
 	return shipUnitsAndLaunch(ctx, numUnits, s);
 }
 

@@ -59,3 +59,13 @@ def test_facade_frames_on_gpu_match_oracle(gpu_frames):
         ref = ob.cull_compact(mem, f["root"], f["level"], lst, f["n"], ind, ptr, f["cull"], f["planes"], f["eye"], f["regions"])
         assert_tier_x_equal(f["gpu_cull"], ref)
         assert ref["num_instances"] > 0
+
+
+def test_facade_long_run_with_several_staging_blocks():
+    """40 frames of the dynamic facade scene, with and without the bounds pre-test, every frame against the oracle
+    (scripts/soak_facade.py).  Regression: from frame 5 on the uploads of one executeCopyOperations come from more than one
+    staging block."""
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "soak_facade.py"), "40"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "soak_facade: ok" in r.stdout

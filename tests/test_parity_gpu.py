@@ -307,6 +307,41 @@ def test_upload_scatter_and_patch(ctx):
         ctx.arena_free(arena)
 
 
+def test_upload_with_absolute_sources_in_several_staging_blocks(ctx):
+    """stagingBase == NULL: every region names its source by absolute host address (what the facade's DataMemory does,
+    DataMemory.cpp:417-425 with mapped StagingMemory blocks).  Sources that are dense inside EACH block but lie in
+    different pinned blocks must not be shipped as one span across the gap between the blocks (regression: invalid
+    argument from cudaMemcpyAsync after the facade had grown a second staging block); a source outside every known block
+    is packed."""
+    import ctypes
+    nblk, blk = 3, 1 << 20
+    ptrs = [ctx.host_alloc(blk) for _ in range(nblk)]
+    loose = np.random.default_rng(1).integers(0, 256, 4096, dtype=np.uint8)       # not from host_alloc
+    arena = ctx.arena_alloc(8 << 20)
+    try:
+        ctx.memset(arena, 0, 8 << 20)
+        rng = np.random.default_rng(2)
+        host = np.zeros(8 << 20, np.uint8)
+        regs, dst = [], 0
+        for k, p in enumerate(ptrs):
+            buf = np.ctypeslib.as_array((ctypes.c_uint8 * blk).from_address(p))
+            buf[:] = rng.integers(0, 256, blk, dtype=np.uint8)
+            for j in range(40):                                # dense: 40 x 20 000 B of 1 MiB, contiguous
+                regs.append((arena + dst, p + 20_000 * j + 16, 19_000 + 16 * j))
+                host[dst:dst + 19_000 + 16 * j] = buf[20_000 * j + 16:20_000 * j + 16 + 19_000 + 16 * j]
+                dst += 20_480
+        regs.append((arena + dst, loose.ctypes.data + 100, 3000))
+        host[dst:dst + 3000] = loose[100:3100]
+        ctx.upload(np.array(regs, np.uint64), 0)
+        got = np.empty(8 << 20, np.uint8)
+        ctx.memcpy_d2h(got, arena); ctx.sync()
+        assert np.array_equal(got, host)
+    finally:
+        ctx.arena_free(arena)
+        for p in ptrs:
+            ctx.host_free(p)
+
+
 @pytest.mark.parametrize("kw", [dict(seed=31), dict(seed=32, first_handle=1990), dict(seed=33, first_handle=4_194_250)],
                          ids=["L1", "L2", "L3"])
 def test_patch_handles_matches_oracle(ctx, kw):
