@@ -30,13 +30,18 @@ def main():
     dist.all_gather_object(bases, (ds.arena, ds.drawable_list))
     px = shard.PeerExchange(ctx, ds.cmd_cap, sc.num_state_sets)
     ok = True
-    for frame in range(5):
+    # MG_FRAMES frames; with MG_ASYNC=1 they are queued back to back without any host synchronisation (ranks run ahead
+    # of each other as far as the stream-side wait allows) and only the last one is checked
+    frames, run_async = int(os.environ.get("MG_FRAMES", "5")), os.environ.get("MG_ASYNC") == "1"
+    for frame in range(frames):
         planes, eye = synth.orbit_camera(20 * frame, 250.0, far=500.0)
         ds.upload_drawable_list()
         p = ds.cull_params(planes, eye)
         px.begin_frame(p)
         ctx.process_and_cull(p, stream=ds.stream)
         px.end_frame(ds.counters, stream=ds.stream)
+        if run_async and frame + 1 < frames:
+            continue
         ctx.sync(ds.stream)
         g = px.read()
         assert (g["status"] == 0).all()
@@ -74,7 +79,7 @@ def main():
     ctx.close()
     dist.destroy_process_group()
     if rank == 0:
-        print("multigpu_check", "ok" if int(t.item()) == 1 else "FAILED", f"({world} ranks, 5 frames)")
+        print("multigpu_check", "ok" if int(t.item()) == 1 else "FAILED", f"({world} ranks, {frames} frames{', queued without host sync' if run_async else ''})")
     sys.exit(0 if int(t.item()) == 1 else 1)
 
 
