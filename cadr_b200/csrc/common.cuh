@@ -95,6 +95,13 @@ __device__ __forceinline__ void st_stream_u4(void* p, uint4 v)
 	             :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// 32-byte store (STG.E.256, sm_100): one full sector per lane
+__device__ __forceinline__ void st_u8(void* p, uint4 a, uint4 b)
+{
+	asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+	             :: "l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
 // Handle lookup, restating lookupHandle() of processDrawables.comp:77-89.
 // uint(handle) truncations are kept as written there (no masking of the top index).
 template<int LEVEL>

@@ -128,6 +128,15 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 
 	// ---- number of work items this drawable needs in the large-list queue --------------------------
 	uint32_t nChunks = (N > SMALL_MAX) ? (N + CHUNK - 1) / CHUNK : 0;
+	// PrimitiveSets of a queued list: requested here, ahead of the scans and CTA barriers below, so that their latency
+	// (a DRAM round trip when every drawable has its own geometry) is not paid after the queue reservation
+	uint32_t ps[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+	if(nChunks) {
+		const uint64_t psBase = FUSED ? psBaseResolved : primitiveSetBase<LEVEL>(A, d);
+#pragma unroll
+		for(int l = 0; l < 3; l++)
+			if(uint32_t(l) < L.lodCount) { const uint2 v = ldg_u2(psBase + psOff[l]); ps[l][0] = v.x; ps[l][1] = v.y; }
+	}
 	uint32_t chunkIncl = warpInclusiveScan(nChunks, lane);
 	if(lane == 31) sChunkTot[warp] = chunkIncl;
 
@@ -211,24 +220,17 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 	if(nChunks) {
 		uint32_t base = sChunkBase + (chunkIncl - nChunks);
 		for(int w = 0; w < warp; w++) base += sChunkTot[w];
-		const uint64_t psBase = FUSED ? psBaseResolved : primitiveSetBase<LEVEL>(A, d);
-		uint32_t ps[3][2] = {{0, 0}, {0, 0}, {0, 0}};
-#pragma unroll
-		for(int l = 0; l < 3; l++)
-			if(uint32_t(l) < L.lodCount) { ps[l][0] = ldg_u32(psBase + psOff[l]); ps[l][1] = ldg_u32(psBase + psOff[l] + 4); }
 		for(uint32_t c = 0; c < nChunks; c++) {
 			if(base + c >= A.chunkCapacity) { atomicOr(&A.hdr->status, CADR_CULL_STATUS_CHUNK_OVERFLOW); break; }
 			const uint32_t j0 = c * CHUNK;
 			const uint64_t mats = matrixList + CADR_MATRIX_LIST_HEADER_BYTES + 64ull * j0;
-			uint4* w = reinterpret_cast<uint4*>(A.items + (base + c));
-			w[0] = make_uint4(uint32_t(mats), uint32_t(mats >> 32), min(CHUNK, N - j0), j0);
-			w[1] = make_uint4(d, stateSet, L.lodCount, 0u);
-			w[2] = make_uint4(__float_as_uint(L.sphere.x), __float_as_uint(L.sphere.y), __float_as_uint(L.sphere.z), __float_as_uint(L.sphere.w));
-			w[3] = make_uint4(__float_as_uint(L.thr0), __float_as_uint(L.thr1), 0u, 0u);
-			w[4] = make_uint4(ps[0][0], ps[0][1], ps[1][0], ps[1][1]);
-			w[5] = make_uint4(ps[2][0], ps[2][1], 0u, 0u);
-			w[6] = p0;
-			w[7] = p1;
+			// the 128-byte descriptor as four 256-bit stores (full 32-byte sectors)
+			uint8_t* w = reinterpret_cast<uint8_t*>(A.items + (base + c));
+			st_u8(w,      make_uint4(uint32_t(mats), uint32_t(mats >> 32), min(CHUNK, N - j0), j0), make_uint4(d, stateSet, L.lodCount, 0u));
+			st_u8(w + 32, make_uint4(__float_as_uint(L.sphere.x), __float_as_uint(L.sphere.y), __float_as_uint(L.sphere.z), __float_as_uint(L.sphere.w)),
+			              make_uint4(__float_as_uint(L.thr0), __float_as_uint(L.thr1), 0u, 0u));
+			st_u8(w + 64, make_uint4(ps[0][0], ps[0][1], ps[1][0], ps[1][1]), make_uint4(ps[2][0], ps[2][1], 0u, 0u));
+			st_u8(w + 96, p0, p1);
 		}
 	}
 
@@ -380,7 +382,11 @@ __device__ __forceinline__ void emitItem(const CullArgs& A, unsigned long long h
 
 constexpr int LW_DESCS = 4;     // descriptor ring per warp: items A, B, C and the slot being refilled
 
-__global__ void __launch_bounds__(CM_THREADS, 4)
+// EARLY2 (CADR_B200_CULL_VARIANT=4 / 5): the SECOND step of item B is requested as well before A's results are emitted
+// (right after A's last evaluation, when `nxt` has just been handed over to `cur`), so that a 33..64-matrix item is
+// completely in flight while the warp waits for A's output reservation; costs 16 more live registers across emitItem.
+template<bool EARLY2, int CTAS_PER_SM>
+__global__ void __launch_bounds__(CM_THREADS, CTAS_PER_SM)
 cullListWarpKernel(const __grid_constant__ CullArgs A)
 {
 	__shared__ __align__(16) uint8_t sDescs[CM_THREADS / 32][LW_DESCS * sizeof(WorkItem)];
@@ -407,6 +413,7 @@ cullListWarpKernel(const __grid_constant__ CullArgs A)
 	uint32_t seq = 0;                  // warp-local sequence number of A; its descriptor slot is seq & 3
 	uint4 dIn;
 	Mat cur, nxt;
+	bool preloaded = false;
 	{
 		const uint4 a = loadItemWord(A, iA, total, lane);
 		dIn = loadItemWord(A, iB, total, lane);       // stored to the ring at the top of the first iteration
@@ -437,8 +444,10 @@ cullListWarpKernel(const __grid_constant__ CullArgs A)
 		unsigned long long hist = 0;       // 2 bits per step, newest at the top
 		uint32_t nb = 0, steps = 1, left = a0.z;
 		const uint8_t* p = reinterpret_cast<const uint8_t*>(uint64_t(a0.x) | (uint64_t(a0.y) << 32)) + 64u * lane;
+		bool pre = EARLY2 && preloaded;    // warp-uniform: A's second step was requested before the previous item's emission
 		while(left > 32u) {                // full steps that have a successor inside A
-			if(lane + 32u < left) nxt = loadMat(p + 2048);
+			if(!pre) { if(lane + 32u < left) nxt = loadMat(p + 2048); }
+			pre = false;
 			bool nbi = false;
 			const int lod = A.diagNoEval ? ((cur.c0.x == 12345.f && cur.c2.x == 1.f) ? 0 : -1) : evalInstance(cur, L, A.plane, A.eye, nbi);
 			nb += nbi ? 1u : 0u;
@@ -459,6 +468,10 @@ cullListWarpKernel(const __grid_constant__ CullArgs A)
 			cur = nxt;
 		}
 		hist >>= (64u - 2u * steps);       // step s now sits at bits [2s, 2s + 1]
+		if constexpr(EARLY2) {
+			preloaded = b0.z > 32u;
+			if(lane + 32u < b0.z) nxt = loadMat(reinterpret_cast<const uint8_t*>(uint64_t(b0.x) | (uint64_t(b0.y) << 32)) + 64u * lane + 2048);
+		}
 
 		emitItem(A, hist, steps, nb, dA, a0, a1, lane);
 		__syncwarp();       // A's descriptor slot is rewritten three iterations from now; keep the warp together
@@ -735,10 +748,12 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 			if(int r = launchCullVariant(ctx, A, variant, p.chunkCapacity, s)) return r;
 		}
 		else {
-			uint32_t gridL = uint32_t(ctx->smCount) * 4u;   // persistent warps: four CTAs of eight warps per SM
+			uint32_t gridL = uint32_t(ctx->smCount) * (variant == 5 ? 3u : 4u);   // persistent warps: four (three) CTAs of eight warps per SM
 			const uint32_t need = (p.chunkCapacity + CM_THREADS / 32 - 1) / (CM_THREADS / 32);
 			if(gridL > need) gridL = need;
-			cullListWarpKernel<<<gridL, CM_THREADS, 0, s>>>(A);
+			if(variant == 4)      cullListWarpKernel<true, 4><<<gridL, CM_THREADS, 0, s>>>(A);
+			else if(variant == 5) cullListWarpKernel<true, 3><<<gridL, CM_THREADS, 0, s>>>(A);
+			else                  cullListWarpKernel<false, 4><<<gridL, CM_THREADS, 0, s>>>(A);
 		}
 		ctx->timeEnd(KS_CULL_LARGE, s);
 		ctx->launches++;

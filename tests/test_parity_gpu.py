@@ -117,7 +117,8 @@ BOUNDARY_COUNTS = [0, 1, 2, 31, 32, 33, 34, 63, 64, 65, 95, 96, 97, 127, 128, 12
                    1023, 1024, 1025, 2047, 2048, 2049, 3072]
 
 
-@pytest.mark.parametrize("variant", ["2", "3", "1", "0"], ids=["warp-per-item", "warp-ring", "tma-pipeline", "cta-per-item"])
+@pytest.mark.parametrize("variant", ["2", "4", "5", "3", "1", "0"],
+                         ids=["warp-per-item", "warp-per-item-early2", "warp-per-item-early2-3cta", "warp-ring", "tma-pipeline", "cta-per-item"])
 @pytest.mark.parametrize("fused", [False, True], ids=["two-calls", "fused"])
 def test_tier_x_list_length_boundaries(ctx, monkeypatch, variant, fused):
     """Every hand-over point between the kernels: thread-per-list (<= 32 matrices), warp-per-list (33..512), work
