@@ -47,6 +47,7 @@ struct CullArgs {
 	const float4* bounds;                 // optional cadr_drawable_bound[n] = 2 x float4 each (pre-test of long lists), or nullptr
 	uint32_t  n;
 	uint32_t  numStateSets;
+	uint32_t  medMax;                     // lists of SMALL_MAX < n <= medMax matrices go to the medium queue (0: there is none)
 	uint32_t  diagNoEval;                 // CADR_B200_DIAG_NOEVAL=1: list kernels skip the evaluation (memory-system ceiling of the access structure)
 	float4 plane[6];
 	float4 eye;

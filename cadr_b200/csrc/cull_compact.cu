@@ -37,6 +37,18 @@ namespace cadr {
 // ---------------------------------------------------------------------------------------------------
 // small lists + work-item queueing: one thread per drawable
 // ---------------------------------------------------------------------------------------------------
+// the 128-byte descriptor of a work item as four 256-bit stores (full 32-byte sectors)
+__device__ __forceinline__ void writeWorkItem(WorkItem* item, uint64_t mats, uint32_t count, uint32_t firstInstance, uint32_t d,
+                                              uint32_t stateSet, const LodInfo& L, const uint32_t (&ps)[3][2], uint4 p0, uint4 p1)
+{
+	uint8_t* w = reinterpret_cast<uint8_t*>(item);
+	st_u8(w,      make_uint4(uint32_t(mats), uint32_t(mats >> 32), count, firstInstance), make_uint4(d, stateSet, L.lodCount, 0u));
+	st_u8(w + 32, make_uint4(__float_as_uint(L.sphere.x), __float_as_uint(L.sphere.y), __float_as_uint(L.sphere.z), __float_as_uint(L.sphere.w)),
+	              make_uint4(__float_as_uint(L.thr0), __float_as_uint(L.thr1), 0u, 0u));
+	st_u8(w + 64, make_uint4(ps[0][0], ps[0][1], ps[1][0], ps[1][1]), make_uint4(ps[2][0], ps[2][1], 0u, 0u));
+	st_u8(w + 96, p0, p1);
+}
+
 // FUSED = true additionally does the work of processDrawablesKernel for the same drawable (handle resolve + Tier R
 // records), so the drawable list is read once per frame and the indirect / pointers records are not re-read.
 template<int LEVEL, bool FUSED>
@@ -46,6 +58,8 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 	__shared__ uint32_t sChunkTot[CS_THREADS / 32];
 	__shared__ uint32_t sGroupTot[CS_THREADS / 32];
 	__shared__ uint32_t sChunkBase;
+	__shared__ uint32_t sMedTot[CS_THREADS / 32];
+	__shared__ uint32_t sMedBase;
 	__shared__ uint32_t sDomSet;
 	__shared__ unsigned long long sDomBase;
 
@@ -127,16 +141,20 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 	}
 
 	// ---- number of work items this drawable needs in the large-list queue --------------------------
-	uint32_t nChunks = (N > SMALL_MAX) ? (N + CHUNK - 1) / CHUNK : 0;
+	// medium lists (one item each) go to their own queue, consumed 32 at a time by cullMediumBatches
+	const bool isMed = N > SMALL_MAX && N <= A.medMax;
+	uint32_t nChunks = (N > SMALL_MAX && !isMed) ? (N + CHUNK - 1) / CHUNK : 0;
 	// PrimitiveSets of a queued list: requested here, ahead of the scans and CTA barriers below, so that their latency
 	// (a DRAM round trip when every drawable has its own geometry) is not paid after the queue reservation
 	uint32_t ps[3][2] = {{0, 0}, {0, 0}, {0, 0}};
-	if(nChunks) {
+	if(nChunks || isMed) {
 		const uint64_t psBase = FUSED ? psBaseResolved : primitiveSetBase<LEVEL>(A, d);
 #pragma unroll
 		for(int l = 0; l < 3; l++)
 			if(uint32_t(l) < L.lodCount) { const uint2 v = ldg_u2(psBase + psOff[l]); ps[l][0] = v.x; ps[l][1] = v.y; }
 	}
+	const unsigned medBallot = __ballot_sync(0xffffffffu, isMed);
+	if(lane == 0) sMedTot[warp] = __popc(medBallot);
 	uint32_t chunkIncl = warpInclusiveScan(nChunks, lane);
 	if(lane == 31) sChunkTot[warp] = chunkIncl;
 
@@ -174,6 +192,10 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 #pragma unroll
 		for(int w = 0; w < CS_THREADS / 32; w++) tot += sChunkTot[w];
 		sChunkBase = tot ? atomicAdd(&A.hdr->chunkCount, tot) : 0u;
+		uint32_t totM = 0;
+#pragma unroll
+		for(int w = 0; w < CS_THREADS / 32; w++) totM += sMedTot[w];
+		sMedBase = totM ? atomicAdd(&A.hdr->medCount, totM) : 0u;
 	}
 
 	// dominant group: block-aggregated reservation of the output ranges
@@ -223,15 +245,15 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 		for(uint32_t c = 0; c < nChunks; c++) {
 			if(base + c >= A.chunkCapacity) { atomicOr(&A.hdr->status, CADR_CULL_STATUS_CHUNK_OVERFLOW); break; }
 			const uint32_t j0 = c * CHUNK;
-			const uint64_t mats = matrixList + CADR_MATRIX_LIST_HEADER_BYTES + 64ull * j0;
-			// the 128-byte descriptor as four 256-bit stores (full 32-byte sectors)
-			uint8_t* w = reinterpret_cast<uint8_t*>(A.items + (base + c));
-			st_u8(w,      make_uint4(uint32_t(mats), uint32_t(mats >> 32), min(CHUNK, N - j0), j0), make_uint4(d, stateSet, L.lodCount, 0u));
-			st_u8(w + 32, make_uint4(__float_as_uint(L.sphere.x), __float_as_uint(L.sphere.y), __float_as_uint(L.sphere.z), __float_as_uint(L.sphere.w)),
-			              make_uint4(__float_as_uint(L.thr0), __float_as_uint(L.thr1), 0u, 0u));
-			st_u8(w + 64, make_uint4(ps[0][0], ps[0][1], ps[1][0], ps[1][1]), make_uint4(ps[2][0], ps[2][1], 0u, 0u));
-			st_u8(w + 96, p0, p1);
+			writeWorkItem(A.items + (base + c), matrixList + CADR_MATRIX_LIST_HEADER_BYTES + 64ull * j0, min(CHUNK, N - j0), j0, d, stateSet, L, ps, p0, p1);
 		}
+	}
+	if(isMed) {
+		// the medium queue grows downwards from the end of the same workspace (see cullListWarpKernel)
+		uint32_t m = sMedBase + __popc(medBallot & ((1u << lane) - 1u));
+		for(int w = 0; w < warp; w++) m += sMedTot[w];
+		if(m >= A.chunkCapacity) atomicOr(&A.hdr->status, CADR_CULL_STATUS_CHUNK_OVERFLOW);
+		else writeWorkItem(A.items + (A.chunkCapacity - 1u - m), matrixList + CADR_MATRIX_LIST_HEADER_BYTES, N, 0u, d, stateSet, L, ps, p0, p1);
 	}
 
 	if(inDom) {
@@ -380,22 +402,218 @@ __device__ __forceinline__ void emitItem(const CullArgs& A, unsigned long long h
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------
+// medium lists (33 .. CADR_CULL_MEDIUM_LIST_MAX matrices): 32 items per warp, evaluated as ONE flat run of instances
+// ---------------------------------------------------------------------------------------------------
+// One warp per item spends ~270 instructions per item on its descriptor pipeline, its output reservation and its
+// emission, and a 33-matrix list still costs two full evaluation steps: on short items the warp-per-item loop above is
+// bound by instruction issue, not by memory (33-matrix lists: 47 G instances/s, DRAM at ~45 %).  Medium items therefore
+// get their own queue (the same workspace, filled from its upper end) and are consumed 32 at a time:
+//   * the warp copies the 32 descriptors of a batch into shared memory (4 KiB, coalesced), a warp scan of the counts
+//     gives every item its first flat index;
+//   * the instances of all 32 items are evaluated as one run, 32 per step, next step prefetched in registers: lane l of
+//     the step starting at flat index f0 handles instance f0 + l, which belongs to the item containing f0 or to the one
+//     after it (items are longer than a step, so a step touches at most two): no ragged steps except the batch's last;
+//   * per step three votes (one per LOD); the lane whose index equals an item's position in the batch ORs that item's
+//     part of the votes into its 64-bit masks, so after the run lane i holds the complete result of item i - exactly
+//     what cullSmallKernel's one-thread-per-list path produces;
+//   * one output reservation per (warp, StateSet) instead of one per item, then every lane emits its own item.
+constexpr uint32_t FL_STRIDE     = 144;                 // descriptor stride in shared memory: 128 + 16, so that lanes reading
+                                                        // their own descriptor (emission) do not all hit the same banks
+constexpr uint32_t FL_WARP_BYTES = 32 * FL_STRIDE;      // 4.5 KiB per warp, 36 KiB per CTA
+static_assert(CADR_CULL_MEDIUM_LIST_MAX <= 64 && CADR_CULL_MEDIUM_LIST_MAX > CADR_CULL_SMALL_LIST_MAX, "one 64-bit mask per LOD; a step spans at most two items");
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ uint2 ldsU2(uint32_t addr)
+{
+	uint2 v;
+	asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+	return v;
+}
+
+// position of the run: the item that contains the first instance of a step, and that item's flat index range
+struct FlatPos { uint32_t item, start, end; };
+
+__device__ __forceinline__ void flatAdvance(FlatPos& P, uint32_t f0, uint32_t descs)
+{
+	// the step starting at f0: at most one item boundary was passed since the previous step (items are longer than 32)
+	if(f0 >= P.end && P.item < 31u) {
+		P.item++;
+		P.start = P.end;
+		P.end += lds32(descs + P.item * FL_STRIDE + 8u);     // WorkItem::count
+	}
+}
+
+__device__ __forceinline__ void cullMediumBatches(const CullArgs& A, const uint32_t descs, const uint32_t lane, const uint32_t totalM)
+{
+	const unsigned FULL = 0xffffffffu;
+	const uint32_t cap = A.chunkCapacity;
+	uint32_t base = 0;
+	if(lane == 0) base = atomicAdd(&A.hdr->medCursor, 32u);
+	base = __shfl_sync(FULL, base, 0);
+	while(base < totalM) {
+		uint32_t nextBase = 0;
+		if(lane == 0) nextBase = atomicAdd(&A.hdr->medCursor, 32u);      // looked at when this batch is done
+		const uint32_t nItems = min(32u, totalM - base);
+		{
+			// medium item m lives in slot cap - 1 - m: the batch is one contiguous 4-KiB piece of the workspace
+			uint4 v[8];
+#pragma unroll
+			for(uint32_t k = 0; k < 8; k++) {
+				const uint32_t it = k * 4u + (lane >> 3);
+				v[k] = make_uint4(0u, 0u, 0u, 0u);       // count 0: no item
+				if(it < nItems) v[k] = ldg_stream_u4(reinterpret_cast<const uint4*>(A.items + (cap - 1u - (base + it))) + (lane & 7u));
+			}
+#pragma unroll
+			for(uint32_t k = 0; k < 8; k++)
+				stsU4(descs + (k * 4u + (lane >> 3)) * FL_STRIDE + (lane & 7u) * 16u, v[k]);
+		}
+		__syncwarp();
+		const uint32_t myDesc = descs + lane * FL_STRIDE;
+		const uint32_t total = __reduce_add_sync(FULL, lds32(myDesc + 8u));     // instances of the batch
+
+		unsigned long long m0 = 0, m1 = 0, m2 = 0;       // lane i: survivors of item i per LOD, bit j = matrix j
+		uint32_t nb = 0;
+		Mat cur, nxt;
+		FlatPos PL, PE;                                  // position of the step being loaded / being evaluated
+		PL.item = 0; PL.start = 0; PL.end = lds32(descs + 8u);
+		PE = PL;
+		{
+			const uint32_t f = lane;
+			if(f < total) {
+				const bool second = f >= PL.end;
+				const uint2 a = ldsU2(descs + (PL.item + (second ? 1u : 0u)) * FL_STRIDE);
+				cur = loadMat(reinterpret_cast<const uint8_t*>(uint64_t(a.x) | (uint64_t(a.y) << 32)) + 64ull * (f - (second ? PL.end : PL.start)));
+			}
+		}
+		for(uint32_t f0 = 0; f0 < total; f0 += 32u) {
+			// ---- next step in flight ------------------------------------------------------------------------
+			flatAdvance(PL, f0 + 32u, descs);
+			{
+				const uint32_t f = f0 + 32u + lane;
+				if(f < total) {
+					const bool second = f >= PL.end;
+					const uint2 a = ldsU2(descs + (PL.item + (second ? 1u : 0u)) * FL_STRIDE);
+					nxt = loadMat(reinterpret_cast<const uint8_t*>(uint64_t(a.x) | (uint64_t(a.y) << 32)) + 64ull * (f - (second ? PL.end : PL.start)));
+				}
+			}
+			// ---- evaluate this step -------------------------------------------------------------------------
+			uint32_t code = 0;
+			if(f0 + lane < total) {
+				const uint32_t dsc = descs + (PE.item + ((f0 + lane >= PE.end) ? 1u : 0u)) * FL_STRIDE;
+				const uint4 a1 = ldsU4(dsc + 16u), a2 = ldsU4(dsc + 32u);
+				const uint2 a3 = ldsU2(dsc + 48u);
+				LodInfo L;
+				L.lodCount = a1.z;
+				L.sphere = make_float4(__uint_as_float(a2.x), __uint_as_float(a2.y), __uint_as_float(a2.z), __uint_as_float(a2.w));
+				L.thr0 = __uint_as_float(a3.x); L.thr1 = __uint_as_float(a3.y);
+				bool nbi = false;
+				const int lod = A.diagNoEval ? ((cur.c0.x == 12345.f && cur.c2.x == 1.f) ? 0 : -1) : evalInstance(cur, L, A.plane, A.eye, nbi);
+				nb += nbi ? 1u : 0u;
+				code = uint32_t(lod + 1);
+			}
+			const unsigned b0 = __ballot_sync(FULL, code == 1u), b1 = __ballot_sync(FULL, code == 2u), b2 = __ballot_sync(FULL, code == 3u);
+			// lanes [0, cut) of the step belong to item PE.item (from its matrix f0 - PE.start on), lanes [cut, 32) are the
+			// first matrices of the next item
+			const uint32_t cut = min(32u, PE.end - f0);
+			if(lane == PE.item) {
+				const uint32_t keep = (cut >= 32u) ? FULL : ((1u << cut) - 1u), sh = f0 - PE.start;
+				m0 |= (unsigned long long)(b0 & keep) << sh; m1 |= (unsigned long long)(b1 & keep) << sh; m2 |= (unsigned long long)(b2 & keep) << sh;
+			}
+			else if(lane == PE.item + 1u && cut < 32u) {
+				m0 |= (unsigned long long)(b0 >> cut); m1 |= (unsigned long long)(b1 >> cut); m2 |= (unsigned long long)(b2 >> cut);
+			}
+			flatAdvance(PE, f0 + 32u, descs);
+			cur = nxt;
+		}
+
+		// ---- lane i now owns item i: reserve per (warp, StateSet), emit -------------------------------------------
+		if(__any_sync(FULL, nb != 0u)) {
+			nb = __reduce_add_sync(FULL, nb);
+			if(lane == 0) atomicAdd(&A.hdr->nearBandCount, nb);
+		}
+		const uint32_t k0 = uint32_t(__popcll(m0)), k1 = uint32_t(__popcll(m1)), k2 = uint32_t(__popcll(m2));
+		const uint32_t nInst = k0 + k1 + k2, nCmd = (k0 ? 1u : 0u) + (k1 ? 1u : 0u) + (k2 ? 1u : 0u);
+		const bool has = nInst > 0;
+		const uint32_t packed = nCmd | (nInst << 12);    // warp totals: commands <= 96 < 2^12, instances <= 2048 < 2^20
+		const uint32_t stateSet = lds32(myDesc + 20u);   // WorkItem::stateSet
+		uint32_t cmdOff = 0, instOff = 0;
+		unsigned pend = __ballot_sync(FULL, has);
+		while(pend) {
+			const int leader = __ffs(pend) - 1;
+			const uint32_t sl = __shfl_sync(FULL, stateSet, leader);
+			const bool inGrp = has && stateSet == sl;
+			const unsigned grp = __ballot_sync(FULL, inGrp);
+			const uint32_t incl = warpInclusiveScan(inGrp ? packed : 0u, int(lane));
+			const uint32_t tot = __shfl_sync(FULL, incl, 31);
+			unsigned long long rb = 0;
+			if(int(lane) == leader)
+				rb = atomicAdd(A.counts + sl, (unsigned long long)(tot & 0xfffu) | ((unsigned long long)(tot >> 12) << 32));
+			rb = __shfl_sync(FULL, rb, leader);
+			if(inGrp) {
+				const uint32_t excl = incl - packed;
+				cmdOff = uint32_t(rb) + (excl & 0xfffu);
+				instOff = uint32_t(rb >> 32) + (excl >> 12);
+			}
+			pend &= ~grp;
+		}
+		if(has) {
+			const uint4 reg = ldg_u4(reinterpret_cast<uint64_t>(A.regions + stateSet));   // cmdBase, cmdCap, instBase, instCap
+			if(cmdOff + nCmd > reg.y || instOff + nInst > reg.w) {
+				atomicOr(&A.hdr->status, CADR_CULL_STATUS_REGION_OVERFLOW);
+			}
+			else {
+				const uint4 w0 = ldsU4(myDesc), w1 = ldsU4(myDesc + 16u), w4 = ldsU4(myDesc + 64u), w5 = ldsU4(myDesc + 80u);
+				const uint4 p0 = ldsU4(myDesc + 96u), p1 = ldsU4(myDesc + 112u);
+				uint32_t ci = reg.x + cmdOff, ii = reg.z + instOff;
+#pragma unroll
+				for(int l = 0; l < 3; l++) {
+					unsigned long long mk = (l == 0) ? m0 : (l == 1) ? m1 : m2;
+					if(mk == 0) continue;
+					const uint32_t psCount = (l == 0) ? w4.x : (l == 1) ? w4.z : w5.x, psFirst = (l == 0) ? w4.y : (l == 1) ? w4.w : w5.y;
+					writeCommandRecord(A, ci, psCount, uint32_t(__popcll(mk)), psFirst, ii, w1.x, uint32_t(l), p0, p1);
+					ci++;
+					while(mk) {
+						const int j = __ffsll((long long)mk) - 1;
+						A.instOut[ii++] = w0.w + uint32_t(j);     // WorkItem::firstInstance (0 for a whole list) + j
+						mk &= mk - 1;
+					}
+				}
+			}
+		}
+		__syncwarp();       // the descriptors are overwritten by the next batch
+		base = __shfl_sync(FULL, nextBase, 0);
+	}
+}
+
 constexpr int LW_DESCS = 4;     // descriptor ring per warp: items A, B, C and the slot being refilled
 
-// EARLY2 (CADR_B200_CULL_VARIANT=4 / 5): the SECOND step of item B is requested as well before A's results are emitted
-// (right after A's last evaluation, when `nxt` has just been handed over to `cur`), so that a 33..64-matrix item is
-// completely in flight while the warp waits for A's output reservation; costs 16 more live registers across emitItem.
-template<bool EARLY2, int CTAS_PER_SM>
-__global__ void __launch_bounds__(CM_THREADS, CTAS_PER_SM)
+// FLAT: after the queue of long items has run dry, the warp goes on with the medium items (cullMediumBatches above).
+template<bool FLAT>
+__global__ void __launch_bounds__(CM_THREADS, 4)
 cullListWarpKernel(const __grid_constant__ CullArgs A)
 {
-	__shared__ __align__(16) uint8_t sDescs[CM_THREADS / 32][LW_DESCS * sizeof(WorkItem)];
+	// per warp: the descriptor ring of the long items (LW_DESCS x 128 B) and, afterwards, the 32 descriptors of a batch of
+	// medium items (FL_WARP_BYTES) share the same bytes
+	__shared__ __align__(16) uint8_t sDescs[CM_THREADS / 32][FLAT ? FL_WARP_BYTES : LW_DESCS * sizeof(WorkItem)];
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t descs = smemAddr(sDescs[threadIdx.x >> 5]);
 	const unsigned FULL = 0xffffffffu;
 
-	uint32_t total = A.hdr->chunkCount;
-	if(total > A.chunkCapacity) total = A.chunkCapacity;
+	// The workspace is filled from both ends: long items in slots 0, 1, ..., medium items in slots capacity - 1,
+	// capacity - 2, ...  Slot i is a valid long item iff i < longCount and i + mediumCount < capacity (and the mirror
+	// image for medium items): both counters only grow while the producer runs, so a valid slot was always written
+	// and never written by the other side; when the two ends overlap, the overlapping items are dropped and reported.
+	const uint32_t queuedL = A.hdr->chunkCount, queuedM = FLAT ? A.hdr->medCount : 0u;
+	uint32_t total = min(queuedL, A.chunkCapacity - min(queuedM, A.chunkCapacity));
+	const uint32_t totalM = min(queuedM, A.chunkCapacity - min(queuedL, A.chunkCapacity));
+	if(FLAT && blockIdx.x == 0 && threadIdx.x == 0 && uint64_t(queuedL) + queuedM > A.chunkCapacity)
+		atomicOr(&A.hdr->status, CADR_CULL_STATUS_CHUNK_OVERFLOW);
 	const uint32_t numWarps = gridDim.x * (CM_THREADS / 32);
 	uint32_t batch = total / (numWarps * 16u);          // long queues: fewer atomics; short queues: best balance
 	batch = batch < 1u ? 1u : (batch > 8u ? 8u : batch);
@@ -413,7 +631,6 @@ cullListWarpKernel(const __grid_constant__ CullArgs A)
 	uint32_t seq = 0;                  // warp-local sequence number of A; its descriptor slot is seq & 3
 	uint4 dIn;
 	Mat cur, nxt;
-	bool preloaded = false;
 	{
 		const uint4 a = loadItemWord(A, iA, total, lane);
 		dIn = loadItemWord(A, iB, total, lane);       // stored to the ring at the top of the first iteration
@@ -444,10 +661,8 @@ cullListWarpKernel(const __grid_constant__ CullArgs A)
 		unsigned long long hist = 0;       // 2 bits per step, newest at the top
 		uint32_t nb = 0, steps = 1, left = a0.z;
 		const uint8_t* p = reinterpret_cast<const uint8_t*>(uint64_t(a0.x) | (uint64_t(a0.y) << 32)) + 64u * lane;
-		bool pre = EARLY2 && preloaded;    // warp-uniform: A's second step was requested before the previous item's emission
 		while(left > 32u) {                // full steps that have a successor inside A
-			if(!pre) { if(lane + 32u < left) nxt = loadMat(p + 2048); }
-			pre = false;
+			if(lane + 32u < left) nxt = loadMat(p + 2048);
 			bool nbi = false;
 			const int lod = A.diagNoEval ? ((cur.c0.x == 12345.f && cur.c2.x == 1.f) ? 0 : -1) : evalInstance(cur, L, A.plane, A.eye, nbi);
 			nb += nbi ? 1u : 0u;
@@ -468,10 +683,6 @@ cullListWarpKernel(const __grid_constant__ CullArgs A)
 			cur = nxt;
 		}
 		hist >>= (64u - 2u * steps);       // step s now sits at bits [2s, 2s + 1]
-		if constexpr(EARLY2) {
-			preloaded = b0.z > 32u;
-			if(lane + 32u < b0.z) nxt = loadMat(reinterpret_cast<const uint8_t*>(uint64_t(b0.x) | (uint64_t(b0.y) << 32)) + 64u * lane + 2048);
-		}
 
 		emitItem(A, hist, steps, nb, dA, a0, a1, lane);
 		__syncwarp();       // A's descriptor slot is rewritten three iterations from now; keep the warp together
@@ -479,6 +690,10 @@ cullListWarpKernel(const __grid_constant__ CullArgs A)
 		// ---- advance the pipeline: B becomes A ---------------------------------------------------------------
 		seq++;
 		iA = iB; iB = iC; iC = __shfl_sync(FULL, iD, 0);
+	}
+	if constexpr(FLAT) {
+		__syncwarp();
+		if(totalM) cullMediumBatches(A, descs, lane, totalM);
 	}
 }
 
@@ -645,8 +860,9 @@ cullListRingKernel(const __grid_constant__ CullArgs A)
 static int cullVariant()
 {
 	const char* v = std::getenv("CADR_B200_CULL_VARIANT");
-	return v ? std::atoi(v) : 2;   // 2 = warp per item, register prefetch (default); 3 = warp per item, shared-memory ring;
-	                               // 1 = CTA-wide TMA pipeline; 0 = first direct-load version
+	return v ? std::atoi(v) : 2;   // 2 = warp per item, register prefetch + flat medium batches (default); 4 = the same without
+	                               // the medium queue; 3 = warp per item, shared-memory ring; 1 = CTA-wide TMA pipeline;
+	                               // 0 = first direct-load version
 }
 
 int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, bool fused)
@@ -711,6 +927,11 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 		A.xTag[r] = reinterpret_cast<uint2*>(exchange && r < p.exchangeWorld ? p.exchangeTag[r] : 0);
 	}
 
+	// medium lists get their own queue only with the default list kernel (2); 4 = the same kernel with every list longer
+	// than 32 matrices in the one queue (the state before the flat medium path existed), for A/B measurements
+	const int variant = cullVariant();
+	A.medMax = (variant == 2 && p.chunkCapacity) ? CADR_CULL_MEDIUM_LIST_MAX : 0u;
+
 	uint32_t gridS = (p.numDrawables + CS_THREADS - 1) / CS_THREADS;
 	ctx->timeBegin(KS_CULL_SMALL, s);
 	if(fused) {
@@ -732,7 +953,6 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 	CADR_CUDA(cudaGetLastError());
 
 	if(p.chunkCapacity) {
-		const int variant = cullVariant();
 		ctx->timeBegin(KS_CULL_LARGE, s);
 		if(variant == 3) {
 			if(!ctx->ringKernelConfigured) {   // per device (a process may hold one context per GPU)
@@ -748,12 +968,11 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 			if(int r = launchCullVariant(ctx, A, variant, p.chunkCapacity, s)) return r;
 		}
 		else {
-			uint32_t gridL = uint32_t(ctx->smCount) * (variant == 5 ? 3u : 4u);   // persistent warps: four (three) CTAs of eight warps per SM
+			uint32_t gridL = uint32_t(ctx->smCount) * 4u;   // persistent warps: four CTAs of eight warps per SM
 			const uint32_t need = (p.chunkCapacity + CM_THREADS / 32 - 1) / (CM_THREADS / 32);
 			if(gridL > need) gridL = need;
-			if(variant == 4)      cullListWarpKernel<true, 4><<<gridL, CM_THREADS, 0, s>>>(A);
-			else if(variant == 5) cullListWarpKernel<true, 3><<<gridL, CM_THREADS, 0, s>>>(A);
-			else                  cullListWarpKernel<false, 4><<<gridL, CM_THREADS, 0, s>>>(A);
+			if(A.medMax) cullListWarpKernel<true><<<gridL, CM_THREADS, 0, s>>>(A);
+			else         cullListWarpKernel<false><<<gridL, CM_THREADS, 0, s>>>(A);
 		}
 		ctx->timeEnd(KS_CULL_LARGE, s);
 		ctx->launches++;

@@ -159,7 +159,8 @@ class DeviceScene:
         raw = self._read(self.counters, self.counters_bytes, np.uint8)
         hdr = raw[:64].view(np.uint32)
         packed = raw[64:].view(np.uint64)
-        return dict(status=int(hdr[0]), near_band=int(hdr[1]), chunk_count=int(hdr[2]),
+        # work items queued: long items (hdr[2]) + medium lists (hdr[4], the other end of the same workspace)
+        return dict(status=int(hdr[0]), near_band=int(hdr[1]), chunk_count=int(hdr[2]) + int(hdr[4]), medium_count=int(hdr[4]),
                     cmd_count=(packed & np.uint64(0xFFFFFFFF)).astype(np.int64), inst_count=(packed >> np.uint64(32)).astype(np.int64))
 
     def read_tier_x(self) -> dict:

@@ -130,7 +130,9 @@ typedef struct cadr_cull_header {
 	uint32_t nearBandCount;   /* instances whose deciding plane test, or LOD threshold, is within 1e-5 */
 	uint32_t chunkCount;      /* internal: work items queued for the list kernel                     */
 	uint32_t chunkCursor;     /* internal: work items claimed                                        */
-	uint32_t reserved[12];
+	uint32_t medCount;        /* internal: medium lists queued (same workspace, filled from its end)  */
+	uint32_t medCursor;       /* internal: medium lists claimed                                      */
+	uint32_t reserved[10];
 } cadr_cull_header;           /* 64 B */
 #define CADR_CULL_STATUS_REGION_OVERFLOW 1u
 #define CADR_CULL_STATUS_CHUNK_OVERFLOW  2u
@@ -138,6 +140,7 @@ typedef struct cadr_cull_header {
 #define CADR_CULL_WORK_ITEM_BYTES        128u   /* one self-contained descriptor per <= 1024 matrices */
 #define CADR_CULL_SMALL_LIST_MAX         32u    /* lists up to this size are evaluated by one thread; longer ones become work items */
 #define CADR_CULL_WORK_ITEM_INSTANCES    1024u
+#define CADR_CULL_MEDIUM_LIST_MAX        64u    /* lists of 33..64 matrices are one work item each, consumed 32 at a time */
 #define CADR_CULL_BOUNDS_MIN_LIST         4u     /* the optional bounds pre-test applies to lists of at least this many matrices */
 
 #define CADR_MAX_PEERS 8

@@ -117,8 +117,8 @@ BOUNDARY_COUNTS = [0, 1, 2, 31, 32, 33, 34, 63, 64, 65, 95, 96, 97, 127, 128, 12
                    1023, 1024, 1025, 2047, 2048, 2049, 3072]
 
 
-@pytest.mark.parametrize("variant", ["2", "4", "5", "3", "1", "0"],
-                         ids=["warp-per-item", "warp-per-item-early2", "warp-per-item-early2-3cta", "warp-ring", "tma-pipeline", "cta-per-item"])
+@pytest.mark.parametrize("variant", ["2", "4", "3", "1", "0"],
+                         ids=["warp-per-item+flat-medium", "warp-per-item-one-queue", "warp-ring", "tma-pipeline", "cta-per-item"])
 @pytest.mark.parametrize("fused", [False, True], ids=["two-calls", "fused"])
 def test_tier_x_list_length_boundaries(ctx, monkeypatch, variant, fused):
     """Every hand-over point between the kernels: thread-per-list (<= 32 matrices), warp-per-list (33..512), work
@@ -141,6 +141,50 @@ def test_tier_x_list_length_boundaries(ctx, monkeypatch, variant, fused):
             _, _, ref = oracle_tier_x(sc, planes, eye, arena_base=ds.arena, list_base=ds.drawable_list)
             assert_tier_x_equal(got, ref)
             assert 0 < got["inst_count"].sum() < sc.total_instances
+    finally:
+        ds.close()
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["two-calls", "fused"])
+@pytest.mark.parametrize("shape", ["all-medium", "mixed", "one-partial-batch", "exactly-32"])
+def test_tier_x_medium_lists_in_flat_batches(ctx, shape, fused):
+    """Lists of 33..64 matrices are consumed 32 items per warp as one flat run of instances (cullMediumBatches): several
+    batches with a ragged last one, items of every length in the range, batches that mix StateSets, medium items queued
+    next to long items (the two ends of one workspace) and short lists, under a culling camera, with everything
+    visible (all 64 bits of the masks set) and with nothing visible."""
+    rng = np.random.default_rng(97)
+    if shape == "all-medium":
+        counts, n = rng.integers(33, 65, 333).tolist(), 333
+    elif shape == "mixed":
+        counts = rng.integers(33, 65, 150).tolist() + [1, 0, 5, 32, 65, 100, 1024, 1500, 2100] * 6
+        rng.shuffle(counts)
+        n = len(counts) + 40                     # some lists are shared by two drawables
+    elif shape == "one-partial-batch":
+        counts, n = [64, 33, 50, 34, 63], 5
+    else:
+        counts, n = [33 + (k % 32) for k in range(32)], 32
+    sc = synth.random_scene(52, n=n, list_counts=counts, state_sets=min(6, n), first_handle=2000)
+    big = 1e9
+    all_in = np.array([[1, 0, 0, big], [-1, 0, 0, big], [0, 1, 0, big], [0, -1, 0, big], [0, 0, 1, big], [0, 0, -1, big]], np.float32)
+    none_in = all_in.copy(); none_in[0, 3] = -big
+    cams = [synth.orbit_camera(10, 250.0, far=500.0), synth.orbit_camera(200, 250.0, far=500.0),
+            (all_in, np.zeros(3, np.float32)), (none_in, np.zeros(3, np.float32))]
+    ds = DeviceScene(ctx, sc)
+    try:
+        for planes, eye in cams:
+            if fused:
+                ds.upload_drawable_list()
+                ds.process_and_cull(planes, eye)
+            else:
+                ds.record_drawable_processing()
+                ds.cull(planes, eye)
+            ctx.sync(ds.stream)
+            got = ds.read_tier_x()
+            _, _, ref = oracle_tier_x(sc, planes, eye, arena_base=ds.arena, list_base=ds.drawable_list)
+            assert_tier_x_equal(got, ref)
+            cnt = sc.ml_count[sc.drawable_ml]
+            assert got["medium_count"] == int(((cnt > 32) & (cnt <= 64)).sum())
+            assert got["status"] == 0
     finally:
         ds.close()
 
