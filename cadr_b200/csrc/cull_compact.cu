@@ -436,6 +436,23 @@ __device__ __forceinline__ uint2 ldsU2(uint32_t addr)
 	return v;
 }
 
+__device__ __forceinline__ void stsU2(uint32_t addr, uint2 v)
+{
+	asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ unsigned long long ldsU64(uint32_t addr)
+{
+	const uint2 v = ldsU2(addr);
+	return (unsigned long long)v.x | ((unsigned long long)v.y << 32);
+}
+__device__ __forceinline__ void orMask(uint32_t addr, unsigned long long bits)
+{
+	if(bits) {
+		const uint2 v = ldsU2(addr);
+		stsU2(addr, make_uint2(v.x | uint32_t(bits), v.y | uint32_t(bits >> 32)));
+	}
+}
+
 // position of the run: the item that contains the first instance of a step, and that item's flat index range
 struct FlatPos { uint32_t item, start, end; };
 
@@ -477,7 +494,11 @@ __device__ __forceinline__ void cullMediumBatches(const CullArgs& A, const uint3
 		const uint32_t myDesc = descs + lane * FL_STRIDE;
 		const uint32_t total = __reduce_add_sync(FULL, lds32(myDesc + 8u));     // instances of the batch
 
-		unsigned long long m0 = 0, m1 = 0, m2 = 0;       // lane i: survivors of item i per LOD, bit j = matrix j
+		// lane i collects the survivors of item i per LOD (bit j = matrix j) in three 64-bit masks kept in padding of its
+		// shared-memory descriptor (WorkItem::pad1, ::pad2, and the 16 bytes between descriptors), not in registers: they
+		// are touched by two lanes per step and would otherwise be spilled around the evaluation
+		constexpr uint32_t M0 = 56u, M1 = 88u, M2 = 128u;
+		stsU2(myDesc + M2, make_uint2(0u, 0u));          // the two pad fields arrive as zeros from the producer
 		uint32_t nb = 0;
 		Mat cur, nxt;
 		FlatPos PL, PE;                                  // position of the step being loaded / being evaluated
@@ -523,10 +544,14 @@ __device__ __forceinline__ void cullMediumBatches(const CullArgs& A, const uint3
 			const uint32_t cut = min(32u, PE.end - f0);
 			if(lane == PE.item) {
 				const uint32_t keep = (cut >= 32u) ? FULL : ((1u << cut) - 1u), sh = f0 - PE.start;
-				m0 |= (unsigned long long)(b0 & keep) << sh; m1 |= (unsigned long long)(b1 & keep) << sh; m2 |= (unsigned long long)(b2 & keep) << sh;
+				orMask(myDesc + M0, (unsigned long long)(b0 & keep) << sh);
+				orMask(myDesc + M1, (unsigned long long)(b1 & keep) << sh);
+				orMask(myDesc + M2, (unsigned long long)(b2 & keep) << sh);
 			}
 			else if(lane == PE.item + 1u && cut < 32u) {
-				m0 |= (unsigned long long)(b0 >> cut); m1 |= (unsigned long long)(b1 >> cut); m2 |= (unsigned long long)(b2 >> cut);
+				orMask(myDesc + M0, (unsigned long long)(b0 >> cut));
+				orMask(myDesc + M1, (unsigned long long)(b1 >> cut));
+				orMask(myDesc + M2, (unsigned long long)(b2 >> cut));
 			}
 			flatAdvance(PE, f0 + 32u, descs);
 			cur = nxt;
@@ -537,6 +562,7 @@ __device__ __forceinline__ void cullMediumBatches(const CullArgs& A, const uint3
 			nb = __reduce_add_sync(FULL, nb);
 			if(lane == 0) atomicAdd(&A.hdr->nearBandCount, nb);
 		}
+		const unsigned long long m0 = ldsU64(myDesc + M0), m1 = ldsU64(myDesc + M1), m2 = ldsU64(myDesc + M2);
 		const uint32_t k0 = uint32_t(__popcll(m0)), k1 = uint32_t(__popcll(m1)), k2 = uint32_t(__popcll(m2));
 		const uint32_t nInst = k0 + k1 + k2, nCmd = (k0 ? 1u : 0u) + (k1 ? 1u : 0u) + (k2 ? 1u : 0u);
 		const bool has = nInst > 0;
@@ -591,9 +617,39 @@ __device__ __forceinline__ void cullMediumBatches(const CullArgs& A, const uint3
 	}
 }
 
+// Valid part of the two queues that share the work-item workspace.  Long items fill slots 0, 1, ... upwards, medium
+// items slots capacity - 1, capacity - 2, ... downwards.  Slot i is a valid long item iff i < longCount and
+// i + mediumCount < capacity (mirror image for medium items): both counters only grow while the producer runs, so a
+// valid slot was always written, and never by the other side; where the two ends overlap, the overlapping items are
+// dropped and reported (status bit 1).
+__device__ __forceinline__ void queueExtents(const CullArgs& A, uint32_t& totalLong, uint32_t& totalMedium, bool& overflow)
+{
+	const uint32_t queuedL = A.hdr->chunkCount, queuedM = A.hdr->medCount, cap = A.chunkCapacity;
+	totalLong = min(queuedL, cap - min(queuedM, cap));
+	totalMedium = min(queuedM, cap - min(queuedL, cap));
+	overflow = uint64_t(queuedL) + queuedM > cap;
+}
+
+// The medium items as a kernel of their own (default).  It is launched right behind cullListWarpKernel as a
+// programmatic dependent launch and does not wait for it (the two consume disjoint queues and share only the atomic
+// output counters): its CTAs move in as the long-item CTAs retire, and when there are no medium items they leave at once,
+// so a frame without medium lists pays neither a launch gap nor - unlike with the batches appended to
+// cullListWarpKernel (variant 5) - a larger shared-memory carve-out: that kernel streams C3 1 % slower under any
+// carve-out above its own 4 KiB per CTA (measured with an unused dynamic allocation of 4 .. 32 KiB).
+__global__ void __launch_bounds__(CM_THREADS, 4)
+cullMediumKernel(const __grid_constant__ CullArgs A)
+{
+	__shared__ __align__(16) uint8_t sDescs[CM_THREADS / 32][FL_WARP_BYTES];
+	uint32_t totalL, totalM;
+	bool overflow;
+	queueExtents(A, totalL, totalM, overflow);
+	if(totalM) cullMediumBatches(A, smemAddr(sDescs[threadIdx.x >> 5]), threadIdx.x & 31, totalM);
+}
+
 constexpr int LW_DESCS = 4;     // descriptor ring per warp: items A, B, C and the slot being refilled
 
-// FLAT: after the queue of long items has run dry, the warp goes on with the medium items (cullMediumBatches above).
+// FLAT (CADR_B200_CULL_VARIANT=5): after the queue of long items has run dry, the warp goes on with the medium items
+// itself instead of leaving them to cullMediumKernel.
 template<bool FLAT>
 __global__ void __launch_bounds__(CM_THREADS, 4)
 cullListWarpKernel(const __grid_constant__ CullArgs A)
@@ -605,15 +661,11 @@ cullListWarpKernel(const __grid_constant__ CullArgs A)
 	const uint32_t descs = smemAddr(sDescs[threadIdx.x >> 5]);
 	const unsigned FULL = 0xffffffffu;
 
-	// The workspace is filled from both ends: long items in slots 0, 1, ..., medium items in slots capacity - 1,
-	// capacity - 2, ...  Slot i is a valid long item iff i < longCount and i + mediumCount < capacity (and the mirror
-	// image for medium items): both counters only grow while the producer runs, so a valid slot was always written
-	// and never written by the other side; when the two ends overlap, the overlapping items are dropped and reported.
-	const uint32_t queuedL = A.hdr->chunkCount, queuedM = FLAT ? A.hdr->medCount : 0u;
-	uint32_t total = min(queuedL, A.chunkCapacity - min(queuedM, A.chunkCapacity));
-	const uint32_t totalM = min(queuedM, A.chunkCapacity - min(queuedL, A.chunkCapacity));
-	if(FLAT && blockIdx.x == 0 && threadIdx.x == 0 && uint64_t(queuedL) + queuedM > A.chunkCapacity)
-		atomicOr(&A.hdr->status, CADR_CULL_STATUS_CHUNK_OVERFLOW);
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");    // cullMediumKernel may move in as soon as CTAs retire
+	uint32_t total, totalM;
+	bool overflow;
+	queueExtents(A, total, totalM, overflow);
+	if(overflow && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&A.hdr->status, CADR_CULL_STATUS_CHUNK_OVERFLOW);
 	const uint32_t numWarps = gridDim.x * (CM_THREADS / 32);
 	uint32_t batch = total / (numWarps * 16u);          // long queues: fewer atomics; short queues: best balance
 	batch = batch < 1u ? 1u : (batch > 8u ? 8u : batch);
@@ -860,9 +912,9 @@ cullListRingKernel(const __grid_constant__ CullArgs A)
 static int cullVariant()
 {
 	const char* v = std::getenv("CADR_B200_CULL_VARIANT");
-	return v ? std::atoi(v) : 2;   // 2 = warp per item, register prefetch + flat medium batches (default); 4 = the same without
-	                               // the medium queue; 3 = warp per item, shared-memory ring; 1 = CTA-wide TMA pipeline;
-	                               // 0 = first direct-load version
+	return v ? std::atoi(v) : 2;   // 2 = warp per item, register prefetch + cullMediumKernel (default); 5 = medium batches inside
+	                               // cullListWarpKernel; 4 = no medium queue; 3 = warp per item, shared-memory ring;
+	                               // 1 = CTA-wide TMA pipeline; 0 = first direct-load version
 }
 
 int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, bool fused)
@@ -927,10 +979,11 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 		A.xTag[r] = reinterpret_cast<uint2*>(exchange && r < p.exchangeWorld ? p.exchangeTag[r] : 0);
 	}
 
-	// medium lists get their own queue only with the default list kernel (2); 4 = the same kernel with every list longer
-	// than 32 matrices in the one queue (the state before the flat medium path existed), for A/B measurements
+	// medium lists get their own queue only with the default list kernels (2; 5 = medium batches appended to
+	// cullListWarpKernel instead of cullMediumKernel); 4 = every list longer than 32 matrices in the one queue (the
+	// state before the medium path existed), for A/B measurements
 	const int variant = cullVariant();
-	A.medMax = (variant == 2 && p.chunkCapacity) ? CADR_CULL_MEDIUM_LIST_MAX : 0u;
+	A.medMax = ((variant == 2 || variant == 5) && p.chunkCapacity) ? CADR_CULL_MEDIUM_LIST_MAX : 0u;
 
 	uint32_t gridS = (p.numDrawables + CS_THREADS - 1) / CS_THREADS;
 	ctx->timeBegin(KS_CULL_SMALL, s);
@@ -971,8 +1024,21 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 			uint32_t gridL = uint32_t(ctx->smCount) * 4u;   // persistent warps: four CTAs of eight warps per SM
 			const uint32_t need = (p.chunkCapacity + CM_THREADS / 32 - 1) / (CM_THREADS / 32);
 			if(gridL > need) gridL = need;
-			if(A.medMax) cullListWarpKernel<true><<<gridL, CM_THREADS, 0, s>>>(A);
-			else         cullListWarpKernel<false><<<gridL, CM_THREADS, 0, s>>>(A);
+			if(variant == 5) cullListWarpKernel<true><<<gridL, CM_THREADS, 0, s>>>(A);
+			else {
+				cullListWarpKernel<false><<<gridL, CM_THREADS, 0, s>>>(A);
+				if(A.medMax) {
+					// programmatic dependent launch: may start while cullListWarpKernel is still running
+					cudaLaunchConfig_t cfg = {};
+					cfg.gridDim = dim3(gridL); cfg.blockDim = dim3(CM_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+					cudaLaunchAttribute attr[1];
+					attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+					attr[0].val.programmaticStreamSerializationAllowed = 1;
+					cfg.attrs = attr; cfg.numAttrs = 1;
+					CADR_CUDA(cudaLaunchKernelEx(&cfg, cullMediumKernel, A));
+					ctx->launches++;
+				}
+			}
 		}
 		ctx->timeEnd(KS_CULL_LARGE, s);
 		ctx->launches++;
