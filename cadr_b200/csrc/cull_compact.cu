@@ -4,7 +4,7 @@
 // DESIGN.md "Tier X" and derived from CadR::BoundingSphere operator* (src/CadR/BoundingSphere.h:70-87).
 // Parity is therefore against this repo's own CPU oracle ("parity unpinned by the reference").
 //
-// Two kernels per frame, both HBM-bound (no tensor-core work: gather + compaction):
+// Three kernels per frame, HBM-bound (no tensor-core work: gather + compaction):
 //
 //   cullSmallKernel     one THREAD per drawable.  Lists of <= 32 matrices are evaluated by the drawable's own
 //                       thread (config C2: 10 M drawables x 1 matrix).  Longer lists are cut into work items of
@@ -15,7 +15,9 @@
 //                       item index is claimed three items ahead, the descriptor is requested two items ahead, and
 //                       the last 32-matrix step of an item already loads the first step of the next one, so no
 //                       dependent load and no atomic round trip is ever waited for in front of a matrix load.
-//                       Default for every list longer than 32 matrices.
+//                       Default for every list longer than CADR_CULL_MEDIUM_LIST_MAX (64) matrices.
+//   cullMediumKernel    lists of 33..64 matrices (their own queue): 32 work items per warp, evaluated as one flat run
+//                       of instances; launched behind cullListWarpKernel as a programmatic dependent launch.
 //   cullListRingKernel  the same with a warp-private shared-memory ring filled by asynchronous copies (LDGSTS) three
 //                       steps ahead (CADR_B200_CULL_VARIANT=3): higher memory-side ceiling, but issue-bound.
 //   cull_variants.cu    two earlier versions of the long-list stage, kept for A/B measurements: cullLargeKernel, a
