@@ -6,34 +6,11 @@
 //   * what the facade's own getters say the result must be (expected indirect / pointers),
 //   * with a device: what the GPU produced (Tier R outputs and the compacted Tier X buffers).
 // usage: facade_scene_test <cuda device | -1> <dump file> [frames]
-#include <CadR/CadR.h>
-#include "../../../include/cadr_b200.h"
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <map>
+#include "frame_dump.h"
 #include <memory>
 #include <random>
 
 using namespace CadR;
-
-static FILE* g_out;
-template<typename T> static void put(const T& v) { fwrite(&v, sizeof(T), 1, g_out); }
-static void putBytes(const void* p, size_t n) { if(n) fwrite(p, 1, n, g_out); }
-
-struct Shadow {
-	std::map<uint64_t, std::vector<uint8_t>> seg;   // DataMemory base -> bytes
-	void sync(DataStorage& ds) { for(DataMemory* m : ds.dataMemoryList()) if(m->size() && !seg.count(m->deviceAddress())) seg[m->deviceAddress()].assign(m->size(), 0); }
-	void apply(const cadr_copy_region* r, size_t n) {
-		for(size_t i = 0; i < n; i++) {
-			auto it = seg.upper_bound(r[i].dstAddr);
-			if(it == seg.begin()) { fprintf(stderr, "region outside every DataMemory\n"); exit(3); }
-			--it;
-			if(r[i].dstAddr + r[i].bytes > it->first + it->second.size()) { fprintf(stderr, "region overruns its DataMemory\n"); exit(3); }
-			memcpy(it->second.data() + (r[i].dstAddr - it->first), reinterpret_cast<const void*>(r[i].srcOffset), r[i].bytes);
-		}
-	}
-};
 
 struct Geo { std::unique_ptr<Geometry> g; std::vector<PrimitiveSet> ps; };
 
@@ -42,13 +19,14 @@ int main(int argc, char** argv)
 	if(argc < 3) { fprintf(stderr, "usage: %s <device|-1> <dump> [frames] [bounds]\n", argv[0]); return 2; }
 	const int device = atoi(argv[1]);
 	const int frames = argc > 3 ? atoi(argv[3]) : 4;
-	g_out = fopen(argv[2], "wb");
-	if(!g_out) return 2;
+	dump::Writer w;
+	w.out = fopen(argv[2], "wb");
+	if(!w.out) return 2;
 	try {
 		Renderer r(device);
 		if(argc > 4 && std::string(argv[4]) == "bounds") r.setDrawableBounds(true);
-		Shadow shadow;
-		r.dataStorage().uploadObserver = [&](const cadr_copy_region* regs, size_t n) { shadow.sync(r.dataStorage()); shadow.apply(regs, n); };
+		dump::Shadow shadow;
+		shadow.attach(r);
 		std::mt19937 rng(1234);
 		auto rnd = [&](uint32_t n) { return uint32_t(rng() % n); };
 
@@ -161,67 +139,20 @@ int main(int argc, char** argv)
 			r.endFrame();
 
 			// ---- dump ---------------------------------------------------------------------------------
-			shadow.sync(r.dataStorage());
-			fwrite("CADRF002", 1, 8, g_out);
-			put(uint32_t(frame)); put(uint32_t(device >= 0));
-			put(uint32_t(shadow.seg.size()));
-			for(auto& [base, bytes] : shadow.seg) { put(uint64_t(base)); put(uint64_t(bytes.size())); putBytes(bytes.data(), bytes.size()); }
-			put(uint64_t(r.dataStorage().handleTableDeviceAddress())); put(uint32_t(r.dataStorage().handleLevel())); put(uint32_t(n));
-			put(uint64_t(r.dataStorage().handleTable().highestHandle()));
-			put(uint64_t(r.drawableBufferAddress()));
-			putBytes(r.drawableStagingData(), n * 48);
-			putBytes(r.cullStagingData(), n * 48);
-			put(f);
-			const auto& ranges = r.drawRanges();
-			put(uint32_t(ranges.size()));
-			for(size_t k = 0; k < ranges.size(); k++) {
-				put(uint32_t(ranges[k].firstDrawable)); put(uint32_t(ranges[k].numDrawables));
-				put(uint64_t(ranges[k].drawablePointersAddress - r.drawablePointersBufferAddress())); put(uint64_t(ranges[k].indirectOffset));
-			}
 			// what the facade itself says the processing result must be
-			for(const DrawRange& dr : ranges)
-				for(size_t i = 0; i < dr.numDrawables; i++) {
-					Drawable& d = dr.stateSet->getDrawable(i);
-					const Geo& geo = geos[geoOf[&d]];
-					const PrimitiveSet& ps = geo.ps[psOffsetOf[&d] / 8];
-					uint32_t ind[4] = {ps.indexCount, uint32_t(d.matrixList().numMatrices()), ps.startIndex, 0};
-					// Drawable::create() drops the drawable-data handle (reference behaviour, Drawable.cpp:128,147)
-					const DrawableGpuData& rec = dr.stateSet->drawableDataList()[i];
-					uint64_t ptr[4] = {geo.g->vertexDataAllocation().deviceAddress(), geo.g->indexDataAllocation().deviceAddress(),
-					                   d.matrixList().allocation().deviceAddress(),
-					                   (d.drawableData() && rec.drawableDataHandle) ? d.drawableData()->deviceAddress() : 0};
-					putBytes(ind, 16); putBytes(ptr, 32);
-				}
-			{
-				const CullResult& c = r.cullResult();
-				put(uint32_t(c.numRanges));
-				for(auto& reg : c.regions) putBytes(reg.data(), 16);
-			}
-			if(r.hasDevice()) {
-				std::vector<uint8_t> buf(n * 48);
-				r.readDevice(buf.data(), r.drawIndirectBufferAddress(), n * 16); putBytes(buf.data(), n * 16);
-				r.readDevice(buf.data(), r.drawablePointersBufferAddress(), n * 32); putBytes(buf.data(), n * 32);
-				const CullResult& c = r.cullResult();
-				uint64_t cmdCap = 0, instCap = 0;
-				for(auto& reg : c.regions) { cmdCap += reg[1]; instCap += reg[3]; }
-				put(cmdCap); put(instCap);
-				std::vector<uint8_t> big2(std::max<size_t>({size_t(cmdCap) * 32, size_t(instCap) * 4, cadr_b200_cull_counters_bytes(c.numRanges), 16}));
-				r.readDevice(big2.data(), c.counters, cadr_b200_cull_counters_bytes(c.numRanges)); putBytes(big2.data(), cadr_b200_cull_counters_bytes(c.numRanges));
-				if(cmdCap) {
-					r.readDevice(big2.data(), c.commands, cmdCap * 20); putBytes(big2.data(), cmdCap * 20);
-					r.readDevice(big2.data(), c.pointers, cmdCap * 32); putBytes(big2.data(), cmdCap * 32);
-					r.readDevice(big2.data(), c.tags, cmdCap * 8); putBytes(big2.data(), cmdCap * 8);
-				}
-				if(instCap) { r.readDevice(big2.data(), c.instances, instCap * 4); putBytes(big2.data(), instCap * 4); }
-			}
-			fprintf(stderr, "frame %d: %zu drawables, %zu ranges, handle level %u (%llu handles), %zu DataMemory, staging in use %zu / pooled %zu, list upload %zu bytes\n",
-			        frame, n, ranges.size(), r.dataStorage().handleLevel(), (unsigned long long)r.dataStorage().handleTable().highestHandle(),
-			        r.dataStorage().dataMemoryList().size(), r.stagingManager().numBlocksInUse(), r.stagingManager().numBlocksAvailable(),
-			        r.lastDrawableUploadBytes());
+			w.frame(r, shadow, n, f, frame, [&](Drawable& d, const DrawableGpuData& rec, uint32_t ind[4], uint64_t ptr[4]) {
+				const Geo& geo = geos[geoOf[&d]];
+				const PrimitiveSet& ps = geo.ps[psOffsetOf[&d] / 8];
+				ind[0] = ps.indexCount; ind[1] = uint32_t(d.matrixList().numMatrices()); ind[2] = ps.startIndex; ind[3] = 0;
+				ptr[0] = geo.g->vertexDataAllocation().deviceAddress(); ptr[1] = geo.g->indexDataAllocation().deviceAddress();
+				ptr[2] = d.matrixList().allocation().deviceAddress();
+				// Drawable::create() drops the drawable-data handle (reference behaviour, Drawable.cpp:128,147)
+				ptr[3] = (d.drawableData() && rec.drawableDataHandle) ? d.drawableData()->deviceAddress() : 0;
+			});
 		}
 		drawables.clear();
 	}
-	catch(Error& e) { fprintf(stderr, "CadR::Error: %s\n", e.what()); fclose(g_out); return 1; }
-	fclose(g_out);
+	catch(Error& e) { fprintf(stderr, "CadR::Error: %s\n", e.what()); fclose(w.out); return 1; }
+	fclose(w.out);
 	return 0;
 }

@@ -13,7 +13,7 @@ import pytest
 from oracle import binding as ob
 from facade_dump import parse
 from helpers import assert_tier_x_equal
-from test_host_cpu import check_frame_against_oracle
+from test_host_cpu import BOX_SCENES, boxes_expectation, check_frame_against_oracle, run_boxes_scene
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "cadr_b200", "host", "bin")
@@ -69,3 +69,20 @@ def test_facade_long_run_with_several_staging_blocks():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "soak_facade.py"), "40"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "soak_facade: ok" in r.stdout
+
+
+@pytest.mark.parametrize("scene", BOX_SCENES)
+def test_reference_example_scenes_on_gpu_match_oracle(scene, tmp_path):
+    """The scenes of the reference's examples/RenderingPerformance (Tests.cpp) driven through CadR::Renderer on the
+    device, the show/hide scenes destroying and re-creating their drawables every frame: Tier R buffers and the
+    compacted Tier X buffers of every frame against the oracle."""
+    frames = run_boxes_scene(scene, 0, tmp_path)
+    for k, f in enumerate(frames):
+        assert f["has_device"]
+        mem, lst, ind, ptr = check_frame_against_oracle(f)
+        assert f["n"] == boxes_expectation(scene, k)[0]
+        assert np.array_equal(f["gpu_indirect"], ind)
+        assert np.array_equal(f["gpu_pointers"], ptr)
+        ref = ob.cull_compact(mem, f["root"], f["level"], lst, f["n"], ind, ptr, f["cull"], f["planes"], f["eye"], f["regions"])
+        assert_tier_x_equal(f["gpu_cull"], ref)
+        assert ref["num_instances"] > 0
