@@ -66,7 +66,7 @@ static_assert(sizeof(DrawableCullData) == 48, "cull record is 48 bytes");
 class Geometry {                  // src/CadR/Geometry.h
 	friend class Drawable;
 	DataAllocation _vertices, _indices, _primitiveSets;
-	std::list<Drawable*> _drawableList;
+	Drawable* _firstDrawable = nullptr;   ///< intrusive list of the drawables that use this geometry (O(1) link / unlink, like the reference's auto-unlink hooks)
 public:
 	explicit Geometry(Renderer& r);
 	Geometry(const Geometry&) = delete;
@@ -121,8 +121,12 @@ class Drawable {                  // src/CadR/Drawable.{h,cpp}
 	DataAllocation* _drawableData = nullptr;
 	Geometry* _geometry = nullptr;
 	uint32_t _indexIntoStateSet = ~0u;
+	Drawable* _geometryPrev = nullptr;     // neighbours in Geometry's list of drawables
+	Drawable* _geometryNext = nullptr;
 	void create(Geometry& geometry, uint32_t primitiveSetOffset, MatrixList& matrixList, DataAllocation* drawableData, StateSet& stateSet);
+	void linkToGeometry(Geometry& geometry) noexcept;
 	void unlinkFromGeometry() noexcept;
+	void takeGeometryLinkOf(Drawable& other) noexcept;
 public:
 	Drawable() noexcept = default;
 	Drawable(Geometry& geometry, uint32_t primitiveSetOffset, MatrixList& matrixList, StateSet& stateSet);

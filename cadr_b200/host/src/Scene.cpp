@@ -10,7 +10,11 @@ Geometry::Geometry(Renderer& r) : _vertices(r.dataStorage()), _indices(r.dataSto
 Geometry::~Geometry()
 {
 	// drawables that still reference this geometry are detached (auto-unlink hooks in the reference)
-	for(Drawable* d : _drawableList) d->_geometry = nullptr;
+	for(Drawable* d = _firstDrawable; d; ) {
+		Drawable* next = d->_geometryNext;
+		d->_geometry = nullptr; d->_geometryPrev = d->_geometryNext = nullptr;
+		d = next;
+	}
 }
 
 // ---- MatrixList -------------------------------------------------------------------------------------
@@ -40,31 +44,54 @@ mat4* MatrixList::editNewContent(size_t numMatrices)
 
 // ---- Drawable ---------------------------------------------------------------------------------------
 Drawable::Drawable(Geometry& geometry, uint32_t primitiveSetOffset, MatrixList& matrixList, StateSet& stateSet)
-	: _matrixList(&matrixList), _drawableData(nullptr), _geometry(&geometry)
+	: _matrixList(&matrixList), _drawableData(nullptr)
 {
-	geometry._drawableList.push_back(this);
+	linkToGeometry(geometry);
 	stateSet.appendDrawableInternal(*this, DrawableGpuData(
 		geometry.vertexDataAllocation().handle(), geometry.indexDataAllocation().handle(), matrixList.handle(),
 		0, geometry.primitiveSetDataAllocation().handle(), primitiveSetOffset));
 }
 
 Drawable::Drawable(Geometry& geometry, uint32_t primitiveSetOffset, MatrixList& matrixList, DataAllocation& drawableData, StateSet& stateSet)
-	: _matrixList(&matrixList), _drawableData(&drawableData), _geometry(&geometry)
+	: _matrixList(&matrixList), _drawableData(&drawableData)
 {
-	geometry._drawableList.push_back(this);
+	linkToGeometry(geometry);
 	stateSet.appendDrawableInternal(*this, DrawableGpuData(
 		geometry.vertexDataAllocation().handle(), geometry.indexDataAllocation().handle(), matrixList.handle(),
 		drawableData.handle(), geometry.primitiveSetDataAllocation().handle(), primitiveSetOffset));
 }
 
+void Drawable::linkToGeometry(Geometry& geometry) noexcept
+{
+	_geometry = &geometry;
+	_geometryPrev = nullptr;
+	_geometryNext = geometry._firstDrawable;
+	if(_geometryNext) _geometryNext->_geometryPrev = this;
+	geometry._firstDrawable = this;
+}
+
 void Drawable::unlinkFromGeometry() noexcept
 {
 	if(_geometry) {
-		auto& l = _geometry->_drawableList;
-		auto it = std::find(l.begin(), l.end(), this);
-		if(it != l.end()) l.erase(it);
+		if(_geometryPrev) _geometryPrev->_geometryNext = _geometryNext;
+		else _geometry->_firstDrawable = _geometryNext;
+		if(_geometryNext) _geometryNext->_geometryPrev = _geometryPrev;
 		_geometry = nullptr;
+		_geometryPrev = _geometryNext = nullptr;
 	}
+}
+
+// this object replaces `other` in the list of other's geometry (move construction / assignment)
+void Drawable::takeGeometryLinkOf(Drawable& other) noexcept
+{
+	_geometry = other._geometry; _geometryPrev = other._geometryPrev; _geometryNext = other._geometryNext;
+	if(_geometry) {
+		if(_geometryPrev) _geometryPrev->_geometryNext = this;
+		else _geometry->_firstDrawable = this;
+		if(_geometryNext) _geometryNext->_geometryPrev = this;
+	}
+	other._geometry = nullptr;
+	other._geometryPrev = other._geometryNext = nullptr;
 }
 
 Drawable::~Drawable() noexcept
@@ -83,13 +110,11 @@ void Drawable::destroy() noexcept
 }
 
 Drawable::Drawable(Drawable&& o) noexcept
-	: _stateSet(o._stateSet), _matrixList(o._matrixList), _drawableData(o._drawableData), _geometry(o._geometry),
-	  _indexIntoStateSet(o._indexIntoStateSet)
+	: _stateSet(o._stateSet), _matrixList(o._matrixList), _drawableData(o._drawableData), _indexIntoStateSet(o._indexIntoStateSet)
 {
 	if(_indexIntoStateSet != ~0u) _stateSet->_drawablePtrList[_indexIntoStateSet] = this;
-	if(_geometry) std::replace(_geometry->_drawableList.begin(), _geometry->_drawableList.end(), &o, this);
+	takeGeometryLinkOf(o);
 	o._indexIntoStateSet = ~0u;
-	o._geometry = nullptr;
 }
 
 Drawable& Drawable::operator=(Drawable&& rhs) noexcept
@@ -98,19 +123,17 @@ Drawable& Drawable::operator=(Drawable&& rhs) noexcept
 	if(_indexIntoStateSet != ~0u) _stateSet->removeDrawableInternal(*this);
 	unlinkFromGeometry();
 	_stateSet = rhs._stateSet; _matrixList = rhs._matrixList; _drawableData = rhs._drawableData;
-	_geometry = rhs._geometry; _indexIntoStateSet = rhs._indexIntoStateSet;
+	_indexIntoStateSet = rhs._indexIntoStateSet;
 	if(_indexIntoStateSet != ~0u) _stateSet->_drawablePtrList[_indexIntoStateSet] = this;
-	if(_geometry) std::replace(_geometry->_drawableList.begin(), _geometry->_drawableList.end(), &rhs, this);
+	takeGeometryLinkOf(rhs);
 	rhs._indexIntoStateSet = ~0u;
-	rhs._geometry = nullptr;
 	return *this;
 }
 
 void Drawable::create(Geometry& geometry, uint32_t primitiveSetOffset, MatrixList& matrixList, DataAllocation* drawableData, StateSet& stateSet)
 {
 	unlinkFromGeometry();
-	geometry._drawableList.push_back(this);
-	_geometry = &geometry;
+	linkToGeometry(geometry);
 	_matrixList = &matrixList;
 	_drawableData = drawableData;
 	// NOTE: like the reference (Drawable.cpp:128,147) create() stores drawableDataHandle = 0 even when drawableData

@@ -9,14 +9,20 @@
 //   materials           IndependentBoxes1000MaterialsScene: the same with M materials handed out round-robin as
 //                       per-drawable data (M = boxes / 8 here, 1000 in the reference)
 //   material-per-box    IndependentBoxes1000000MaterialsScene: one material per box
+//   shared-geometry     generateBoxesScene(instanced = false, singleGeometry = true): every drawable uses the ONE box
+//                       geometry with its own one-matrix MatrixList (also the shape of BASELINE configs[1])
 //   showhide            IndependentBoxesShowHideScene: no drawables at creation; EVERY frame all drawables are destroyed
 //                       and every other box gets a new one, even boxes on even frames, odd ones on odd frames
+//   showhide-shared     the singleGeometry branch of the same update (:667-671)
 //   showhide-instanced  the instanced branch of the same update (:636-657): the one MatrixList is rewritten every frame
 //                       with the matrices of every other column of boxes
 //
 // Every box gets its bounding sphere (Drawable::setCullData), so the culling extension runs on the same frames.
-// usage: boxes_scene_test <cuda device | -1> <dump file> <scene> [boxes per side = 6] [frames = 3]
+// usage: boxes_scene_test <cuda device | -1> <dump file | -> <scene> [boxes per side = 6] [frames = 3]
+// With "-" instead of a dump file nothing is dumped and the host time of every phase of the frame is printed instead
+// (the reference application's "scene update / construct" and "cpu time" columns, main.cpp:1634-1791).
 #include "frame_dump.h"
+#include <chrono>
 #include <cmath>
 #include <deque>
 #include <string>
@@ -73,6 +79,7 @@ struct Scene {
 	std::vector<Drawable> drawables;
 	std::map<const Geometry*, PrimitiveSet> primitiveSetOf;   // what was uploaded for each geometry
 	std::map<const Drawable*, const Geometry*> geometryOf;
+	bool track = true;                 // off in timing mode: the maps above are test bookkeeping, not application work
 
 	Scene(Renderer& r_, StateSet& root_, Grid g) : r(r_), root(root_), grid(g) {}
 
@@ -83,7 +90,7 @@ struct Scene {
 		memcpy(g.createIndexStagingData(sizeof(kBoxIndices)).data<uint32_t>(), kBoxIndices, sizeof(kBoxIndices));
 		PrimitiveSet ps{36, 0};
 		*g.createPrimitiveSetStagingData(sizeof(PrimitiveSet)).data<PrimitiveSet>() = ps;
-		primitiveSetOf[&g] = ps;
+		if(track) primitiveSetOf[&g] = ps;
 		return g;
 	}
 	DataAllocation& addMaterial(size_t index, size_t of) {
@@ -98,7 +105,7 @@ struct Scene {
 	void addDrawable(Geometry& g, MatrixList& ml, DataAllocation& material, float radius) {
 		Drawable& d = drawables.emplace_back(g, 0, ml, material, root);
 		d.setCullData(BoundingSphere{{0.f, 0.f, 0.f}, radius});
-		geometryOf[&d] = &g;
+		if(track) geometryOf[&d] = &g;
 	}
 	float boxRadius() const { return std::sqrt(3.f) * grid.boxSize / 2.f; }
 
@@ -139,9 +146,9 @@ struct Scene {
 		fillInstancedList(0, 1);
 		addDrawable(geometries.front(), lists[0], addMaterial(0, 1), boxRadius());
 	}
-	void createIndependent(size_t numMaterials, bool withDrawables) {
+	void createIndependent(size_t numMaterials, bool withDrawables, bool singleGeometry = false) {
 		const size_t n = grid.count();
-		for(size_t b = 0; b < n; b++) addBoxGeometry();
+		for(size_t b = 0; b < (singleGeometry ? 1 : n); b++) addBoxGeometry();
 		materials.reserve(numMaterials);
 		for(size_t m = 0; m < numMaterials; m++) addMaterial(m, numMaterials);
 		lists.reserve(n);
@@ -151,7 +158,7 @@ struct Scene {
 		});
 		drawables.reserve(n);
 		if(withDrawables)
-			for(size_t b = 0; b < n; b++) addDrawable(geometries[b], lists[b], materials[b % numMaterials], boxRadius());
+			for(size_t b = 0; b < n; b++) addDrawable(geometries[singleGeometry ? 0 : b], lists[b], materials[b % numMaterials], boxRadius());
 	}
 
 	// ---- per-frame update of the show/hide scenes ---------------------------------------------------------------
@@ -162,7 +169,7 @@ struct Scene {
 		// so an odd frame also leaves out the last box; the k-th new drawable takes geometry k, not geometry i
 		size_t geometryIndex = 0;
 		for(size_t i = frameNumber & 1, c = lists.size() - i; i < c; i += 2)
-			addDrawable(geometries[geometryIndex++], lists[i], materials.back(), boxRadius());
+			addDrawable(geometries[geometries.size() == 1 ? 0 : geometryIndex++], lists[i], materials.back(), boxRadius());
 	}
 	void showHideInstanced(size_t frameNumber) { fillInstancedList(uint32_t(frameNumber & 1), 2); }
 };
@@ -174,19 +181,24 @@ int main(int argc, char** argv)
 	const std::string kind = argv[3];
 	const uint32_t side = argc > 4 ? uint32_t(atoi(argv[4])) : 6u;
 	const int frames = argc > 5 ? atoi(argv[5]) : 3;
+	const bool timingOnly = std::string(argv[2]) == "-";
 	dump::Writer w;
-	w.out = fopen(argv[2], "wb");
+	w.out = fopen(timingOnly ? "/dev/null" : argv[2], "wb");
 	if(!w.out) return 2;
+	auto now = [] { return std::chrono::steady_clock::now(); };
+	auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
 	try {
 		Renderer r(device);
 		dump::Shadow shadow;
-		shadow.attach(r);
+		if(!timingOnly) shadow.attach(r);
 		StateSet root(r);
 		// the reference fits 100 boxes per side into 0.9 of the window's shorter edge; box size = half the spacing
 		const float maxSize = 1080.f * 0.9f;
 		Scene s(r, root, Grid{side, side > 1 ? side - 1 : 1, side > 2 ? side - 2 : 1, maxSize / float(side), maxSize / float(2 * side)});
+		s.track = !timingOnly;
 
 		for(int frame = 0; frame < frames; frame++) {
+			const auto t0 = now();
 			r.beginFrame();
 			if(frame == 0) {
 				if(kind == "baked") s.createBaked();
@@ -194,13 +206,17 @@ int main(int argc, char** argv)
 				else if(kind == "independent") s.createIndependent(1, true);
 				else if(kind == "materials") s.createIndependent(std::max<size_t>(s.grid.count() / 8, 2), true);
 				else if(kind == "material-per-box") s.createIndependent(s.grid.count(), true);
+				else if(kind == "shared-geometry") s.createIndependent(1, true, true);
 				else if(kind == "showhide") s.createIndependent(1, false);
+				else if(kind == "showhide-shared") s.createIndependent(1, false, true);
 				else { fprintf(stderr, "unknown scene %s\n", kind.c_str()); return 2; }
 			}
 			// updateTestScene runs every frame, the first one included (main.cpp frame loop)
-			if(kind == "showhide") s.showHideIndependent(r.frameNumber());
+			if(kind == "showhide" || kind == "showhide-shared") s.showHideIndependent(r.frameNumber());
 			if(kind == "showhide-instanced") s.showHideInstanced(r.frameNumber());
+			const auto t1 = now();
 			r.executeCopyOperations();
+			const auto t2 = now();
 
 			r.beginRecording();
 			const size_t n = r.prepareSceneRendering(root);
@@ -217,6 +233,12 @@ int main(int argc, char** argv)
 			r.executeCopyOperations();
 			if(r.hasDevice()) { r.submit(); r.waitIdle(uint64_t(3e9)); }
 			r.endFrame();
+			if(timingOnly) {
+				const auto t3 = now();
+				fprintf(stderr, "frame %d: %zu drawables, handle level %u | scene update %.2f ms, upload recording %.2f ms, frame recording %.2f ms, list upload %zu bytes\n",
+				        frame, n, r.dataStorage().handleLevel(), ms(t0, t1), ms(t1, t2), ms(t2, t3), r.lastDrawableUploadBytes());
+				continue;
+			}
 
 			w.frame(r, shadow, n, f, frame, [&](Drawable& d, const DrawableGpuData&, uint32_t ind[4], uint64_t ptr[4]) {
 				const Geometry& g = *s.geometryOf.at(&d);
@@ -227,7 +249,10 @@ int main(int argc, char** argv)
 				ptr[3] = d.drawableData() ? d.drawableData()->deviceAddress() : 0;
 			});
 		}
-		s.drawables.clear();
+		// teardown newest first (an application that pops its drawables): unlinking from a shared geometry is O(1)
+		const auto t0 = now();
+		while(!s.drawables.empty()) s.drawables.pop_back();
+		if(timingOnly) fprintf(stderr, "teardown of the drawables: %.2f ms\n", ms(t0, now()));
 	}
 	catch(Error& e) { fprintf(stderr, "CadR::Error: %s\n", e.what()); fclose(w.out); return 1; }
 	catch(std::exception& e) { fprintf(stderr, "exception: %s\n", e.what()); fclose(w.out); return 1; }
