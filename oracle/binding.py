@@ -53,12 +53,25 @@ def lib() -> C.CDLL:
         l.oracle_consume_check_culled.argtypes = [C.POINTER(Segment), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                   C.c_uint32, C.c_uint32, C.c_void_p]
         l.oracle_max_threads.restype = C.c_int
+        l.oracle_transform_spheres.restype = None
+        l.oracle_transform_spheres.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         _lib = l
     return _lib
 
 
 def max_threads() -> int:
     return lib().oracle_max_threads()
+
+
+def transform_spheres(matrices: np.ndarray, spheres: np.ndarray) -> np.ndarray:
+    """World-space bounding spheres {cx, cy, cz, r} of n (column-major mat4, model-space sphere) pairs, exactly as the
+    Tier X evaluation computes them (the restatement of BoundingSphere.h:70-87)."""
+    m = np.ascontiguousarray(matrices, dtype=np.float32).reshape(-1, 16)
+    b = np.ascontiguousarray(spheres, dtype=np.float32).reshape(-1, 4)
+    assert len(m) == len(b)
+    out = np.empty((len(m), 4), np.float32)
+    lib().oracle_transform_spheres(m.ctypes.data, b.ctypes.data, len(m), out.ctypes.data)
+    return out
 
 
 class Memory:

@@ -143,21 +143,37 @@ typedef struct oracle_cull_result {
 /* per-instance evaluation; operation order is normative (DESIGN.md "Tier X"): every fmaf() is ONE IEEE-754
  * fusedMultiplyAdd, everything else a separately rounded fp32 operation (-ffp-contract=off keeps the
  * compiler from fusing or un-fusing anything). */
-static inline int eval_instance(const float* M /* 16 floats, column-major */, const float* bs /* xyz r */,
-                                uint32_t lodCount, float thr0, float thr1,
-                                const float planes[6][4], const float eye[3], int* nearBand)
+/* World-space bounding sphere of one instance: what the reference's `M * boundingSphere` computes
+ * (BoundingSphere.h:70-87), with the operation order of the specification.  out = {cx, cy, cz, r}. */
+static inline void transform_sphere(const float* M /* 16 floats, column-major */, const float* bs /* xyz r */, float* out)
 {
 	/* centre = mat3(M)*c + M[3].xyz                       BoundingSphere.h:73 */
-	float cx = fmaf(M[8],  bs[2], fmaf(M[4], bs[1], fmaf(M[0], bs[0], M[12])));
-	float cy = fmaf(M[9],  bs[2], fmaf(M[5], bs[1], fmaf(M[1], bs[0], M[13])));
-	float cz = fmaf(M[10], bs[2], fmaf(M[6], bs[1], fmaf(M[2], bs[0], M[14])));
+	out[0] = fmaf(M[8],  bs[2], fmaf(M[4], bs[1], fmaf(M[0], bs[0], M[12])));
+	out[1] = fmaf(M[9],  bs[2], fmaf(M[5], bs[1], fmaf(M[1], bs[0], M[13])));
+	out[2] = fmaf(M[10], bs[2], fmaf(M[6], bs[1], fmaf(M[2], bs[0], M[14])));
 	/* radius = sqrt(max squared column length) * r        BoundingSphere.h:76-85 */
 	float s0 = fmaf(M[2],  M[2],  fmaf(M[1], M[1], M[0] * M[0]));
 	float s1 = fmaf(M[6],  M[6],  fmaf(M[5], M[5], M[4] * M[4]));
 	float s2 = fmaf(M[10], M[10], fmaf(M[9], M[9], M[8] * M[8]));
 	float s01 = (s0 < s1) ? s1 : s0;       /* std::max */
 	float s = (s01 < s2) ? s2 : s01;
-	float r = sqrtf(s) * bs[3];
+	out[3] = sqrtf(s) * bs[3];
+}
+
+/* The same for n (matrix, sphere) pairs: lets the tests compare this step with outputs of the reference's own
+ * BoundingSphere.h (tests/golden/bounding_sphere_ref.npz, oracle/ref_sphere_probe.cpp). */
+void oracle_transform_spheres(const float* matrices, const float* spheres, uint32_t n, float* out)
+{
+	for(uint32_t i = 0; i < n; i++) transform_sphere(matrices + 16 * (size_t)i, spheres + 4 * (size_t)i, out + 4 * (size_t)i);
+}
+
+static inline int eval_instance(const float* M /* 16 floats, column-major */, const float* bs /* xyz r */,
+                                uint32_t lodCount, float thr0, float thr1,
+                                const float planes[6][4], const float eye[3], int* nearBand)
+{
+	float ws[4];
+	transform_sphere(M, bs, ws);
+	const float cx = ws[0], cy = ws[1], cz = ws[2], r = ws[3];
 
 	int nonEmpty = bs[3] >= 0.f;           /* BoundingSphere.h:39-43: radius -inf (or < 0) == empty */
 	int visible = nonEmpty;

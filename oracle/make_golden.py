@@ -9,6 +9,9 @@
   allocator_kat.json.gz     command streams and the placements chosen by the reference's own
                             CircularAllocationMemory.h (oracle/ref_alloc_probe.cpp): the scenarios of
                             tests/DataAllocationTest.cpp:62-323 plus random alloc/free sequences.
+  bounding_sphere_ref.npz   (matrix, model-space sphere) pairs and the world-space spheres computed by the reference's
+                            own `operator*(const glm::mat4&, BoundingSphere)` (BoundingSphere.h:70-87 with the vendored
+                            GLM, oracle/ref_sphere_probe.cpp): pins the sphere transform of the culling extension.
 
 The committed vectors pin oracle/cadr_oracle.c (Tier R) and cadr_b200/host's allocator; the tests never need
 /root/reference.
@@ -141,9 +144,42 @@ def golden_allocator():
     print(f"{out}: {len(cases)} cases, {os.path.getsize(out) / 1024:.0f} KiB")
 
 
+def golden_bounding_spheres():
+    """Random affine transforms of the kinds CAD scenes hold (rotation x non-uniform scale + translation, pure
+    translations, mirrored and sheared ones, tiny and huge scales) and random spheres incl. empty ones."""
+    rng = np.random.default_rng(0xB5)
+    n = 4096
+    a = rng.normal(size=(n, 3, 3))
+    q, _ = np.linalg.qr(a)                                            # random rotations / reflections
+    scale = np.exp(rng.uniform(-3, 3, size=(n, 3)))                   # 0.05 .. 20 per axis
+    scale[: n // 8] = scale[: n // 8, :1]                             # uniform scales
+    lin = q * scale[:, None, :]
+    lin[n // 8: n // 4] = np.eye(3)                                   # pure translations (the boxes scenes)
+    lin[-n // 8:] += rng.normal(scale=0.3, size=(n // 8, 3, 3))       # shear
+    m = np.zeros((n, 4, 4), np.float32)                               # m[i, c, r]: column-major like glm::mat4
+    m[:, :3, :3] = np.transpose(lin, (0, 2, 1))
+    m[:, 3, :3] = rng.uniform(-2000, 2000, size=(n, 3))
+    m[:, 3, 3] = 1
+    spheres = np.concatenate([rng.uniform(-50, 50, size=(n, 3)), rng.uniform(0, 30, size=(n, 1))], axis=1).astype(np.float32)
+    spheres[::97, 3] = -np.inf                                        # BoundingSphere::empty()
+    spheres[5::97, :3] = 0                                            # centred spheres
+    rec = np.concatenate([m.reshape(n, 16), spheres], axis=1).astype(np.float32)
+    r = subprocess.run([os.path.join(REF, "sphere_probe")], input=rec.tobytes(), capture_output=True, check=True)
+    world = np.frombuffer(r.stdout, dtype=np.float32).reshape(n, 4)
+    out = os.path.join(GOLD, "bounding_sphere_ref.npz")
+    np.savez_compressed(out, matrices=m.reshape(n, 16), spheres=spheres, world=world,
+                        source="CadR::operator*(const glm::mat4&, BoundingSphere), src/CadR/BoundingSphere.h:70-87, via oracle/ref_sphere_probe.cpp (-O1 -ffp-contract=off)")
+    print(f"{out}: {n} pairs, {os.path.getsize(out) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     if not os.path.isdir(REF):
         raise SystemExit("oracle/_ref missing: run `make -C oracle ref` in the build container first")
-    golden_process_drawables()
-    golden_allocator()
+    only = sys.argv[1:]
+    if not only or "process_drawables" in only:
+        golden_process_drawables()
+    if not only or "allocator" in only:
+        golden_allocator()
+    if not only or "bounding_spheres" in only:
+        golden_bounding_spheres()
