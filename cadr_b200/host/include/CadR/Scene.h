@@ -151,28 +151,42 @@ public:
 };
 
 /// Parent/child lists of the StateSet DAG (src/CadR/ParentChildList.h): a StateSet may have several parents and
-/// is then recorded once per parent (StateSet.cpp:266-267).
+/// is then recorded once per parent (StateSet.cpp:266-267).  As in the reference, every append creates ONE relation
+/// object that sits in the parent's child list and in the child's parent list; removing it from either side removes
+/// exactly that relation from both (also when the same two StateSets are linked more than once), in O(1).
+struct StateSetLink {
+	StateSet* parent;
+	StateSet* child;
+	std::list<StateSetLink*>::iterator inChildList;    ///< position in parent->childList
+	std::list<StateSetLink*>::iterator inParentList;   ///< position in child->parentList
+};
+
 template<bool IsChildList> class StateSetLinkList {
 	friend class StateSet;
 	template<bool> friend class StateSetLinkList;
 	StateSet* _owner = nullptr;
-	std::list<StateSet*> _list;
+	std::list<StateSetLink*> _list;
+	static StateSet& other(const StateSetLink* l) { return IsChildList ? *l->child : *l->parent; }
 public:
-	using iterator = std::list<StateSet*>::iterator;
+	using iterator = std::list<StateSetLink*>::iterator;
 	struct deref_iterator {
-		std::list<StateSet*>::const_iterator it;
-		StateSet& operator*() const { return **it; }
+		std::list<StateSetLink*>::const_iterator it;
+		StateSet& operator*() const { return other(*it); }
+		StateSet* operator->() const { return &other(*it); }
 		deref_iterator& operator++() { ++it; return *this; }
+		deref_iterator& operator--() { --it; return *this; }
 		bool operator!=(const deref_iterator& o) const { return it != o.it; }
+		bool operator==(const deref_iterator& o) const { return it == o.it; }
 	};
 	deref_iterator begin() const { return {_list.begin()}; }
 	deref_iterator end() const { return {_list.end()}; }
 	size_t size() const { return _list.size(); }
 	bool empty() const { return _list.empty(); }
-	StateSet& front() const { return *_list.front(); }
-	StateSet& back() const { return *_list.back(); }
+	StateSet& front() const { return other(_list.front()); }
+	StateSet& back() const { return other(_list.back()); }
 	iterator append(StateSet& other);
 	void remove(iterator it);
+	void remove(deref_iterator it) { remove(_list.erase(it.it, it.it)); }   // the iterator begin() hands out, as in the reference
 	void clear() { while(!_list.empty()) remove(_list.begin()); }
 	~StateSetLinkList() { clear(); }
 };

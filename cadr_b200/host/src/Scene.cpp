@@ -178,33 +178,36 @@ StateSet::StateSet(Renderer& renderer) noexcept : _renderer(&renderer)
 	parentList._owner = this;
 }
 
+static StateSetLink* linkStateSets(StateSet& parent, std::list<StateSetLink*>& childListOfParent, StateSet& child, std::list<StateSetLink*>& parentListOfChild)
+{
+	// ParentChildList.h:113-120 / :172-179: the relation is appended to BOTH lists
+	StateSetLink* l = new StateSetLink{&parent, &child, {}, {}};
+	l->inChildList = childListOfParent.insert(childListOfParent.end(), l);
+	l->inParentList = parentListOfChild.insert(parentListOfChild.end(), l);
+	return l;
+}
+
 template<> StateSetLinkList<true>::iterator StateSetLinkList<true>::append(StateSet& child)
 {
-	_list.push_back(&child);
-	child.parentList._list.push_back(_owner);
-	return std::prev(_list.end());
+	return linkStateSets(*_owner, _list, child, child.parentList._list)->inChildList;
 }
 template<> void StateSetLinkList<true>::remove(iterator it)
 {
-	StateSet* child = *it;
-	auto& pl = child->parentList._list;
-	auto pit = std::find(pl.begin(), pl.end(), _owner);
-	if(pit != pl.end()) pl.erase(pit);
-	_list.erase(it);
+	StateSetLink* l = *it;
+	l->child->parentList._list.erase(l->inParentList);
+	_list.erase(l->inChildList);
+	delete l;
 }
 template<> StateSetLinkList<false>::iterator StateSetLinkList<false>::append(StateSet& parent)
 {
-	_list.push_back(&parent);
-	parent.childList._list.push_back(_owner);
-	return std::prev(_list.end());
+	return linkStateSets(parent, parent.childList._list, *_owner, _list)->inParentList;
 }
 template<> void StateSetLinkList<false>::remove(iterator it)
 {
-	StateSet* parent = *it;
-	auto& cl = parent->childList._list;
-	auto cit = std::find(cl.begin(), cl.end(), _owner);
-	if(cit != cl.end()) cl.erase(cit);
-	_list.erase(it);
+	StateSetLink* l = *it;
+	l->parent->childList._list.erase(l->inChildList);
+	_list.erase(l->inParentList);
+	delete l;
 }
 
 void StateSet::appendDrawableInternal(Drawable& d, const DrawableGpuData& gpuData)

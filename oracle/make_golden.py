@@ -9,6 +9,10 @@
   allocator_kat.json.gz     command streams and the placements chosen by the reference's own
                             CircularAllocationMemory.h (oracle/ref_alloc_probe.cpp): the scenarios of
                             tests/DataAllocationTest.cpp:62-323 plus random alloc/free sequences.
+  parent_child_kat.json.gz  command streams over StateSet-like nodes and the child / parent orders the reference's own
+                            ParentChildList.h leaves behind (oracle/ref_parent_child_probe.cpp): the scenario of
+                            tests/ParentChildTest.cpp:12-38, repeated links between the same two nodes, removal from
+                            either side, clears, and random streams.
   bounding_sphere_ref.npz   (matrix, model-space sphere) pairs and the world-space spheres computed by the reference's
                             own `operator*(const glm::mat4&, BoundingSphere)` (BoundingSphere.h:70-87 with the vendored
                             GLM, oracle/ref_sphere_probe.cpp): pins the sphere transform of the culling extension.
@@ -144,6 +148,68 @@ def golden_allocator():
     print(f"{out}: {len(cases)} cases, {os.path.getsize(out) / 1024:.0f} KiB")
 
 
+def golden_parent_child():
+    import random
+    cases = []
+
+    def add(name, nodes, cmds):
+        text = f"{nodes}\n" + "\n".join(" ".join(str(x) for x in c) + "\ns" for c in cmds) + "\n"
+        r = subprocess.run([os.path.join(REF, "parent_child_probe")], input=text, capture_output=True, text=True, check=True)
+        states = r.stdout.strip("\n").split("\n")
+        assert len(states) == len(cmds)
+        cases.append(dict(name=name, nodes=nodes, cmds=[list(c) for c in cmds], states=[s.strip() for s in states]))
+
+    # tests/ParentChildTest.cpp:12-38
+    add("reference_test", 3, [("ac", 0, 1), ("rc", 0, 0), ("cc", 0), ("ap", 1, 0), ("rp", 1, 0), ("cp", 1)])
+    # the same child twice under one parent, another parent in between; every removal position from either side
+    dup = [("ac", 0, 2), ("ac", 1, 2), ("ac", 0, 3), ("ac", 0, 2), ("ap", 2, 1)]
+    for k in range(3):
+        add(f"duplicate_links_remove_child_{k}", 4, dup + [("rc", 0, k)])
+    for k in range(4):
+        add(f"duplicate_links_remove_parent_{k}", 4, dup + [("rp", 2, k)])
+    add("clear_child_list_with_duplicates", 4, dup + [("cc", 0)])
+    add("clear_parent_list_with_duplicates", 4, dup + [("cp", 2)])
+    rng = random.Random(0x5C)
+    for case in range(120):
+        nodes = rng.randint(2, 7)
+        cmds = []
+        for _ in range(rng.randint(10, 60)):
+            op = rng.choice(["ac", "ac", "ap", "ap", "rc", "rp", "cc", "cp"] if case % 3 else ["ac", "ap", "rc", "rp"])
+            a = rng.randrange(nodes)
+            if op in ("ac", "ap"):
+                b = rng.randrange(nodes)
+                if a == b:
+                    continue                               # a StateSet is never its own child
+                cmds.append((op, a, b))
+            elif op == "rc":
+                cmds.append(("rc?", a))
+            elif op == "rp":
+                cmds.append(("rp?", a))
+            else:
+                cmds.append((op, a))
+        # resolve the removal positions against the real list lengths by replaying with the probe
+        resolved = []
+        for c in cmds:
+            if c[0] in ("rc?", "rp?"):
+                text = f"{nodes}\n" + "\n".join(" ".join(str(x) for x in r) for r in resolved) + "\ns\n"
+                out = subprocess.run([os.path.join(REF, "parent_child_probe")], input=text, capture_output=True, text=True, check=True).stdout
+                entry = out.split()[c[1]]
+                lst = entry.split(":")[1].split(";")[0 if c[0] == "rc?" else 1].split("=")[1]
+                n = len([x for x in lst.split(",") if x])
+                if n == 0:
+                    continue
+                resolved.append((c[0][:2], c[1], rng.randrange(n)))
+            else:
+                resolved.append(c)
+        if resolved:
+            add(f"random_{case}", nodes, resolved)
+    out = os.path.join(GOLD, "parent_child_kat.json.gz")
+    with gzip.open(out, "wt") as f:
+        json.dump(dict(source="CadR::ChildList / ParentList (src/CadR/ParentChildList.h) via oracle/ref_parent_child_probe.cpp", cases=cases), f,
+                  separators=(",", ":"))
+    print(f"{out}: {len(cases)} cases, {sum(len(c['cmds']) for c in cases)} commands, {os.path.getsize(out) / 1024:.0f} KiB")
+
+
 def golden_bounding_spheres():
     """Random affine transforms of the kinds CAD scenes hold (rotation x non-uniform scale + translation, pure
     translations, mirrored and sheared ones, tiny and huge scales) and random spheres incl. empty ones."""
@@ -181,5 +247,7 @@ if __name__ == "__main__":
         golden_process_drawables()
     if not only or "allocator" in only:
         golden_allocator()
+    if not only or "parent_child" in only:
+        golden_parent_child()
     if not only or "bounding_spheres" in only:
         golden_bounding_spheres()
