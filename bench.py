@@ -575,7 +575,7 @@ def run_b200(args):
         line["exchange"] = ("fused: cull kernels store records into every rank's gathered arrays over NVLink peer mappings (no collective call)"
                             if px is not None else f"NCCL all_gather_into_tensor of {ex.bytes_per_rank} padded bytes per rank after the cull")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, desc, threads, _ = cpu_sample_run(args, 40, 2)
+        v, desc, threads, _ = cpu_sample_run(args, 300, 2)      # ~5 s of all host cores (about 75 core-seconds on a 16-core box)
         line["cpu_baseline"] = {"value": round(v / 1e6, 3), "unit": "M instances/s", "cores": threads, "kind": "port", "sample": desc}
     if rank == 0:
         print(json.dumps(line))
