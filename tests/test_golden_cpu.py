@@ -107,3 +107,14 @@ def test_plane_decisions_on_reference_spheres_differ_only_within_rounding():
         differing += int(flip.sum()); total += len(flip)
         assert 0.02 < (sr >= 0).mean() < 0.98                                               # the camera culls some, keeps some
     assert differing <= total // 1000
+
+
+def test_reference_struct_layouts_match_the_abi():
+    """oracle/_ref/layout_check exists only if its static_asserts held when it was compiled against the reference's own
+    PrimitiveSet.h / BoundingSphere.h / GLM (oracle/ref_layout_check.cpp, `make -C oracle ref`)."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "layout_check")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "layout_check ok" in r.stdout
