@@ -3,7 +3,10 @@
   partition()   cut the flattened drawable list into `world` contiguous slices balanced by INSTANCE count, at drawable
                 boundaries only; StateSet ranges are contiguous in flatten order (StateSet.cpp:233-264), so
                 concatenating per-rank outputs in rank order keeps every StateSet's commands contiguous per rank.
-  Exchange      the one real exchange step: all-gather of every rank's compacted command list (commands, forwarded
+  TierRGather   the fixed-size records of the processing pass (IndirectData 16 B, DrawablePointers 32 B per drawable):
+                every rank's slice lands at its global drawable index in one array on every rank, i.e. exactly the
+                arrays a single GPU would have written for the whole list (the pointers are addresses of the owning GPU).
+  Exchange      the one real exchange step of the culling pass: all-gather of every rank's compacted command list (commands, forwarded
                 pointers, tags) and per-range counters into one buffer on every rank, plus a directory
                 {rank, range} -> (command offset, count) a renderer walks.  Instance-index lists stay on the owning GPU
                 (gathering 4 B per survivor costs more NVLink time than the cull itself at p ~ 0.5).
@@ -35,6 +38,53 @@ def partition(instance_counts: np.ndarray, world: int) -> list[tuple[int, int]]:
         cuts.append(max(k, cuts[-1]))
     cuts.append(n)
     return [(cuts[r], cuts[r + 1] - cuts[r]) for r in range(world)]
+
+
+class TierRGather:
+    """Gathers the per-drawable Tier R records of all ranks into whole-scene arrays ("Tier R (fixed-size
+    records)").  Slices are contiguous in flatten order and of different lengths, so rank r's records are broadcast
+    straight into rows [first_r, first_r + count_r) of the result: no padding, no re-packing, and the result is
+    bit-identical to a single-GPU pass over the whole list.  `slices` = partition(...) of the global list."""
+
+    def __init__(self, slices: list[tuple[int, int]], device: torch.device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if len(slices) != self.world:
+            raise ValueError("TierRGather: one slice per rank expected")
+        first = 0
+        for f, c in slices:
+            if f != first or c < 0:
+                raise ValueError("TierRGather: slices must be contiguous and start at 0")
+            first += c
+        self.slices = [(int(f), int(c)) for f, c in slices]
+        self.n = first
+        self.indirect = torch.zeros(self.n * 16, dtype=torch.uint8, device=device)     # cadr_indirect_data[n]
+        self.pointers = torch.zeros(self.n * 32, dtype=torch.uint8, device=device)     # cadr_drawable_pointers[n]
+
+    def run(self, indirect: torch.Tensor, pointers: torch.Tensor) -> None:
+        """`indirect` / `pointers`: this rank's uint8 views of its slice's records (count_r * 16 / * 32 bytes)."""
+        f, c = self.slices[self.rank]
+        if indirect.numel() < c * 16 or pointers.numel() < c * 32:
+            raise ValueError("TierRGather: this rank's record arrays are shorter than its slice")
+        self.indirect[f * 16:(f + c) * 16].copy_(indirect[:c * 16])
+        self.pointers[f * 32:(f + c) * 32].copy_(pointers[:c * 32])
+        for r, (rf, rc) in enumerate(self.slices):
+            if rc == 0:
+                continue
+            src = dist.get_global_rank(self.group, r) if self.group is not None else r
+            dist.broadcast(self.indirect[rf * 16:(rf + rc) * 16], src=src, group=self.group)
+            dist.broadcast(self.pointers[rf * 32:(rf + rc) * 32], src=src, group=self.group)
+
+    def records(self) -> tuple[np.ndarray, np.ndarray]:
+        """-> (indirect [n,4] u32, pointers [n,4] u64) on the host; `owner(i)` tells whose addresses row i holds."""
+        return (self.indirect.cpu().numpy().view(np.uint32).reshape(-1, 4), self.pointers.cpu().numpy().view(np.uint64).reshape(-1, 4))
+
+    def owner(self, drawable: int) -> int:
+        for r, (f, c) in enumerate(self.slices):
+            if f <= drawable < f + c:
+                return r
+        raise IndexError(drawable)
 
 
 class Exchange:

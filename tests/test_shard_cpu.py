@@ -99,3 +99,56 @@ def test_exchange_world_size_2_gloo():
     status, nbytes = q.get(timeout=5)
     assert status == "ok", status
     assert nbytes > 0
+
+
+def _tier_r_worker(rank, world, port, q):
+    from helpers import oracle_tier_r
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sc = synth.random_scene(78, n=700, num_lists=90, max_count=40, state_sets=5, first_handle=1990)
+        counts = sc.ml_count[sc.drawable_ml]
+        slices = shard.partition(counts, world)
+        first, count = slices[rank]
+        _, ind, ptr = oracle_tier_r(_shard_scene(sc, first, count))      # this rank's slice (stand-in for its GPU pass)
+        g = shard.TierRGather(slices, torch.device("cpu"))
+        g.run(torch.from_numpy(np.ascontiguousarray(ind).view(np.uint8).reshape(-1)), torch.from_numpy(np.ascontiguousarray(ptr).view(np.uint8).reshape(-1)))
+        got_ind, got_ptr = g.records()
+        _, whole_ind, whole_ptr = oracle_tier_r(sc)
+        ok = np.array_equal(got_ind, whole_ind) and np.array_equal(got_ptr, whole_ptr) and g.n == sc.n
+        ok = ok and [g.owner(f) for f, c in slices if c] == [r for r, (f, c) in enumerate(slices) if c]
+        q.put((rank, "ok" if ok else "mismatch"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_tier_r_gather_equals_single_pass_gloo(world):
+    """Every rank resolves its slice of the drawable list; after TierRGather every rank holds the indirect / pointers
+    arrays of the WHOLE list, bit-identical to one pass over it (slices of unequal length, no padding)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tier_r_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=5) for _ in range(world))
+    assert got == [(r, "ok") for r in range(world)]
+
+
+def test_tier_r_gather_rejects_bad_slices():
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()))
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        with pytest.raises(ValueError):
+            shard.TierRGather([(0, 5), (6, 2)], torch.device("cpu"))          # two slices for one rank
+        with pytest.raises(ValueError):
+            shard.TierRGather([(1, 5)], torch.device("cpu"))                  # does not start at 0
+        g = shard.TierRGather([(0, 3)], torch.device("cpu"))
+        with pytest.raises(ValueError):
+            g.run(torch.zeros(16, dtype=torch.uint8), torch.zeros(96, dtype=torch.uint8))   # indirect too short
+    finally:
+        dist.destroy_process_group()
