@@ -25,7 +25,7 @@ int main()
 		}
 		else if(c == 'f') {
 			auto it = live.find(id);
-			if(it == live.end()) return 2;
+			if(it == live.end()) { printf("f %ld -1\n", id); continue; }   // the allocation had failed: nothing to free
 			ring.release(it->second);
 			live.erase(it);
 			printf("f %ld %llu\n", id, (unsigned long long)ring.usedBytes());
