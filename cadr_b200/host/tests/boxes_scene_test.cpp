@@ -196,6 +196,7 @@ int main(int argc, char** argv)
 		const float maxSize = 1080.f * 0.9f;
 		Scene s(r, root, Grid{side, side > 1 ? side - 1 : 1, side > 2 ? side - 2 : 1, maxSize / float(side), maxSize / float(2 * side)});
 		s.track = !timingOnly;
+		if(timingOnly && r.hasDevice()) r.setCollectFrameInfo(true);   // per-kernel CUDA events of the library (FrameInfo)
 
 		for(int frame = 0; frame < frames; frame++) {
 			const auto t0 = now();
@@ -237,6 +238,8 @@ int main(int argc, char** argv)
 				const auto t3 = now();
 				fprintf(stderr, "frame %d: %zu drawables, handle level %u | scene update %.2f ms, upload recording %.2f ms, frame recording %.2f ms, list upload %zu bytes\n",
 				        frame, n, r.dataStorage().handleLevel(), ms(t0, t1), ms(t1, t2), ms(t2, t3), r.lastDrawableUploadBytes());
+				if(r.hasDevice())     // the reference application's "gpu drawable processing" column (main.cpp:1717), here incl. culling
+					fprintf(stderr, "         gpu drawable processing + culling %.4f ms\n", double(r.getFrameInfo().gpuEndExecution));
 				continue;
 			}
 
