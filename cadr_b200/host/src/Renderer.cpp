@@ -1,5 +1,6 @@
 // Renderer of the facade: frame API over the C ABI.  See CadR/Renderer.h for the mapping to the reference.
 #include <CadR/CadR.h>
+#include <thread>
 #include "../../../include/cadr_b200.h"
 #include <chrono>
 #include <cstring>
@@ -152,10 +153,25 @@ void Renderer::recordStateSetRange(StateSet& ss, size_t first)
 	const bool resident = _incrementalList && _residentValid && pl.first == first && pl.range == rangeIndex && pl.modCount == ss._modCount;
 	if(!resident) {
 		// copy the StateSet's records into the staging list (StateSet.cpp:233-237)
-		std::memcpy(&_drawableStagingData[first], ss._drawableDataList.data(), n * sizeof(DrawableGpuData));
-		DrawableCullData* c = &_cullStagingData[first];
-		std::memcpy(c, ss._drawableCullList.data(), n * sizeof(DrawableCullData));
-		for(size_t i = 0; i < n; i++) c[i].stateSetIndex = rangeIndex;
+		// (one core moves ~7 GB/s: at 10 M drawables the two copies take 145 ms, more than the PCIe transfer that
+		// follows; large ranges are therefore cut into slices copied by several threads)
+		auto copySlice = [&](size_t b, size_t e) {
+			std::memcpy(&_drawableStagingData[first + b], ss._drawableDataList.data() + b, (e - b) * sizeof(DrawableGpuData));
+			DrawableCullData* c = &_cullStagingData[first + b];
+			std::memcpy(c, ss._drawableCullList.data() + b, (e - b) * sizeof(DrawableCullData));
+			for(size_t i = 0; i < e - b; i++) c[i].stateSetIndex = rangeIndex;
+		};
+		constexpr size_t sliceMin = size_t(1) << 17;     // 128 Ki records = 12 MiB per slice at least
+		const size_t threads = std::min<size_t>({n / sliceMin, size_t(std::max(1u, std::thread::hardware_concurrency())), size_t(16)});
+		if(threads < 2) copySlice(0, n);
+		else {
+			std::vector<std::thread> pool;
+			pool.reserve(threads - 1);
+			const size_t per = (n + threads - 1) / threads;
+			for(size_t t = 1; t < threads; t++) pool.emplace_back(copySlice, std::min(n, t * per), std::min(n, (t + 1) * per));
+			copySlice(0, std::min(n, per));
+			for(std::thread& t : pool) t.join();
+		}
 		if(!_dirtyRanges.empty() && _dirtyRanges.back().first + _dirtyRanges.back().second == first) _dirtyRanges.back().second += n;
 		else _dirtyRanges.emplace_back(first, n);
 		pl = StateSet::Placement{first, rangeIndex, ss._modCount};
