@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cadr_b200  # noqa: E402
 from cadr_b200 import shard, synth  # noqa: E402
 from cadr_b200.frame import DeviceScene  # noqa: E402
-from helpers import oracle_tier_x  # noqa: E402
+from helpers import oracle_tier_r, oracle_tier_x  # noqa: E402
 
 
 def main():
@@ -72,6 +72,21 @@ def main():
                 ok = False
                 print(f"rank {rank}: commands of rank {r} differ in frame {frame} ({len(got)} vs {len(exp)})")
         dist.barrier()
+    if os.environ.get("MG_TIER_R") == "1":
+        # opt-in until it has run on NCCL once: the fixed-size Tier R records of every rank's slice gathered into whole-list
+        # arrays (shard.TierRGather); here every rank's "slice" is its own scene, the oracle resolves each of them
+        slices, first = [], 0
+        for r in range(world):
+            slices.append((first, scenes[r].n)); first += scenes[r].n
+        ind, ptr = ds.read_tier_r()
+        tg = shard.TierRGather(slices, torch.device("cuda", local))
+        tg.run(torch.from_numpy(np.ascontiguousarray(ind).view(np.uint8).reshape(-1)).cuda(), torch.from_numpy(np.ascontiguousarray(ptr).view(np.uint8).reshape(-1)).cuda())
+        g_ind, g_ptr = tg.records()
+        for r, (f0, c) in enumerate(slices):
+            _, e_ind, e_ptr = oracle_tier_r(scenes[r], arena_base=bases[r][0], list_base=bases[r][1])
+            if not (np.array_equal(g_ind[f0:f0 + c], e_ind) and np.array_equal(g_ptr[f0:f0 + c], e_ptr)):
+                ok = False
+                print(f"rank {rank}: gathered Tier R records of rank {r} differ")
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     px.close()
