@@ -484,7 +484,7 @@ def run_b200(args):
             tier_r.append(ctx.kernel_times()[0])
         ctx.set_profiling(False)
 
-    large_name = {"0": "cullLargeLdgKernel", "1": "cullLargeKernel", "3": "cullListRingKernel"}.get(os.environ.get("CADR_B200_CULL_VARIANT", "2"), "cullListWarpKernel")
+    large_name = "cullListWarpKernel"
     kt = np.array(ktimes)
     k_process, k_small, k_large = (float(kt[:, i].mean()) for i in range(3))
     p = float(np.mean(surv)) / inst

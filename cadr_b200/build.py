@@ -16,7 +16,10 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--cudart", "static", "-shared",
 ]
-CUDA_SOURCES = ["capi.cu", "process_drawables.cu", "cull_compact.cu", "cull_variants.cu", "cull_bounds.cu", "upload.cu", "exchange.cu", "consume_check.cu", "external.cu"]
+CUDA_SOURCES = ["capi.cu", "process_drawables.cu", "cull_compact.cu", "cull_bounds.cu", "upload.cu", "exchange.cu", "consume_check.cu", "external.cu"]
+# A/B build only (libcadr_b200_exp.so, -DCADR_B200_EXPERIMENTS): earlier / alternative long-list kernels selectable through
+# CADR_B200_CULL_VARIANT, evaluation stub CADR_B200_DIAG_NOEVAL.  Never part of libcadr_b200.so.
+EXPERIMENT_SOURCES = ["experiments/cull_variants.cu"]
 
 
 def _run(cmd, **kw):
@@ -41,14 +44,15 @@ def nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def build_cuda(force: bool = False, verbose: bool = False) -> str:
-    """libcadr_b200.so: every CUDA kernel + the C ABI, sm_100a only."""
+def build_cuda(force: bool = False, verbose: bool = False, experiments: bool = False) -> str:
+    """libcadr_b200.so: every CUDA kernel + the C ABI, sm_100a only.  experiments=True builds the A/B library
+    libcadr_b200_exp.so instead (same ABI + the experiment kernels; used by scripts/, never by tests or bench.py)."""
     os.makedirs(LIBDIR, exist_ok=True)
-    out = os.path.join(LIBDIR, "libcadr_b200.so")
-    srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
+    out = os.path.join(LIBDIR, "libcadr_b200_exp.so" if experiments else "libcadr_b200.so")
+    srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES + (EXPERIMENT_SOURCES if experiments else [])]
     deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "cull_common.cuh"), os.path.join(ROOT, "include", "cadr_b200.h")]
     if force or _stale(out, deps):
-        flags = NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+        flags = NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DCADR_B200_EXPERIMENTS"] if experiments else [])
         log = _run([nvcc()] + flags + ["-o", out] + srcs)
         if verbose:
             print(log)
@@ -92,5 +96,8 @@ def build_all(force: bool = False, verbose: bool = False) -> None:
 
 
 if __name__ == "__main__":
+    if "--experiments" in sys.argv:
+        print("built:", build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv, experiments=True))
+        sys.exit(0)
     build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print("built:", os.path.join(LIBDIR, "libcadr_b200.so"))

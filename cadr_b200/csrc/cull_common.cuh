@@ -1,6 +1,7 @@
-// Definitions shared by the culling kernels (cull_compact.cu: the default path; cull_variants.cu: earlier versions of
-// the long-list stage kept for A/B measurements): work-item and argument layouts, matrix loads, the per-instance
-// evaluation (normative operation order, DESIGN.md "Tier X"), command-record emission.
+// Definitions shared by the culling kernels (cull_compact.cu: the product path; experiments/: earlier and alternative
+// versions of the long-list stage, compiled only with -DCADR_B200_EXPERIMENTS into libcadr_b200_exp.so for A/B
+// measurements): work-item and argument layouts, matrix loads, the per-instance evaluation (normative operation order,
+// DESIGN.md "Tier X"), command-record emission.
 #pragma once
 
 #include "common.cuh"
@@ -48,7 +49,9 @@ struct CullArgs {
 	uint32_t  n;
 	uint32_t  numStateSets;
 	uint32_t  medMax;                     // lists of SMALL_MAX < n <= medMax matrices go to the medium queue (0: there is none)
+#ifdef CADR_B200_EXPERIMENTS
 	uint32_t  diagNoEval;                 // CADR_B200_DIAG_NOEVAL=1: list kernels skip the evaluation (memory-system ceiling of the access structure)
+#endif
 	float4 plane[6];
 	float4 eye;
 	// fused multi-GPU exchange: gathered arrays of every rank (peer mappings), 0 ranks = write cmdOut/ptrOut/tagOut
@@ -231,7 +234,15 @@ __device__ __forceinline__ void writeCommandRecord(const CullArgs& A, uint32_t c
 	A.tagOut[ci] = make_uint2(d, lod);
 }
 
-// long-list stage, variants 0 (CTA per item, direct loads) and 1 (CTA-wide TMA pipeline); cull_variants.cu
+#ifdef CADR_B200_EXPERIMENTS
+// experiments build only: the evaluation can be stubbed out to measure the memory-system ceiling of an access structure
+#define CADR_DIAG_NOEVAL(A, m) (A).diagNoEval ? (((m).c0.x == 12345.f && (m).c2.x == 1.f) ? 0 : -1) :
+// long-list stage, variants 0 (CTA per item, direct loads) and 1 (CTA-wide TMA pipeline); experiments/cull_variants.cu
 int launchCullVariant(cadr_ctx* ctx, const CullArgs& A, int variant, uint32_t chunkCapacity, cudaStream_t s);
+// variant 3 (warp-private shared-memory ring); experiments/cull_ring.cu
+int launchCullRing(cadr_ctx* ctx, const CullArgs& A, uint32_t chunkCapacity, cudaStream_t s);
+#else
+#define CADR_DIAG_NOEVAL(A, m)
+#endif
 
 }  // namespace cadr

@@ -32,7 +32,9 @@
 // overhead / N.
 
 #include "cull_common.cuh"
+#ifdef CADR_B200_EXPERIMENTS
 #include <cstdlib>
+#endif
 
 namespace cadr {
 
@@ -153,7 +155,9 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 		const uint64_t psBase = FUSED ? psBaseResolved : primitiveSetBase<LEVEL>(A, d);
 #pragma unroll
 		for(int l = 0; l < 3; l++)
-			if(uint32_t(l) < L.lodCount) { const uint2 v = ldg_u2(psBase + psOff[l]); ps[l][0] = v.x; ps[l][1] = v.y; }
+			// two 4-byte loads: PrimitiveSetRef is declared buffer_reference_align = 4 (processDrawables.comp:29-33), so a
+			// primitiveSetOffset that is a multiple of 4 but not of 8 is legal
+			if(uint32_t(l) < L.lodCount) { ps[l][0] = ldg_u32(psBase + psOff[l]); ps[l][1] = ldg_u32(psBase + psOff[l] + 4); }
 	}
 	const unsigned medBallot = __ballot_sync(0xffffffffu, isMed);
 	if(lane == 0) sMedTot[warp] = __popc(medBallot);
@@ -536,7 +540,7 @@ __device__ __forceinline__ void cullMediumBatches(const CullArgs& A, const uint3
 				L.sphere = make_float4(__uint_as_float(a2.x), __uint_as_float(a2.y), __uint_as_float(a2.z), __uint_as_float(a2.w));
 				L.thr0 = __uint_as_float(a3.x); L.thr1 = __uint_as_float(a3.y);
 				bool nbi = false;
-				const int lod = A.diagNoEval ? ((cur.c0.x == 12345.f && cur.c2.x == 1.f) ? 0 : -1) : evalInstance(cur, L, A.plane, A.eye, nbi);
+				const int lod = CADR_DIAG_NOEVAL(A, cur) evalInstance(cur, L, A.plane, A.eye, nbi);
 				nb += nbi ? 1u : 0u;
 				code = uint32_t(lod + 1);
 			}
@@ -633,10 +637,10 @@ __device__ __forceinline__ void queueExtents(const CullArgs& A, uint32_t& totalL
 }
 
 // The medium items as a kernel of their own (default).  It is launched right behind cullListWarpKernel as a
-// programmatic dependent launch and does not wait for it (the two consume disjoint queues and share only the atomic
-// output counters): its CTAs move in as the long-item CTAs retire, and when there are no medium items they leave at once,
-// so a frame without medium lists pays neither a launch gap nor - unlike with the batches appended to
-// cullListWarpKernel (variant 5) - a larger shared-memory carve-out: that kernel streams C3 1 % slower under any
+// programmatic dependent launch and does not wait for it BEFORE working (the two consume disjoint queues and share only
+// the atomic output counters): its CTAs move in as the long-item CTAs retire; it waits for the primary at its END (see
+// below).  A frame without medium lists pays neither a launch gap nor - unlike with the batches appended to
+// cullListWarpKernel (experiment variant 5) - a larger shared-memory carve-out: that kernel streams C3 1 % slower under any
 // carve-out above its own 4 KiB per CTA (measured with an unused dynamic allocation of 4 .. 32 KiB).
 __global__ void __launch_bounds__(CM_THREADS, 4)
 cullMediumKernel(const __grid_constant__ CullArgs A)
@@ -646,6 +650,13 @@ cullMediumKernel(const __grid_constant__ CullArgs A)
 	bool overflow;
 	queueExtents(A, totalL, totalM, overflow);
 	if(totalM) cullMediumBatches(A, smemAddr(sDescs[threadIdx.x >> 5]), threadIdx.x & 31, totalM);
+	// PTX ISA, griddepcontrol: a grid launched as a programmatic dependent must execute griddepcontrol.wait before its
+	// completion can stand for the completion (and memory visibility) of the primary grid.  This grid needs nothing from
+	// the primary (disjoint queues), so the wait sits at the END: the overlap is kept, and "cullMediumKernel finished"
+	// again implies "cullListWarpKernel finished" for whatever follows on the stream (the next frame's counters memset,
+	// the counters D2H, publishKernel raising the peers' frame flag).  It costs nothing: this grid's CTAs only become
+	// resident as primary CTAs retire (both kernels fill the register file at four CTAs per SM).
+	asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 constexpr int LW_DESCS = 4;     // descriptor ring per warp: items A, B, C and the slot being refilled
@@ -718,7 +729,7 @@ cullListWarpKernel(const __grid_constant__ CullArgs A)
 		while(left > 32u) {                // full steps that have a successor inside A
 			if(lane + 32u < left) nxt = loadMat(p + 2048);
 			bool nbi = false;
-			const int lod = A.diagNoEval ? ((cur.c0.x == 12345.f && cur.c2.x == 1.f) ? 0 : -1) : evalInstance(cur, L, A.plane, A.eye, nbi);
+			const int lod = CADR_DIAG_NOEVAL(A, cur) evalInstance(cur, L, A.plane, A.eye, nbi);
 			nb += nbi ? 1u : 0u;
 			hist = (hist >> 2) | ((unsigned long long)uint32_t(lod + 1) << 62);
 			steps++;
@@ -729,7 +740,7 @@ cullListWarpKernel(const __grid_constant__ CullArgs A)
 			uint32_t code = 0;
 			if(lane < left) {
 				bool nbi = false;
-				const int lod = A.diagNoEval ? ((cur.c0.x == 12345.f && cur.c2.x == 1.f) ? 0 : -1) : evalInstance(cur, L, A.plane, A.eye, nbi);
+				const int lod = CADR_DIAG_NOEVAL(A, cur) evalInstance(cur, L, A.plane, A.eye, nbi);
 				nb += nbi ? 1u : 0u;
 				code = uint32_t(lod + 1);
 			}
@@ -751,6 +762,7 @@ cullListWarpKernel(const __grid_constant__ CullArgs A)
 	}
 }
 
+#ifdef CADR_B200_EXPERIMENTS
 // ---------------------------------------------------------------------------------------------------
 // the same stage with a warp-private shared-memory ring: matrices are staged by asynchronous copies
 // ---------------------------------------------------------------------------------------------------
@@ -890,7 +902,7 @@ cullListRingKernel(const __grid_constant__ CullArgs A)
 				Mat m;
 				m.c0 = ldsF4(ma); m.c1 = ldsF4(ma ^ 16u); m.c2 = ldsF4(ma ^ 32u); m.c3 = ldsF4(ma ^ 48u);
 				bool nbi = false;
-				const int lod = A.diagNoEval ? ((m.c0.x == 12345.f && m.c2.x == 1.f) ? 0 : -1) : evalInstance(m, L, A.plane, A.eye, nbi);
+				const int lod = CADR_DIAG_NOEVAL(A, m) evalInstance(m, L, A.plane, A.eye, nbi);
 				code = uint32_t(lod + 1);
 				nb += nbi ? 1u : 0u;
 			}
@@ -911,6 +923,11 @@ cullListRingKernel(const __grid_constant__ CullArgs A)
 	}
 }
 
+#endif  // CADR_B200_EXPERIMENTS
+
+// The product library has ONE path (cullSmallKernel -> cullListWarpKernel -> cullMediumKernel) and reads no environment.
+// The A/B build (-DCADR_B200_EXPERIMENTS, libcadr_b200_exp.so, scripts/ab_list_kernels.py) can select earlier versions.
+#ifdef CADR_B200_EXPERIMENTS
 static int cullVariant()
 {
 	const char* v = std::getenv("CADR_B200_CULL_VARIANT");
@@ -918,6 +935,9 @@ static int cullVariant()
 	                               // cullListWarpKernel; 4 = no medium queue; 3 = warp per item, shared-memory ring;
 	                               // 1 = CTA-wide TMA pipeline; 0 = first direct-load version
 }
+#else
+static constexpr int cullVariant() { return 2; }
+#endif
 
 int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, bool fused)
 {
@@ -972,7 +992,9 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 	A.numStateSets = p.numStateSets;
 	for(int k = 0; k < 6; k++) A.plane[k] = make_float4(p.planes[k][0], p.planes[k][1], p.planes[k][2], p.planes[k][3]);
 	A.eye = make_float4(p.eye[0], p.eye[1], p.eye[2], 0.f);
+#ifdef CADR_B200_EXPERIMENTS
 	{ const char* dg = std::getenv("CADR_B200_DIAG_NOEVAL"); A.diagNoEval = (dg && dg[0] == '1') ? 1u : 0u; }
+#endif
 	A.xWorld = exchange ? p.exchangeWorld : 0;
 	A.xSlotBase = exchange ? p.exchangeRank * p.exchangeCmdCapacity : 0;
 	for(uint32_t r = 0; r < CADR_MAX_PEERS; r++) {
@@ -1009,37 +1031,37 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 
 	if(p.chunkCapacity) {
 		ctx->timeBegin(KS_CULL_LARGE, s);
+		uint32_t gridL = uint32_t(ctx->smCount) * 4u;   // persistent warps: four CTAs of eight warps per SM
+		const uint32_t need = (p.chunkCapacity + CM_THREADS / 32 - 1) / (CM_THREADS / 32);
+		if(gridL > need) gridL = need;
+#ifdef CADR_B200_EXPERIMENTS
 		if(variant == 3) {
 			if(!ctx->ringKernelConfigured) {   // per device (a process may hold one context per GPU)
 				CADR_CUDA(cudaFuncSetAttribute(cullListRingKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LW_SMEM_BYTES)));
 				ctx->ringKernelConfigured = true;
 			}
-			uint32_t gridL = uint32_t(ctx->smCount) * 4u;   // persistent warps: four CTAs of eight warps (52 KiB of rings each) per SM
-			const uint32_t need = (p.chunkCapacity + CM_THREADS / 32 - 1) / (CM_THREADS / 32);
-			if(gridL > need) gridL = need;
 			cullListRingKernel<<<gridL, CM_THREADS, LW_SMEM_BYTES, s>>>(A);
 		}
 		else if(variant == 0 || variant == 1) {
 			if(int r = launchCullVariant(ctx, A, variant, p.chunkCapacity, s)) return r;
 		}
-		else {
-			uint32_t gridL = uint32_t(ctx->smCount) * 4u;   // persistent warps: four CTAs of eight warps per SM
-			const uint32_t need = (p.chunkCapacity + CM_THREADS / 32 - 1) / (CM_THREADS / 32);
-			if(gridL > need) gridL = need;
-			if(variant == 5) cullListWarpKernel<true><<<gridL, CM_THREADS, 0, s>>>(A);
-			else {
-				cullListWarpKernel<false><<<gridL, CM_THREADS, 0, s>>>(A);
-				if(A.medMax) {
-					// programmatic dependent launch: may start while cullListWarpKernel is still running
-					cudaLaunchConfig_t cfg = {};
-					cfg.gridDim = dim3(gridL); cfg.blockDim = dim3(CM_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
-					cudaLaunchAttribute attr[1];
-					attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-					attr[0].val.programmaticStreamSerializationAllowed = 1;
-					cfg.attrs = attr; cfg.numAttrs = 1;
-					CADR_CUDA(cudaLaunchKernelEx(&cfg, cullMediumKernel, A));
-					ctx->launches++;
-				}
+		else if(variant == 5) cullListWarpKernel<true><<<gridL, CM_THREADS, 0, s>>>(A);
+		else
+#endif
+		{
+			cullListWarpKernel<false><<<gridL, CM_THREADS, 0, s>>>(A);
+			if(A.medMax) {
+				// programmatic dependent launch: its CTAs may move in while cullListWarpKernel is still running (the primary
+				// signals launch_dependents at entry); cullMediumKernel ends with griddepcontrol.wait, so its completion
+				// implies the primary's and stream order holds for everything queued behind it
+				cudaLaunchConfig_t cfg = {};
+				cfg.gridDim = dim3(gridL); cfg.blockDim = dim3(CM_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+				cudaLaunchAttribute attr[1];
+				attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+				attr[0].val.programmaticStreamSerializationAllowed = 1;
+				cfg.attrs = attr; cfg.numAttrs = 1;
+				CADR_CUDA(cudaLaunchKernelEx(&cfg, cullMediumKernel, A));
+				ctx->launches++;
 			}
 		}
 		ctx->timeEnd(KS_CULL_LARGE, s);

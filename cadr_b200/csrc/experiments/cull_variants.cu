@@ -1,7 +1,7 @@
 // Earlier versions of the long-list stage of the culling pass, kept selectable for A/B measurements
 // (CADR_B200_CULL_VARIANT=1: CTA-wide TMA pipeline, =0: CTA per item with direct loads).  The default path is
 // cullListWarpKernel in cull_compact.cu; DESIGN.md section 3 has the measured history.
-#include "cull_common.cuh"
+#include "../cull_common.cuh"
 
 namespace cadr {
 

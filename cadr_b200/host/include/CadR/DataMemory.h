@@ -26,9 +26,12 @@ class DataMemory {
 		StagingMemory* staging;
 		uint64_t stagingStart, stagingEnd;
 		DataAllocationRecord* pin;
-		int region;
+		int slot;                         // RingSuballocator::physicalIndex of the region the run lies in
 	};
-	std::vector<Run> _runs[2];            // pending runs of ring region 1 / 2, in creation order
+	// Pending runs and the last staging block per PHYSICAL ring region (RingSuballocator::physicalIndex), in creation
+	// order.  Keyed by identity, not by the role "region 1 | 2": the ring swaps the roles when region 1 empties, and a
+	// pending run has to stay with the addresses it covers.
+	std::vector<Run> _runs[2];
 	StagingMemory* _lastStaging[2] = {nullptr, nullptr};
 	Run& newRun(int region, uint64_t addr, size_t numBytes, StagingMemory* previous);
 public:

@@ -132,6 +132,10 @@ public:
 	}
 
 	int regionOf(const Record* rec) const { return rec->_region == _r1 ? 1 : 2; }
+	/// Identity (0 | 1) of the storage that currently plays the role of region 1 | 2.  The roles swap when region 1 empties
+	/// while region 2 holds data (reclaim), the identity of a stretch of addresses does not: state that has to follow the
+	/// ADDRESSES of a region across a swap (DataMemory's pending upload runs) is keyed by this, not by the role.
+	int physicalIndex(int region) const { return ((region == 1) ? _r1 : _r2) == &_a ? 0 : 1; }
 	size_t usedBytes() const { return _usedBytes; }
 	bool empty() const { return _a.records.empty() && _b.records.empty(); }
 	uint64_t bufferStart() const { return _bufferStart; }

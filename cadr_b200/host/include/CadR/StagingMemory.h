@@ -30,8 +30,12 @@ public:
 	size_t size() const { return _size; }
 	uint64_t hostStart() const { return reinterpret_cast<uint64_t>(_host); }
 	uint64_t hostEnd() const { return hostStart() + _size; }
-	/// Does the device range [addr, addr+bytes) fall outside this block under the current mapping?
-	bool addrRangeOverruns(uint64_t deviceAddr, size_t bytes) const { return uint64_t(int64_t(deviceAddr) + _deviceToStaging) + bytes > hostEnd(); }
+	/// Does the device range [addr, addr+bytes) fall outside this block under the current mapping?  Two-sided: a device
+	/// address below the start of the stretch a non-exclusive block mirrors maps in FRONT of the block.
+	bool addrRangeOverruns(uint64_t deviceAddr, size_t bytes) const {
+		const uint64_t s = uint64_t(int64_t(deviceAddr) + _deviceToStaging);
+		return s < hostStart() || s + bytes > hostEnd();
+	}
 };
 
 class StagingManager {

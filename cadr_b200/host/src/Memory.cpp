@@ -116,7 +116,7 @@ DataMemory* DataMemory::tryCreate(DataStorage& storage, size_t size)
 
 DataMemory::Run& DataMemory::newRun(int region, uint64_t addr, size_t numBytes, StagingMemory* previous)
 {
-	const int idx = region - 1;
+	const int idx = _ring.physicalIndex(region);
 	StagingMemory* other = _lastStaging[1 - idx];
 	StagingMemory* sm;
 	uint64_t stagingStart;
@@ -144,7 +144,7 @@ DataMemory::Run& DataMemory::newRun(int region, uint64_t addr, size_t numBytes, 
 	catch(...) { _ring.release(pin); throw; }
 	sm->_referenceCounter++;
 	_lastStaging[idx] = sm;
-	_runs[idx].push_back(Run{addr, sm, stagingStart, stagingStart, pin, region});
+	_runs[idx].push_back(Run{addr, sm, stagingStart, stagingStart, pin, idx});
 	return _runs[idx].back();
 }
 
@@ -152,19 +152,25 @@ DataAllocationRecord* DataMemory::alloc(size_t numBytes)
 {
 	auto [addr, region] = _ring.propose(numBytes);
 	if(region == 0) return nullptr;
-	const int idx = region - 1;
+	// runs and staging blocks belong to the physical region (the ring may have swapped the roles of its two regions since
+	// the pending run was opened: it stays with its addresses)
+	const int idx = _ring.physicalIndex(region);
 	StagingMemory* last = _lastStaging[idx];
 	Run* run = _runs[idx].empty() ? nullptr : &_runs[idx].back();
 	if(run) {
-		if(last->addrRangeOverruns(addr, numBytes))
-			run = &newRun(region, addr, numBytes, last);           // the block is full: continue in a bigger one
+		// a run is ONE copy region: it is continued only by an allocation that lies behind everything it holds
+		// (DataMemory.cpp:417-425 computes size = stagingEnd - stagingStart), inside the same staging block
+		const bool extends = run->staging == last && !last->addrRangeOverruns(addr, numBytes) &&
+		                     uint64_t(int64_t(addr) + last->_deviceToStaging) >= run->stagingEnd;
+		if(!extends)
+			run = &newRun(region, addr, numBytes, last->addrRangeOverruns(addr, numBytes) ? last : nullptr);   // block full: a bigger one
 	}
 	else if(last && !last->addrRangeOverruns(addr, numBytes)) {
 		// first allocation since the last transfer and the previous block still has room behind it
 		DataAllocationRecord* pin = _ring.pin(region, addr);
 		last->_referenceCounter++;
 		uint64_t s = uint64_t(int64_t(addr) + last->_deviceToStaging);
-		_runs[idx].push_back(Run{addr, last, s, s, pin, region});
+		_runs[idx].push_back(Run{addr, last, s, s, pin, idx});
 		run = &_runs[idx].back();
 	}
 	else

@@ -78,6 +78,12 @@ size_t Renderer::beginFrame()
 
 void Renderer::beginRecording()
 {
+	if(!_dirtyRanges.empty()) {
+		// the previous recording was never submitted (or submit() threw before its copies were queued): its ranges were
+		// noted as placed but never reached the device, and the staging they point into is about to be rewritten
+		_dirtyRanges.clear();
+		_residentValid = false;
+	}
 	_recordedDrawables = 0;
 	_processingRecorded = _cullingRecorded = false;
 	_drawRanges.clear();
@@ -109,6 +115,7 @@ size_t Renderer::prepareSceneRendering(StateSet& stateSetRoot)
 		_cullStagingData = static_cast<DrawableCullData*>(p);
 		_drawableCapacity = n;
 		_residentValid = false;      // new buffers: nothing is resident
+		_dirtyRanges.clear();        // ... and ranges noted against the old staging buffers mean nothing any more
 	}
 	return numDrawables;
 }
@@ -255,6 +262,7 @@ void Renderer::submit()
 	// staging -> device copy of the flattened list (Renderer.cpp:635-644) — only the ranges that changed since they
 	// were last copied; with incremental upload off, recordStateSetRange marked every range dirty
 	_lastListUploadBytes = 0;
+	_residentValid = false;              // until every copy below is queued (a throw leaves the list marked stale)
 	for(auto& [first, count] : _dirtyRanges) {
 		check(cadr_b200_memcpy_h2d(_ctx, _drawableBufferAddress + first * sizeof(DrawableGpuData), &_drawableStagingData[first],
 		                           count * sizeof(DrawableGpuData), _stream));
@@ -356,13 +364,13 @@ const FrameInfo& Renderer::getFrameInfo()
 {
 	if(_collectFrameInfo && _completed.frameNumber != _inProgress.frameNumber && hasDevice()) {
 		// drawable processing interval == ts[2] - ts[1] of the reference (main.cpp:1717)
-		float ms[6] = {};
-		check(cadr_b200_kernel_times(_ctx, ms, 6));
+		float ms[5] = {};               // KS_COUNT slots: process, cull small, cull list, scatter, patch
+		check(cadr_b200_kernel_times(_ctx, ms, 5));
 		_completed = _inProgress;
 		_completed.gpuBeginExecution = 0.f;
 		_completed.gpuAfterTransfersAndBeforeDrawableProcessing = 0.f;
 		_completed.gpuAfterDrawableProcessingAndBeforeRendering = ms[0];
-		_completed.gpuEndExecution = ms[0] + ms[1] + ms[2] + ms[5];
+		_completed.gpuEndExecution = ms[0] + ms[1] + ms[2];
 	}
 	return _completed;
 }

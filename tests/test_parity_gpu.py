@@ -117,15 +117,12 @@ BOUNDARY_COUNTS = [0, 1, 2, 31, 32, 33, 34, 63, 64, 65, 95, 96, 97, 127, 128, 12
                    1023, 1024, 1025, 2047, 2048, 2049, 3072]
 
 
-@pytest.mark.parametrize("variant", ["2", "5", "4", "3", "1", "0"],
-                         ids=["warp-per-item+medium-kernel", "warp-per-item+medium-batches", "warp-per-item-one-queue", "warp-ring",
-                              "tma-pipeline", "cta-per-item"])
 @pytest.mark.parametrize("fused", [False, True], ids=["two-calls", "fused"])
-def test_tier_x_list_length_boundaries(ctx, monkeypatch, variant, fused):
-    """Every hand-over point between the kernels: thread-per-list (<= 32 matrices), warp-per-list (33..512), work
-    items of 1024 (> 512), full and ragged last steps of 32, full and ragged last work items; for the three
-    long-list kernel variants."""
-    monkeypatch.setenv("CADR_B200_CULL_VARIANT", variant)
+def test_tier_x_list_length_boundaries(ctx, fused):
+    """Every hand-over point between the kernels: thread-per-list (<= 32 matrices), flat batches of medium lists
+    (33..64), warp-per-item (> 64), work items of 1024, full and ragged last steps of 32, full and ragged last work
+    items.  (The A/B kernels of csrc/experiments are not part of the product library; scripts/fuzz_parity.py runs
+    them from libcadr_b200_exp.so.)"""
     sc = synth.random_scene(51, n=4 * len(BOUNDARY_COUNTS) + 3, list_counts=BOUNDARY_COUNTS, state_sets=4, first_handle=2030)
     ds = DeviceScene(ctx, sc)
     try:
@@ -146,15 +143,13 @@ def test_tier_x_list_length_boundaries(ctx, monkeypatch, variant, fused):
         ds.close()
 
 
-@pytest.mark.parametrize("variant", ["2", "5"], ids=["medium-kernel", "medium-batches-in-list-kernel"])
 @pytest.mark.parametrize("fused", [False, True], ids=["two-calls", "fused"])
 @pytest.mark.parametrize("shape", ["all-medium", "mixed", "one-partial-batch", "exactly-32"])
-def test_tier_x_medium_lists_in_flat_batches(ctx, monkeypatch, shape, fused, variant):
+def test_tier_x_medium_lists_in_flat_batches(ctx, shape, fused):
     """Lists of 33..64 matrices are consumed 32 items per warp as one flat run of instances (cullMediumBatches): several
     batches with a ragged last one, items of every length in the range, batches that mix StateSets, medium items queued
     next to long items (the two ends of one workspace) and short lists, under a culling camera, with everything
     visible (all 64 bits of the masks set) and with nothing visible."""
-    monkeypatch.setenv("CADR_B200_CULL_VARIANT", variant)
     rng = np.random.default_rng(97)
     if shape == "all-medium":
         counts, n = rng.integers(33, 65, 333).tolist(), 333
