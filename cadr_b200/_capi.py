@@ -90,7 +90,7 @@ class CullParams(C.Structure):
         ("exchangePtr", C.c_uint64 * 8),
         ("exchangeTag", C.c_uint64 * 8),
         ("drawableBounds", C.c_uint64),
-        ("reserved3", C.c_uint64),
+        ("addressDelta", C.c_uint64),
     ]
 
 
@@ -133,6 +133,7 @@ SYMBOLS = {
     "cadr_b200_process_and_cull": (C.c_int, [_P, C.POINTER(CullParams), _P]),
     "cadr_b200_compute_drawable_bounds": (C.c_int, [_P, C.POINTER(CullParams), C.c_uint64, C.c_uint64, C.c_uint32, _P]),
     "cadr_b200_ipc_export": (C.c_int, [_P, C.c_uint64, C.c_char_p]),
+    "cadr_b200_ipc_export_range": (C.c_int, [_P, C.c_uint64, C.c_char_p, C.POINTER(C.c_uint64)]),
     "cadr_b200_ipc_import": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_uint64)]),
     "cadr_b200_ipc_close": (C.c_int, [_P, C.c_uint64]),
     "cadr_b200_external_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_size_t)]),
@@ -165,7 +166,7 @@ def lib() -> C.CDLL:
             f = getattr(l, name)  # AttributeError if the library does not export a declared symbol
             f.restype = res
             f.argtypes = args
-        if l.cadr_b200_abi_version() != 5:
+        if l.cadr_b200_abi_version() != 6:
             raise ImportError("libcadr_b200.so ABI version mismatch")
         _lib = l
     return _lib
@@ -305,6 +306,12 @@ class Context:
         buf = C.create_string_buffer(64)
         check(self._l.cadr_b200_ipc_export(self._h, addr, buf))
         return buf.raw
+
+    def ipc_export_range(self, addr: int) -> tuple[bytes, int]:
+        """Any device address inside a cudaMalloc allocation -> (handle of that allocation, offset of addr inside it)."""
+        buf, off = C.create_string_buffer(64), C.c_uint64()
+        check(self._l.cadr_b200_ipc_export_range(self._h, addr, buf, C.byref(off)))
+        return buf.raw, off.value
 
     def ipc_import(self, handle: bytes) -> int:
         a = C.c_uint64()

@@ -67,7 +67,7 @@ __global__ void consumeTierRKernel(const uint4* __restrict__ indirect, const uin
 // one warp per emitted command of one range
 __global__ void consumeTierXKernel(const uint8_t* __restrict__ cmdBuf, const uint4* __restrict__ ptrBuf, const uint2* __restrict__ tagBuf,
                                    const uint32_t* __restrict__ inst, const unsigned long long* __restrict__ counts,
-                                   const uint4* __restrict__ regions, uint32_t range, unsigned long long* digest)
+                                   const uint4* __restrict__ regions, uint32_t range, uint64_t addressDelta, unsigned long long* digest)
 {
 	const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	const uint32_t numCmds = uint32_t(counts[range]);     // the draw count a vkCmdDrawIndexedIndirectCount would read
@@ -76,8 +76,9 @@ __global__ void consumeTierXKernel(const uint8_t* __restrict__ cmdBuf, const uin
 	const uint32_t* cmd = reinterpret_cast<const uint32_t*>(cmdBuf + 20ull * c);   // indexCount, instanceCount, firstIndex, vertexOffset, firstInstance
 	const uint32_t indexCount = cmd[0], instanceCount = cmd[1], firstIndex = cmd[2], firstInstance = cmd[4];
 	const uint4 p0 = ptrBuf[2ull * c], p1 = ptrBuf[2ull * c + 1];
-	const uint64_t vd = uint64_t(p0.x) | uint64_t(p0.y) << 32, id = uint64_t(p0.z) | uint64_t(p0.w) << 32;
-	const uint64_t ml = uint64_t(p1.x) | uint64_t(p1.y) << 32;
+	// addresses of the GPU that emitted the record; addressDelta moves them into this GPU's mapping of that memory
+	const uint64_t vd = (uint64_t(p0.x) | uint64_t(p0.y) << 32) + addressDelta, id = (uint64_t(p0.z) | uint64_t(p0.w) << 32) + addressDelta;
+	const uint64_t ml = (uint64_t(p1.x) | uint64_t(p1.y) << 32) + addressDelta;
 	const uint32_t drawable = tagBuf[c].x;
 	uint64_t sum = 0, count = 0;
 	const uint64_t total = uint64_t(indexCount) * instanceCount;
@@ -133,7 +134,7 @@ int cadr_b200_consume_check_culled(cadr_ctx* ctx, const cadr_cull_params* p, uin
 	consumeTierXKernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(p->cmdOut), reinterpret_cast<const uint4*>(p->ptrOut),
 	                                        reinterpret_cast<const uint2*>(p->tagOut), reinterpret_cast<const uint32_t*>(p->instOut),
 	                                        reinterpret_cast<const unsigned long long*>(p->counters + sizeof(cadr_cull_header)),
-	                                        reinterpret_cast<const uint4*>(p->stateSetRegions), range,
+	                                        reinterpret_cast<const uint4*>(p->stateSetRegions), range, p->addressDelta,
 	                                        reinterpret_cast<unsigned long long*>(digestOut));
 	ctx->launches++;
 	CADR_CUDA(cudaGetLastError());

@@ -2,6 +2,7 @@
 // "frame complete" flag to every peer, and a stream-side wait for all peers.  No reference counterpart (the
 // reference is single-device); see DESIGN.md §4.
 #include "common.cuh"
+#include <cuda.h>
 #include <cstring>
 
 namespace cadr {
@@ -56,6 +57,34 @@ int cadr_b200_ipc_export(cadr_ctx* ctx, uint64_t devAddr, unsigned char handle[C
 	cudaIpcMemHandle_t h;
 	CADR_CUDA(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(devAddr)));
 	memcpy(handle, &h, sizeof(h));
+	return CADR_OK;
+}
+
+int cadr_b200_ipc_export_range(cadr_ctx* ctx, uint64_t devAddr, unsigned char handle[CADR_IPC_HANDLE_BYTES], uint64_t* offset)
+{
+	REQUIRE_DEVICE_X(ctx);
+	if(!handle || !devAddr || !offset) return setError(CADR_E_LOGIC, "ipc_export_range: null argument");
+	// an IPC handle names a whole cudaMalloc allocation: find the one that holds devAddr (cuMemGetAddressRange, looked up
+	// at run time like the driver entry points of external.cu, so the library has no link-time dependency on libcuda)
+	static CUresult (*getRange)(CUdeviceptr*, size_t*, CUdeviceptr) = nullptr;
+	if(!getRange) {
+		cudaDriverEntryPointQueryResult q;
+		void* fn = nullptr;
+		cudaError_t e = cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q);
+		if(e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+			cudaGetLastError();
+			return setError(CADR_E_CUDA, "ipc_export_range: driver entry point cuMemGetAddressRange is not available");
+		}
+		getRange = reinterpret_cast<CUresult (*)(CUdeviceptr*, size_t*, CUdeviceptr)>(fn);
+	}
+	CUdeviceptr base = 0;
+	size_t size = 0;
+	const CUresult r = getRange(&base, &size, CUdeviceptr(devAddr));
+	if(r != CUDA_SUCCESS || !base) return setError(CADR_E_LOGIC, "ipc_export_range: %llx is not inside a device allocation (driver error %d)", (unsigned long long)devAddr, int(r));
+	cudaIpcMemHandle_t h;
+	CADR_CUDA(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+	memcpy(handle, &h, sizeof(h));
+	*offset = devAddr - uint64_t(base);
 	return CADR_OK;
 }
 

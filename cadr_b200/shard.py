@@ -143,7 +143,13 @@ class PeerExchange:
     all peers' flags.  Gathered arrays are double-buffered by frame parity: a rank can run at most one frame ahead
     of a peer (it cannot pass the wait), so set k&1 is never overwritten while a peer still reads frame k-2... k."""
 
-    def __init__(self, ctx, cmd_capacity: int, num_ranges: int, group=None):
+    def __init__(self, ctx, cmd_capacity: int, num_ranges: int, group=None, *, regions: np.ndarray | None = None,
+                 inst_out: int = 0, arena: int = 0, first_drawable: int = 0):
+        """regions / inst_out / arena (optional, all or none): this rank's region table [S,4] u32, its instance-index
+        buffer and the arena that holds its geometry and matrix lists.  They are exported to the peers as well, which
+        makes every rank's result CONSUMABLE on any GPU (consume_params): commands and counters are local copies, instance
+        indices and matrices are read through the peer mappings on demand (mitigation iii).  first_drawable =
+        position of this rank's first drawable in the whole flattened list (the tag's drawable index is slice-relative)."""
         import ctypes as C
         from . import _capi
         self.ctx, self.group = ctx, group
@@ -182,6 +188,42 @@ class PeerExchange:
             self.peer.append(dict(sets=sets, flags=f))
         self.frame = 0
         self._C, self._capi = C, _capi
+        # -- what a consumer on another GPU needs besides the gathered commands ------------------------------------
+        self.consumable = regions is not None
+        if self.consumable:
+            if not inst_out or not arena:
+                raise ValueError("PeerExchange: regions, inst_out and arena go together")
+            reg = np.zeros((self.num_ranges, 4), np.uint32)
+            reg[:regions.shape[0]] = regions
+            mine = dict(regions=reg, first=int(first_drawable), arena=int(arena),
+                        inst=ctx.ipc_export_range(inst_out), mem=ctx.ipc_export_range(arena))
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine, group=group)
+            self.first_drawable = [e["first"] for e in everyone]
+            self.peer_regions = [e["regions"] for e in everyone]
+            self.regions_dev = []                  # [rank] -> device copy of that rank's region table
+            self.peer_inst = []                    # [rank] -> its instance-index buffer as mapped here
+            self.peer_delta = []                   # [rank] -> (its arena as mapped here) - (address on the owner), mod 2^64
+            opened = {}                            # one mapping per exported allocation (two buffers may share one)
+
+            def open_(h_off):
+                h, off = h_off
+                if h not in opened:
+                    opened[h] = ctx.ipc_import(h)
+                    self._imported.append(opened[h])
+                return opened[h] + off
+
+            for r, e in enumerate(everyone):
+                a = ctx.arena_alloc(max(reg.nbytes, 256))
+                ctx.memcpy_h2d(a, np.ascontiguousarray(e["regions"]))
+                self.regions_dev.append(a)
+                if r == self.rank:
+                    self.peer_inst.append(int(inst_out)); self.peer_delta.append(0)
+                else:
+                    self.peer_inst.append(open_(e["inst"]))
+                    self.peer_delta.append((open_(e["mem"]) - e["arena"]) & 0xFFFFFFFFFFFFFFFF)
+            self.digests = ctx.arena_alloc(max(16 * self.num_ranges, 256))
+            ctx.sync()
         dist.barrier(group=group)
 
     def begin_frame(self, params) -> None:
@@ -223,9 +265,62 @@ class PeerExchange:
                     tag=out["tag"].view(np.uint32).reshape(-1, 2), counts=cnt,
                     status=out["counters"].reshape(self.world, self.counters_bytes)[:, :4].copy().view(np.uint32)[:, 0])
 
+    # -- consuming any rank's result on this GPU ----------------------------------------------------------------------
+    def consume_params(self, r: int):
+        """cadr_cull_params describing rank r's result of the current frame AS SEEN FROM THIS GPU: commands, pointers and
+        tags in slot r of the local gathered arrays, the counters rank r published, rank r's region table, and its
+        instance indices + geometry / matrix lists through the peer mappings (addressDelta translates the addresses the
+        records hold).  What a renderer on this GPU binds to draw rank r's part of the scene."""
+        if not self.consumable:
+            raise RuntimeError("PeerExchange was created without regions / inst_out / arena")
+        p = self._capi.CullParams()
+        st = self.local[self.frame & 1]
+        slot = r * self.cmd_cap
+        p.numStateSets = self.num_ranges
+        p.cmdOut, p.ptrOut, p.tagOut = st["cmd"] + 20 * slot, st["ptr"] + 32 * slot, st["tag"] + 8 * slot
+        p.counters = st["counters"] + r * self.counters_bytes
+        p.stateSetRegions = self.regions_dev[r]
+        p.instOut = self.peer_inst[r]
+        p.addressDelta = self.peer_delta[r]
+        return p
+
+    def consume(self, r: int, stream: int = 0) -> tuple[int, int]:
+        """Walk EVERY range of rank r's result on this GPU the way the reference's vertex shader would
+        (cadr_b200_consume_check_culled; shader.vert:99-123) -> (digest, fetches), summed over the ranges."""
+        p = self.consume_params(r)
+        reg = self.peer_regions[r]
+        live = [s for s in range(reg.shape[0]) if reg[s, 1]]
+        for s in live:
+            self.ctx.consume_check_culled(p, s, int(reg[s, 1]), self.digests + 16 * s, stream)
+        out = np.zeros(2 * self.num_ranges, np.uint64)
+        self.ctx.memcpy_d2h(out, self.digests, stream=stream)
+        self.ctx.sync(stream)
+        d = out.reshape(-1, 2)[live] if live else np.zeros((0, 2), np.uint64)
+        return int(d[:, 0].sum(dtype=np.uint64)), int(d[:, 1].sum(dtype=np.uint64))
+
+    def directory(self) -> list[dict]:
+        """Host view after a sync: the draws a renderer issues for the whole scene, StateSet by StateSet - one
+        indirect-count draw per (StateSet, rank that holds a piece of it): where the commands start in the gathered
+        command buffer, how many there are (the count buffer entry), whose instance indices and matrices they refer to."""
+        g = self.read()
+        out = []
+        for s in range(self.num_ranges):
+            for r in range(self.world):
+                c = int(g["counts"][r][s] & np.uint64(0xFFFFFFFF))
+                if c:
+                    reg = self.peer_regions[r] if self.consumable else None
+                    out.append(dict(state_set=s, rank=r, count=c, instances=int(g["counts"][r][s] >> np.uint64(32)),
+                                    first_command=r * self.cmd_cap + (int(reg[s, 0]) if reg is not None else 0)))
+        return out
+
     def close(self) -> None:
         self.ctx.sync()
         dist.barrier(group=self.group)
+        if self.consumable:
+            for a in self.regions_dev:
+                self.ctx.arena_free(a)
+            self.ctx.arena_free(self.digests)
+            self.regions_dev = []
         for a in self._imported:
             self.ctx.ipc_close(a)
         self._imported = []

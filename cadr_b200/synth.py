@@ -269,13 +269,16 @@ def build_scene(name: str, *, geometries: list[dict] | dict, ml_count: np.ndarra
                 drawable_ml: np.ndarray, drawable_ps_offset: np.ndarray, state_set: np.ndarray,
                 sphere: np.ndarray, lod_count: np.ndarray, lod_ps_offset: np.ndarray, lod_threshold: np.ndarray,
                 matrices: np.ndarray | None, drawable_data: np.ndarray | None = None,
-                first_handle: int = 1, force_level: int = 0, seed: int = 0, gen: dict | None = None) -> Scene:
+                first_handle: int = 1, force_level: int = 0, seed: int = 0, gen: dict | None = None,
+                num_state_sets: int = 0) -> Scene:
     """Lay a scene out.
 
     geometries      either a list of {vertices: bytes ndarray, indices: bytes ndarray, primitive_sets: (P,2) u32},
                     or a dict {count, vertex_bytes, index_bytes, primitive_sets} for `count` identical ones
     drawable_data   optional [n] bool: the drawable owns a 64-byte per-drawable data block (its own handle)
     first_handle    handle numbering starts here (as if first_handle-1 handles had been created before)
+    num_state_sets  size of the region table when it is larger than the highest StateSet index used here (a shard of a
+                    bigger scene: StateSet indices are global, absent StateSets get empty regions)
     """
     bump = Bump(64)  # offset 0 is never handed out: a zero table entry means "null"
     n = len(drawable_geom)
@@ -370,7 +373,7 @@ def build_scene(name: str, *, geometries: list[dict] | dict, ml_count: np.ndarra
     c[:, 10] = ss
 
     # ---- per-StateSet output regions, sized for the worst case -------------------------------------
-    S = int(ss.max()) + 1 if n else 1
+    S = max(int(ss.max()) + 1 if n else 1, int(num_state_sets))
     cnt = ml_count[dm].astype(np.int64)
     cmds = np.where(cnt > SMALL_MAX, 3 * ((cnt + CHUNK - 1) // CHUNK), np.minimum(cnt, 3))
     cmd_cap = np.bincount(ss, weights=cmds, minlength=S).astype(np.int64)
@@ -459,8 +462,7 @@ def config3(num_drawables: int = 100_000, instances: int = 1000, state_sets: int
     """cfg 3: `num_drawables` geometries x `instances`-matrix lists, 64 StateSets, 3 LODs (Appendix D).
     Drawable d belongs to StateSet d mod 64; the flattened list groups StateSets contiguously."""
     n = num_drawables
-    orig = np.concatenate([np.arange(s, n, state_sets) for s in range(state_sets)])  # flatten order -> original id
-    ss = np.concatenate([np.full(len(range(s, n, state_sets)), s, np.uint32) for s in range(state_sets)])
+    orig, ss = config3_flatten(n, state_sets)          # flatten order -> original id, StateSet
     mats = None
     if host_matrices:
         mats = config3_matrices(seed, np.arange(n, dtype=np.uint64), instances, cube, sigma)
@@ -472,6 +474,41 @@ def config3(num_drawables: int = 100_000, instances: int = 1000, state_sets: int
                        lod_ps_offset=np.tile(np.array([0, 8, 16], np.uint32), (n, 1)),
                        lod_threshold=np.tile(np.array([300, 900], np.float32), (n, 1)),
                        matrices=mats, seed=seed, gen=dict(kind="c3", cube=cube, sigma=sigma, instances=instances))
+
+
+def config3_flatten(num_drawables: int, state_sets: int) -> tuple[np.ndarray, np.ndarray]:
+    """Flatten order of cfg 3: position f of the flattened list holds the drawable with original id orig[f] (= its
+    geometry = its matrix list) and belongs to StateSet ss[f]; StateSets are contiguous (StateSet.cpp:233-264)."""
+    n = num_drawables
+    orig = np.concatenate([np.arange(s, n, state_sets) for s in range(state_sets)])
+    ss = np.concatenate([np.full(len(range(s, n, state_sets)), s, np.uint32) for s in range(state_sets)])
+    return orig, ss
+
+
+def config3_shard(num_drawables: int, first: int, count: int, instances: int = 1000, state_sets: int = 64,
+                  seed: int = 0xC0FFEE03, host_matrices: bool = True, cube: float = 4000.0, sigma: float = 20.0) -> Scene:
+    """One rank's part of ONE cfg 3 scene of `num_drawables` drawables: positions [first, first + count) of
+    the flattened list, their geometries and matrix lists, and a handle table over these local objects only.  The
+    matrices are those of the GLOBAL scene (the PRNG is keyed by the global list id), StateSet indices are global
+    (regions of StateSets without local drawables have capacity 0), drawable index d of the shard is position
+    first + d of the whole list: the union of the shards' results is the result of config3(num_drawables, ...)."""
+    orig, ss_all = config3_flatten(num_drawables, state_sets)
+    ids = orig[first:first + count].astype(np.uint64)          # global list / geometry id of each local drawable
+    ss = ss_all[first:first + count]
+    n = len(ids)
+    mats = config3_matrices(seed, ids, instances, cube, sigma) if host_matrices else None
+    geo = dict(count=n, **_box_geometry(True))
+    sphere = np.tile(np.array([0, 0, 0, BOX_SPHERE_RADIUS], dtype=np.float32), (n, 1))
+    sc = build_scene(f"C3:{num_drawables}x{instances}[{first}:{first + n}]", geometries=geo, ml_count=np.full(n, instances, np.uint32),
+                     drawable_geom=np.arange(n), drawable_ml=np.arange(n), drawable_ps_offset=np.zeros(n, np.uint64),
+                     state_set=ss, sphere=sphere, lod_count=np.full(n, 3, np.uint32),
+                     lod_ps_offset=np.tile(np.array([0, 8, 16], np.uint32), (n, 1)),
+                     lod_threshold=np.tile(np.array([300, 900], np.float32), (n, 1)),
+                     matrices=mats, seed=seed,
+                     gen=dict(kind="c3", cube=cube, sigma=sigma, instances=instances, list_ids=ids.astype(np.int64),
+                              first=int(first), global_drawables=int(num_drawables)),
+                     num_state_sets=state_sets)
+    return sc
 
 
 def config3_matrices(seed: int, lists: np.ndarray, instances: int, cube: float, sigma: float) -> np.ndarray:

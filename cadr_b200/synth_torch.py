@@ -112,9 +112,12 @@ def fill_matrix_lists(scene: Scene, arena: torch.Tensor, slab_lists: int = 2000)
     blocks[:, :ML_HEADER] = hdr.to(arena.device)
     if kind == "c2":
         slab_lists = max(slab_lists, 1 << 20)
+    # a shard of a bigger scene (synth.config3_shard): local list k holds the matrices of GLOBAL list list_ids[k]
+    ids = scene.gen.get("list_ids")
+    ids = torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int64)).to(arena.device) if ids is not None else None
     for a in range(0, L, slab_lists):
         b = min(L, a + slab_lists)
-        lists = torch.arange(a, b, dtype=torch.int64, device=arena.device)
+        lists = torch.arange(a, b, dtype=torch.int64, device=arena.device) if ids is None else ids[a:b]
         if kind == "c3":
             m = c3_matrices(scene.seed, lists, count, scene.gen["cube"], scene.gen["sigma"])
         elif kind == "c2":

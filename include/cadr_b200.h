@@ -40,7 +40,7 @@ extern "C" {
 # define CADR_API __attribute__((visibility("default")))
 #endif
 
-#define CADR_B200_ABI_VERSION 5
+#define CADR_B200_ABI_VERSION 6
 
 /* ---- error codes (src/CadR/Exceptions.h:13-40) ------------------------------------------------- */
 enum {
@@ -188,7 +188,12 @@ typedef struct cadr_cull_params {
 	 * lies outside one frustum plane by more than a rounding-safe margin is dropped before any of its matrices is read;
 	 * the result of the frame is identical with and without the table. */
 	uint64_t drawableBounds;
-	uint64_t reserved3;
+	/* Consumer side only (cadr_b200_consume_check_culled; the cull ignores it): added to every forwarded pointer before it
+	 * is dereferenced.  A renderer GPU that walks ANOTHER rank's commands reads that rank's geometry and matrix lists
+	 * through a peer mapping (cadr_b200_ipc_import); the records hold addresses of the owning GPU, and
+	 * addressDelta = (address of the owner's arena as mapped here) - (its address on the owner) translates them
+	 * (two's complement: the mapping may lie below).  0 for local results. */
+	uint64_t addressDelta;
 } cadr_cull_params;
 
 /* World-space axis-aligned box that encloses the bounding spheres of ALL instances of a drawable (the drawable's
@@ -322,6 +327,10 @@ CADR_API int  cadr_b200_process_and_cull(cadr_ctx* ctx, const cadr_cull_params* 
 #define CADR_IPC_HANDLE_BYTES 64
 /* Export a buffer returned by cadr_b200_arena_alloc / map a peer's exported buffer into this process. */
 CADR_API int  cadr_b200_ipc_export(cadr_ctx* ctx, uint64_t devAddr, unsigned char handle[CADR_IPC_HANDLE_BYTES]);
+/* The same for ANY device address inside a cudaMalloc allocation (a slice of a bigger buffer, memory handed out by another
+ * allocator of the process): exports the allocation that holds it and reports where devAddr lies inside;
+ * the importer adds *offset to the address cadr_b200_ipc_import returns. */
+CADR_API int  cadr_b200_ipc_export_range(cadr_ctx* ctx, uint64_t devAddr, unsigned char handle[CADR_IPC_HANDLE_BYTES], uint64_t* offset);
 CADR_API int  cadr_b200_ipc_import(cadr_ctx* ctx, const unsigned char handle[CADR_IPC_HANDLE_BYTES], uint64_t* devAddr);
 CADR_API int  cadr_b200_ipc_close(cadr_ctx* ctx, uint64_t devAddr);
 /* Copy this rank's counters into slot `rank` of every peer's gathered counters, then raise flag[rank] = frameSeq
@@ -363,7 +372,10 @@ CADR_API int  cadr_b200_consume_check(cadr_ctx* ctx, uint64_t indirectData, uint
 /* The same for one draw range of a cadr_b200_cull_compact result, read the way vkCmdDrawIndexedIndirectCount would
  * (count from the counters buffer, at most maxCommands draws; instance k of a command is matrix
  * instOut[firstInstance + k]).  The digest is keyed by drawable index, so it does not depend on emission order or on
- * how a long list was cut into commands. */
+ * how a long list was cut into commands.
+ * Multi-GPU: to walk rank r's commands on another GPU point cmdOut / ptrOut / tagOut at slot r * exchangeCmdCapacity of
+ * the local gathered arrays, counters at rank r's block of the gathered counters, stateSetRegions at a copy of rank r's
+ * region table, instOut at rank r's instance-index buffer as mapped here, and set addressDelta (see cadr_cull_params). */
 CADR_API int  cadr_b200_consume_check_culled(cadr_ctx* ctx, const cadr_cull_params* params, uint32_t range, uint32_t maxCommands,
                                              uint64_t digestOut, cadr_stream stream);
 

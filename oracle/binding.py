@@ -43,6 +43,9 @@ def lib() -> C.CDLL:
         l.oracle_cull_count.restype = C.c_uint64
         l.oracle_cull_count.argtypes = [C.POINTER(Segment), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
+        l.oracle_cull_summary.restype = C.c_uint64
+        l.oracle_cull_summary.argtypes = [C.POINTER(Segment), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
         l.oracle_upload.restype = C.c_uint64
         l.oracle_upload.argtypes = [C.POINTER(Segment), C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
         l.oracle_patch_handles.restype = C.c_uint64
@@ -141,6 +144,34 @@ def cull_count(mem: Memory, first: int, count: int, indirect: np.ndarray, pointe
     surv = lib().oracle_cull_count(mem.segs, mem.n, first, count, ind.ctypes.data, pts.ctypes.data, cd.ctypes.data,
                                    pl.ctypes.data, ey.ctypes.data, C.byref(visited), threads)
     return int(surv), int(visited.value)
+
+
+def host_threads() -> int:
+    """Every host core this process may run on (not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1)."""
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or max_threads())
+
+
+def cull_summary(mem: Memory, indirect: np.ndarray, pointers: np.ndarray, cull: np.ndarray, planes: np.ndarray,
+                 eye: np.ndarray, threads: int = 0) -> dict:
+    """Whole-scene parity: per (drawable, lod) survivor count, index sum and index sum of squares of the drawables
+    described by the parallel arrays -> {k [n,3] u32, sum [n,3] u64, sq [n,3] u64, near_band}."""
+    ind = np.ascontiguousarray(indirect, dtype=np.uint32)
+    pts = np.ascontiguousarray(pointers, dtype=np.uint64)
+    cd = np.ascontiguousarray(cull, dtype=np.uint32)
+    n = ind.shape[0]
+    assert pts.shape[0] == n and cd.shape[0] == n
+    pl = np.ascontiguousarray(planes, dtype=np.float32).reshape(6, 4)
+    ey = np.ascontiguousarray(eye, dtype=np.float32).reshape(-1)[:3].copy()
+    k = np.zeros((max(n, 1), 3), np.uint32)
+    sm = np.zeros((max(n, 1), 3), np.uint64)
+    sq = np.zeros((max(n, 1), 3), np.uint64)
+    nb = C.c_uint64()
+    faults = lib().oracle_cull_summary(mem.segs, mem.n, n, ind.ctypes.data, pts.ctypes.data, cd.ctypes.data, pl.ctypes.data,
+                                       ey.ctypes.data, k.ctypes.data, sm.ctypes.data, sq.ctypes.data, C.byref(nb),
+                                       threads or host_threads())
+    if faults:
+        raise RuntimeError(f"oracle: {faults} matrix lists outside device memory")
+    return dict(k=k[:n], sum=sm[:n], sq=sq[:n], near_band=int(nb.value))
 
 
 def upload(mem: Memory, regions: np.ndarray, staging: np.ndarray) -> None:

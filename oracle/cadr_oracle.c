@@ -310,6 +310,55 @@ uint64_t oracle_cull_count(const oracle_segment* segs, uint32_t numSegs, uint32_
 	return survivors;
 }
 
+/* Whole-scene parity at BASELINE sizes: the same evaluation as oracle_cull_compact, on numThreads threads, reduced to
+ * an order-independent summary PER (drawable, lod) instead of emitted buffers - number of survivors, sum and sum of
+ * squares of their instance indices - which a GPU result can be folded into on the device (every emitted command
+ * carries its {drawable, lod} tag).  Two instance sets with equal count, sum and sum of squares differ only by
+ * deliberate construction; together with the per-command checks the tests make on the device (forwarded pointers,
+ * PrimitiveSet fields, runs inside their regions) this compares ALL drawables of a 100 M-instance frame, not a sample.
+ * `count` drawables described by parallel arrays (records of any subset of the list, e.g. one chunk of matrix lists
+ * whose bytes were copied back from the device).  outK [count*3] u32, outSum / outSq [count*3] u64. */
+uint64_t oracle_cull_summary(const oracle_segment* segs, uint32_t numSegs, uint32_t count,
+                             const uint8_t* indirect, const uint8_t* pointers, const uint8_t* cullData,
+                             const float planes[6][4], const float eye[3],
+                             uint32_t* outK, uint64_t* outSum, uint64_t* outSq, uint64_t* nearBandOut, int numThreads)
+{
+	oracle_mem m = { segs, numSegs };
+	uint64_t nearBand = 0, faults = 0;
+	(void)numThreads;
+#pragma omp parallel for schedule(dynamic, 16) reduction(+:nearBand, faults) num_threads(numThreads > 0 ? numThreads : 1)
+	for(int64_t dd = 0; dd < (int64_t)count; dd++) {
+		size_t d = (size_t)dd;
+		int fault = 0;
+		uint32_t N;            memcpy(&N, indirect + d * 16 + 4, 4);
+		uint64_t ml;           memcpy(&ml, pointers + d * 32 + 16, 8);
+		const uint8_t* cd = cullData + d * 48;
+		float bs[4];           memcpy(bs, cd, 16);
+		uint32_t lodCount;     memcpy(&lodCount, cd + 16, 4);
+		float thr[2];          memcpy(thr, cd + 32, 8);
+		if(lodCount < 1) lodCount = 1;
+		if(lodCount > 3) lodCount = 3;
+		uint32_t k[3] = { 0, 0, 0 };
+		uint64_t sum[3] = { 0, 0, 0 }, sq[3] = { 0, 0, 0 };
+		if(N != 0) {
+			const uint8_t* mats = xlate(&m, ml + 64, (uint64_t)N * 64, &fault);
+			if(!mats) faults++;
+			else
+				for(uint32_t j = 0; j < N; j++) {
+					float M[16];
+					memcpy(M, mats + (size_t)j * 64, 64);
+					int nb;
+					int lod = eval_instance(M, bs, lodCount, thr[0], thr[1], planes, eye, &nb);
+					nearBand += (uint64_t)nb;
+					if(lod >= 0) { k[lod]++; sum[lod] += j; sq[lod] += (uint64_t)j * j; }
+				}
+		}
+		for(int l = 0; l < 3; l++) { outK[d * 3 + l] = k[l]; outSum[d * 3 + l] = sum[l]; outSq[d * 3 + l] = sq[l]; }
+	}
+	if(nearBandOut) *nearBandOut = nearBand;
+	return faults;
+}
+
 /* ------------------------------------------------------------------------------------------------------
  * Upload: DataMemory::recordUploads, DataMemory.cpp:400-446 — one copy per marker:
  *   src = stagingStart - stagingBufferStart, dst = marker.deviceAddress, size = stagingEnd - stagingStart.

@@ -47,3 +47,19 @@ def assert_tier_x_equal(gpu: dict, ref: dict):
     assert gpu["near_band"] == ref["near_band"], "near-band counts differ"
     ok, why = canon_equal(canonicalise(gpu), canonicalise(ref))
     assert ok, why
+
+
+def fold_by_drawable_lod(result: dict, n: int):
+    """The per-(drawable, lod) summary of an emitted Tier X result (numpy): survivors, index sum, index sum of squares
+    - what oracle/binding.cull_summary computes straight from the matrices.  Commands of one (drawable, lod) that were
+    emitted per work item are folded together."""
+    k = np.zeros((n, 3), np.uint64); sm = np.zeros((n, 3), np.uint64); sq = np.zeros((n, 3), np.uint64)
+    regions = result["regions"]
+    for s in range(regions.shape[0]):
+        base = int(regions[s, 0])
+        for ci in range(base, base + int(result["cmd_count"][s])):
+            d, lod = int(result["tag"][ci, 0]), int(result["tag"][ci, 1])
+            cnt, first = int(result["cmd"][ci, 1]), int(result["cmd"][ci, 4])
+            run = result["inst"][first:first + cnt].astype(np.uint64)
+            k[d, lod] += np.uint64(cnt); sm[d, lod] += run.sum(dtype=np.uint64); sq[d, lod] += (run * run).sum(dtype=np.uint64)
+    return k, sm, sq

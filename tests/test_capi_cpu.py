@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     l = ctypes.CDLL(cadr_b200.LIB_PATH)
     for name in declared_symbols():
         assert hasattr(l, name), name
-    assert cadr_b200.lib().cadr_b200_abi_version() == 5
+    assert cadr_b200.lib().cadr_b200_abi_version() == 6
 
 
 def test_struct_sizes_match_header():

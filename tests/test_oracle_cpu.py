@@ -7,7 +7,7 @@ import pytest
 from cadr_b200 import synth
 from cadr_b200.frame import canonicalise
 from oracle import binding as ob
-from helpers import FAKE_BASE, FAKE_LIST, oracle_tier_r, oracle_tier_x
+from helpers import FAKE_BASE, FAKE_LIST, fold_by_drawable_lod, oracle_tier_r, oracle_tier_x
 
 CASES = [
     dict(seed=1),                                           # level 1
@@ -211,3 +211,28 @@ def test_upload_and_patch_restatements():
     ob.patch_handles(mem, FAKE_BASE + sc.root_off, sc.handle_level, np.array([[h, FAKE_BASE + 4096]], np.uint64))
     _, ptr = ob.process_drawables(mem, FAKE_BASE + sc.root_off, sc.handle_level, FAKE_LIST, sc.n)
     assert (ptr[sc.drawables[:, 2] == np.uint64(h), 2] == FAKE_BASE + 4096).all()
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_parallel_summary_equals_the_emitted_result(seed):
+    """oracle_cull_summary (the whole-scene parity entry: OpenMP, per (drawable, lod) count / index sum / sum of
+    squares) against the sequential oracle_cull_compact folded the same way, on ragged scenes with long lists, in one
+    call and chunk by chunk over arbitrary subsets of the drawables (how the full-size GPU tests feed it)."""
+    sc = synth.random_scene(seed, n=700, num_lists=120, max_count=90, state_sets=6, big_lists=3)
+    planes, eye = synth.orbit_camera(40 * seed, 250.0, far=500.0)
+    img = sc.image(FAKE_BASE)
+    mem, ind, ptr = oracle_tier_r(sc, img=img)
+    ref = ob.cull_compact(mem, FAKE_BASE + sc.root_off, sc.handle_level, FAKE_LIST, sc.n, ind, ptr, sc.cull, planes, eye, sc.regions)
+    k, sm, sq = fold_by_drawable_lod(ref, sc.n)
+    for threads in (1, 4):
+        got = ob.cull_summary(mem, ind, ptr, sc.cull, planes, eye, threads)
+        assert np.array_equal(got["k"].astype(np.uint64), k) and np.array_equal(got["sum"], sm) and np.array_equal(got["sq"], sq)
+        assert got["near_band"] == ref["near_band"] and int(got["k"].sum()) == ref["num_instances"]
+    rng = np.random.default_rng(seed)
+    order = rng.permutation(sc.n)
+    nb = 0
+    for part in np.array_split(order, 5):
+        got = ob.cull_summary(mem, ind[part], ptr[part], sc.cull[part], planes, eye, 3)
+        assert np.array_equal(got["k"].astype(np.uint64), k[part]) and np.array_equal(got["sum"], sm[part]) and np.array_equal(got["sq"], sq[part])
+        nb += got["near_band"]
+    assert nb == ref["near_band"]
