@@ -64,6 +64,11 @@ def parse_args():
                     help="multi-GPU: peer = records stored into every rank's gathered arrays by the cull kernels over NVLink; "
                          "nccl = all_gather_into_tensor after the cull (baseline)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="drawables in the CPU sample (0: auto)")
+    ap.add_argument("--independent-scenes", action="store_true",
+                    help="multi-GPU: every rank builds a scene of its own (round-1 behaviour) instead of culling its slice of ONE scene")
+    ap.add_argument("--no-verify", action="store_true", help="multi-GPU: skip the cross-checks of the exchange after the timed loops")
+    ap.add_argument("--no-workloads", action="store_true",
+                    help="single GPU, default workload: do not append the compact lines of the other BASELINE configs (c1, c2, c4, c5)")
     ap.add_argument("--list-bounds", action="store_true",
                     help="optional pre-test: per-drawable bounds (computed once, untimed; static scene) let the cull drop long lists "
                          "outside the frustum without reading their matrices; identical results, fewer bytes (not the headline number)")
@@ -77,9 +82,16 @@ def c3_drawables(args) -> int:
     return args.drawables or (125_000 if args.workload == "c5" else 100_000)
 
 
-def make_scene(args, rank: int, host_matrices: bool, drawables: int | None = None) -> synth.Scene:
+def make_scene(args, rank: int, host_matrices: bool, drawables: int | None = None, world: int = 1) -> synth.Scene:
     if args.workload in C3_SHAPED:
         n = drawables or c3_drawables(args)
+        if world > 1 and not args.independent_scenes:
+            # ONE scene of world x n drawables (north_star: "drawables are partitioned across the 8 B200s"): the flattened
+            # list is cut into per-rank slices balanced by instance count (shard.partition), every rank lays out its slice
+            from cadr_b200 import shard
+            first, count = shard.partition(np.full(n * world, args.instances, np.int64), world)[rank]
+            return synth.config3_shard(n * world, first, count, args.instances, state_sets=args.state_sets, seed=0xC0FFEE03,
+                                       host_matrices=host_matrices)
         return synth.config3(n, args.instances, state_sets=args.state_sets, seed=0xC0FFEE03 + rank, host_matrices=host_matrices)
     if args.workload == "c1":
         side = round((drawables or args.drawables or 1_000_000) ** (1 / 3))
@@ -223,12 +235,16 @@ def workload_config(args, n_gpus: int) -> dict:
         n = c3_drawables(args)
         which = {"c3": "configs[2]: synthetic CAD assembly", "c5": "configs[4]: 1 B-instance scene sharded over 8 GPUs, this is the per-GPU shard",
                  "c4": "configs[3]: dynamic scene, 10 % of the MatrixLists rewritten per frame through the upload path, then culled"}[args.workload]
+        scene_txt = ("every rank culls a scene of its own" if args.independent_scenes else
+                     f"ONE scene of {n * n_gpus} geometries ({n * n_gpus * args.instances / 1e6:.0f} M instances) cut into {n_gpus} slices "
+                     f"balanced by instance count (shard.partition); StateSet indices are global")
         if n_gpus == 1:
             mg = "single GPU"
         elif args.exchange == "peer":
-            mg = "each rank culls its own shard; the cull kernels store command records into every rank's gathered arrays over NVLink peer mappings"
+            mg = (scene_txt + "; the cull kernels store command records into every rank's gathered arrays over NVLink peer mappings; "
+                  "instance indices and matrices stay on the owning GPU and are readable from every GPU through peer mappings")
         else:
-            mg = "each rank culls its own shard; command lists + counters all-gathered with NCCL after the cull"
+            mg = scene_txt + "; command lists + counters all-gathered with NCCL after the cull"
         return {"workload": f"BASELINE {which}, {n} geometries x {args.instances}-instance MatrixLists "
                             f"({n * args.instances / 1e6:.0f} M instances) per GPU, {args.state_sets} StateSets, 3-level LOD, orbiting camera 1 deg/frame",
                 "per_gpu_instances": n * args.instances, "gpus": n_gpus,
@@ -268,7 +284,7 @@ def run_b200(args):
     ctx = cadr_b200.Context(local)
     stream_t = torch.cuda.Stream(device=dev)
     stream = stream_t.cuda_stream
-    scene = make_scene(args, rank, host_matrices=False)
+    scene = make_scene(args, rank, host_matrices=False, world=world)
     arena = TorchArena(dev)
     with torch.cuda.stream(stream_t):
         ds = DeviceScene(ctx, scene, alloc=arena.alloc, free=arena.free, upload=False, stream=stream)
@@ -329,9 +345,16 @@ def run_b200(args):
             ex = Exchange(ds.cmd_cap, scene.num_state_sets, dev)
             parts = [arena.tensor(ds.cmd_out), arena.tensor(ds.ptr_out), arena.tensor(ds.tag_out), arena.tensor(ds.counters)]
         else:
-            px = PeerExchange(ctx, ds.cmd_cap, scene.num_state_sets)
+            # instance indices alternate between two buffers by frame parity (a peer may still read frame k's runs while
+            # this rank culls frame k + 1); regions / index buffers / arena are exported too, so that every rank's result
+            # can be CONSUMED on any GPU through peer mappings
+            inst2 = arena.alloc(ds.inst_cap * 4)
+            px = PeerExchange(ctx, ds.cmd_cap, scene.num_state_sets, regions=scene.regions, inst_out=[ds.inst_out, inst2],
+                              arena=ds.arena, first_drawable=int(scene.gen.get("first", 0)))
 
-    def run_cull(k, with_exchange):
+    RENDERER = 0            # the rank whose GPU plays the renderer in the "instance runs pulled" series
+
+    def run_cull(k, with_exchange, pull=False):
         planes, eye = cams[k % 360]
         if px is not None and with_exchange:
             p = ds.cull_params(planes, eye)
@@ -342,6 +365,8 @@ def run_b200(args):
             else:
                 ctx.process_and_cull(p, stream=stream)
             px.end_frame(ds.counters, stream=stream)
+            if pull and rank == RENDERER:
+                px.pull_instances(stream=stream)
             return
         if args.unfused:
             ds.process_drawables()
@@ -436,6 +461,15 @@ def run_b200(args):
 
         ms_cull_only = timed(lambda k: step_device(k, with_exchange=False), args.steps) if world > 1 else ms_total
 
+        # second series ("the exchange is NOT free"): besides the commands, the survivors' instance-index runs
+        # of every rank are pulled to ONE renderer GPU (rank 0) through the peer mappings after each frame
+        ms_pull = None
+        if px is not None:
+            px.enable_pull(ds.inst_cap)
+            for k in range(3):
+                run_cull(k, True, pull=True)
+            ms_pull = timed(lambda k: run_cull(k, True, pull=True), args.steps)
+
         upload_list(0)
         for k in range(3):
             step_e2e(k)
@@ -483,6 +517,74 @@ def run_b200(args):
             stream_t.synchronize()
             tier_r.append(ctx.kernel_times()[0])
         ctx.set_profiling(False)
+
+        # ---- multi-GPU: is what the exchange delivered right, and can ONE GPU consume the whole frame? ------------------
+        verify = None
+        if px is not None and not args.no_verify:
+            kf = args.warmup + 7
+            barrier()
+            run_cull(kf, False)                       # the same frame without the exchange: per-range totals are deterministic
+            stream_t.synchronize()
+            alone = ds.read_counters()
+            barrier()
+            run_cull(kf, True, pull=True)             # ... and with it (rank 0 also pulls the instance runs)
+            barrier()
+            v = px.verify(dev)                        # NCCL all-gather of every rank's own slot vs what the peer stores left here
+            g = px.read()
+            counts_ok = bool(np.array_equal((g["counts"][rank] >> np.uint64(32)).astype(np.int64)[:scene.num_state_sets], alone["inst_count"])
+                             and (g["status"] == 0).all())
+            # consumer walk (the reference's vertex shader, shader.vert:99-123): every rank walks its own result locally, the
+            # renderer GPU walks EVERY rank's ranges through the peer mappings (indices + matrices fetched from the owner,
+            # addresses translated) and once more with the pulled index copies; the digests must agree
+            t0 = time.perf_counter()
+            mine = px.consume(rank, stream)
+            t_local = time.perf_counter() - t0
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine)
+            consume_ok, pulled_ok, t_walk = True, True, 0.0
+            if rank == RENDERER:
+                t0 = time.perf_counter()
+                for r in range(world):
+                    consume_ok = consume_ok and px.consume(r, stream) == everyone[r]
+                t_walk = time.perf_counter() - t0
+                for r in range(world):
+                    if r != rank:
+                        pulled_ok = pulled_ok and px.consume(r, stream, pulled=True) == everyone[r]
+            directory = px.directory() if rank == RENDERER else []
+            barrier()                                 # peers keep their buffers untouched until the renderer is done
+            # Tier R records of every slice gathered into whole-list arrays over NCCL (shard.TierRGather)
+            tier_r_gather = None
+            if not args.independent_scenes and args.workload in C3_SHAPED:
+                from cadr_b200.shard import TierRGather, partition
+                slices = partition(np.full(c3_drawables(args) * world, args.instances, np.int64), world)
+                tg = TierRGather(slices, dev)
+                ind_t, ptr_t = arena.tensor(ds.indirect), arena.tensor(ds.pointers)
+                tg.run(ind_t, ptr_t)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                e0.record()
+                for _ in range(5):
+                    tg.run(ind_t, ptr_t)
+                e1.record()
+                torch.cuda.synchronize()
+                f0, c0 = slices[rank]
+                mine_ok = bool(torch.equal(tg.indirect[f0 * 16:(f0 + c0) * 16], ind_t[:c0 * 16]) and torch.equal(tg.pointers[f0 * 32:(f0 + c0) * 32], ptr_t[:c0 * 32]))
+                chk = [None] * world
+                dist.all_gather_object(chk, (int(tg.indirect.view(torch.int32).sum(dtype=torch.int64)), int(tg.pointers.view(torch.int64).sum()), mine_ok))
+                tier_r_gather = {"ms": round(e0.elapsed_time(e1) / 5, 4), "bytes_per_rank": c0 * 48, "drawables": tg.n,
+                                 "verified": bool(all(c == chk[0] for c in chk) and chk[0][2]),
+                                 "how": "dist.broadcast of every slice into rows [first, first+count) of whole-list arrays on every rank (NCCL)"}
+            flag = torch.tensor([int(v["ok"] and counts_ok and consume_ok and pulled_ok and (tier_r_gather is None or tier_r_gather["verified"]))], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            verify = {"ok": bool(int(flag.item())), "nccl_cross_check": v, "counts_equal_cull_only": counts_ok,
+                      "consumer_walk": {"renderer_rank": RENDERER, "digests_equal_owner": consume_ok, "with_pulled_indices_equal": pulled_ok,
+                                        "fetches_per_rank": [int(e[1]) for e in everyone], "owner_local_walk_s": round(t_local, 3),
+                                        "renderer_walk_all_ranks_s": round(t_walk, 3),
+                                        "what": "cadr_b200_consume_check_culled over every range of every rank from ONE GPU: commands from the local "
+                                                "gathered arrays, instance indices + matrices + geometry read from the owning GPU through CUDA IPC peer "
+                                                "mappings (addressDelta); digest compared with each owner's own local walk"},
+                      "draws_for_whole_scene": len(directory), "tier_r_gather": tier_r_gather}
 
     large_name = "cullListWarpKernel"
     kt = np.array(ktimes)
@@ -574,13 +676,23 @@ def run_b200(args):
                              "ms_per_step": round(ms_cull_only / args.steps, 4)}
         line["exchange"] = ("fused: cull kernels store records into every rank's gathered arrays over NVLink peer mappings (no collective call)"
                             if px is not None else f"NCCL all_gather_into_tensor of {ex.bytes_per_rank} padded bytes per rank after the cull")
+        if ms_pull is not None:
+            # two series, p stated: `value` = commands + counters on every GPU, survivors reachable through peer
+            # mappings; this one additionally copies every rank's survivor index runs to ONE renderer GPU each frame
+            line["with_instance_pull"] = {"value": round(total_inst * args.steps / (ms_pull * 1e-3) / 1e6, 1), "unit": "M instances/s",
+                                          "ms_per_step": round(ms_pull / args.steps, 4), "survivor_fraction": round(p, 4),
+                                          "inbound_bytes_per_step_on_renderer": int(4 * p * inst * (world - 1)),
+                                          "what": "value's frame + cadr_b200_exchange_pull_instances on rank 0: 4 B x survivors of the other "
+                                                  "ranks cross NVLink into one renderer-visible index buffer; matrices stay sharded"}
+        if verify is not None:
+            line["exchange_verified"] = verify["ok"]
+            line["verification"] = verify
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, desc, threads, _ = cpu_sample_run(args, 300, 2)      # ~5 s of all host cores (about 75 core-seconds on a 16-core box)
         line["cpu_baseline"] = {"value": round(v / 1e6, 3), "unit": "M instances/s", "cores": threads, "kind": "port", "sample": desc}
-    if rank == 0:
-        print(json.dumps(line))
     if px is not None:
         px.close()
+        arena.free(inst2)
     if rewrite is not None:
         ctx.host_free(rewrite["stage_host"])
     arena.free(lists[1])
@@ -588,7 +700,45 @@ def run_b200(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    if world == 1 and args.workload == "c3" and not args.no_workloads and not args.drawables and args.instances == 1000 and not args.list_bounds:
+        # the other BASELINE configs, a few seconds each, so that the driver's record carries all five (each in a process
+        # of its own, after this one has returned its device memory)
+        arena.tensors.clear()
+        torch.cuda.empty_cache()
+        line["workloads"] = other_workloads(args)
+    if rank == 0:
+        print(json.dumps(line))
+    if verify is not None and not verify["ok"]:
+        sys.stderr.write("bench.py: the multi-GPU exchange did not verify: " + json.dumps(verify)[:2000] + "\n")
+        return 1
     return 0
+
+
+def other_workloads(args) -> dict:
+    """Compact lines of BASELINE configs[0], [1], [3] and [4] (c1, c2, c4, c5): the same measurement as the main line, run
+    by this script in a child process per workload."""
+    out = {}
+    steps = str(max(20, min(args.steps, 100)))
+    for w in ("c1", "c2", "c4", "c5"):
+        cmd = [sys.executable, os.path.abspath(__file__), "--workload", w, "--steps", steps, "--warmup", str(max(args.warmup, 3)),
+               "--no-cpu-baseline", "--no-workloads"]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:                      # reported, never hidden: the main line stands on its own
+            out[w] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            continue
+        c = {"workload": d["config"]["workload"], "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
+             "survivor_fraction": d["survivor_fraction"], "gpu_launches": d["gpu_launches"],
+             "e2e": {k: d["e2e"][k] for k in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+             "e2e_resident_list": {k: d["e2e_resident_list"][k] for k in ("value", "ms_per_step")},
+             "roofline": {k: d["roofline"][k] for k in ("kernel", "achieved", "peak", "frac", "launch_ms", "traffic", "frac_of_line_granular_floor")
+                          if k in d["roofline"]},
+             "tier_r": {k: d["tier_r"][k] for k in ("value", "unit", "launch_ms", "frac", "frac_of_line_granular_floor") if k in d["tier_r"]}}
+        if "upload" in d:
+            c["upload"] = {k: d["upload"][k] for k in ("bytes_per_step", "launch_ms", "achieved", "frac")}
+        out[w] = c
+    return out
 
 
 def main():

@@ -52,6 +52,13 @@ class NoDevice(CadrError):
 _ERR = {E_LOGIC: LogicError, E_OUT_OF_RESOURCES: OutOfResources, E_TIMEOUT: Timeout, E_NO_DEVICE: NoDevice}
 
 
+class ExchangePull(C.Structure):
+    _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("numRanges", C.c_uint32), ("countersBytes", C.c_uint32),
+                ("gatheredCounters", C.c_uint64), ("gatheredInst", C.c_uint64), ("instCapacity", C.c_uint64),
+                ("includeLocal", C.c_uint32), ("reserved", C.c_uint32),
+                ("regions", C.c_uint64 * 8), ("peerInst", C.c_uint64 * 8)]
+
+
 class CopyRegion(C.Structure):
     _fields_ = [("dstAddr", C.c_uint64), ("srcOffset", C.c_uint64), ("bytes", C.c_uint64)]
 
@@ -133,6 +140,7 @@ SYMBOLS = {
     "cadr_b200_process_and_cull": (C.c_int, [_P, C.POINTER(CullParams), _P]),
     "cadr_b200_compute_drawable_bounds": (C.c_int, [_P, C.POINTER(CullParams), C.c_uint64, C.c_uint64, C.c_uint32, _P]),
     "cadr_b200_ipc_export": (C.c_int, [_P, C.c_uint64, C.c_char_p]),
+    "cadr_b200_exchange_pull_instances": (C.c_int, [_P, C.POINTER(ExchangePull), _P]),
     "cadr_b200_ipc_export_range": (C.c_int, [_P, C.c_uint64, C.c_char_p, C.POINTER(C.c_uint64)]),
     "cadr_b200_ipc_import": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_uint64)]),
     "cadr_b200_ipc_close": (C.c_int, [_P, C.c_uint64]),
@@ -306,6 +314,9 @@ class Context:
         buf = C.create_string_buffer(64)
         check(self._l.cadr_b200_ipc_export(self._h, addr, buf))
         return buf.raw
+
+    def exchange_pull_instances(self, pull: "ExchangePull", stream: int = 0) -> None:
+        check(self._l.cadr_b200_exchange_pull_instances(self._h, C.byref(pull), _P(stream)))
 
     def ipc_export_range(self, addr: int) -> tuple[bytes, int]:
         """Any device address inside a cudaMalloc allocation -> (handle of that allocation, offset of addr inside it)."""

@@ -33,6 +33,7 @@ struct cadr_ctx {
 	bool profiling = false;
 	bool largeKernelConfigured = false;   // dynamic shared-memory opt-in of cullLargeKernel done on this device
 	bool ringKernelConfigured = false;    // same for cullListRingKernel
+	bool stagedKernelConfigured[3] = {false, false, false};   // same for cullSmallStagedKernel<1..3>
 	cudaEvent_t evBegin[cadr::KS_COUNT] = {};
 	cudaEvent_t evEnd[cadr::KS_COUNT] = {};
 	bool evUsed[cadr::KS_COUNT] = {};
@@ -118,6 +119,31 @@ __device__ __forceinline__ uint64_t lookupHandle(uint64_t root, uint64_t handle)
 		uint64_t t2 = ldg_u64(root + 8ull * uint32_t(handle >> 22));
 		uint64_t t3 = ldg_u64(t2 + 8ull * (uint32_t(handle >> 11) & 0x7ffu));
 		return ldg_u64(t3 + 8ull * (uint32_t(handle) & 0x7ffu));
+	}
+}
+
+// The same walk with loads the compiler must keep where they are written (volatile asm): the staged kernel issues the walks
+// of a tile two iterations before it needs the results, and a load sunk to its first use would bring the latency back.
+__device__ __forceinline__ uint64_t ldg_u64_pinned(uint64_t addr)
+{
+	uint64_t v;
+	asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(addr));
+	return v;
+}
+template<int LEVEL>
+__device__ __forceinline__ uint64_t lookupHandlePinned(uint64_t root, uint64_t handle)
+{
+	if constexpr(LEVEL == 1) {
+		return ldg_u64_pinned(root + 8ull * uint32_t(handle));
+	}
+	else if constexpr(LEVEL == 2) {
+		uint64_t t2 = ldg_u64_pinned(root + 8ull * uint32_t(handle >> 11));
+		return ldg_u64_pinned(t2 + 8ull * (uint32_t(handle) & 0x7ffu));
+	}
+	else {
+		uint64_t t2 = ldg_u64_pinned(root + 8ull * uint32_t(handle >> 22));
+		uint64_t t3 = ldg_u64_pinned(t2 + 8ull * (uint32_t(handle >> 11) & 0x7ffu));
+		return ldg_u64_pinned(t3 + 8ull * (uint32_t(handle) & 0x7ffu));
 	}
 }
 

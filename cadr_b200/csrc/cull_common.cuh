@@ -209,6 +209,54 @@ __device__ __forceinline__ uint32_t warpInclusiveScan(uint32_t v, int lane)
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
+// shared-memory accessors on 32-bit shared-window addresses (no generic-address conversion in the loops)
+__device__ __forceinline__ uint4 ldsU4(uint32_t addr)
+{
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ float4 ldsF4(uint32_t addr)
+{
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ void stsU4(uint32_t addr, uint4 v)
+{
+	asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ uint2 ldsU2(uint32_t addr)
+{
+	uint2 v;
+	asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ void stsU2(uint32_t addr, uint2 v)
+{
+	asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ unsigned long long ldsU64(uint32_t addr)
+{
+	const uint2 v = ldsU2(addr);
+	return (unsigned long long)v.x | ((unsigned long long)v.y << 32);
+}
+__device__ __forceinline__ void orMask(uint32_t addr, unsigned long long bits)
+{
+	if(bits) {
+		const uint2 v = ldsU2(addr);
+		stsU2(addr, make_uint2(v.x | uint32_t(bits), v.y | uint32_t(bits >> 32)));
+	}
+}
+
 // command + forwarded pointers + tag of one (drawable, lod[, item])
 __device__ __forceinline__ void writeCommandRecord(const CullArgs& A, uint32_t ci, uint32_t indexCount, uint32_t instanceCount,
                                                    uint32_t firstIndex, uint32_t firstInstance, uint32_t d, uint32_t lod,

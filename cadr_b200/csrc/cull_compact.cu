@@ -53,60 +53,40 @@ __device__ __forceinline__ void writeWorkItem(WorkItem* item, uint64_t mats, uin
 	st_u8(w + 96, p0, p1);
 }
 
-// FUSED = true additionally does the work of processDrawablesKernel for the same drawable (handle resolve + Tier R
-// records), so the drawable list is read once per frame and the indirect / pointers records are not re-read.
-template<int LEVEL, bool FUSED>
-__global__ void __launch_bounds__(CS_THREADS)
-cullSmallKernel(const __grid_constant__ CullArgs A)
+__device__ __forceinline__ void cpAsync16(uint32_t dstSmem, const uint8_t* src)
 {
-	__shared__ uint32_t sChunkTot[CS_THREADS / 32];
-	__shared__ uint32_t sGroupTot[CS_THREADS / 32];
-	__shared__ uint32_t sChunkBase;
-	__shared__ uint32_t sMedTot[CS_THREADS / 32];
-	__shared__ uint32_t sMedBase;
-	__shared__ uint32_t sDomSet;
-	__shared__ unsigned long long sDomBase;
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dstSmem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 
+// Scratch of one CTA of the thread-per-drawable kernels (block-aggregated reservations).
+struct SmallShared {
+	uint32_t chunkTot[CS_THREADS / 32];
+	uint32_t groupTot[CS_THREADS / 32];
+	uint32_t medTot[CS_THREADS / 32];
+	uint32_t chunkBase;
+	uint32_t medBase;
+	uint32_t domSet;
+	unsigned long long domBase;
+};
+
+// Everything the thread-per-drawable kernels do once a drawable's records are known: evaluate a short list, queue a
+// longer one, reserve the output ranges block-aggregated, emit.  Shared by cullSmallKernel (direct loads) and
+// cullSmallStagedKernel (records, culling data and the first matrix staged through shared memory); `firstMatrix()`
+// returns matrix 0 of the drawable's list.  Must be called by all threads of the CTA (barriers inside).
+template<int LEVEL, bool FUSED, int THREADS = CS_THREADS, typename FirstMatrix>
+__device__ __forceinline__ void smallListsBody(const CullArgs& A, SmallShared& sh, const uint32_t d, const bool valid, uint32_t N,
+                                               const uint4 ca, const uint4 cb, const uint4 cc, const uint4 p0, const uint4 p1,
+                                               const uint64_t psBaseResolved, FirstMatrix firstMatrix)
+{
+	uint32_t (&sChunkTot)[CS_THREADS / 32] = sh.chunkTot;
+	uint32_t (&sGroupTot)[CS_THREADS / 32] = sh.groupTot;
+	uint32_t (&sMedTot)[CS_THREADS / 32] = sh.medTot;
+	uint32_t& sChunkBase = sh.chunkBase;
+	uint32_t& sMedBase = sh.medBase;
+	uint32_t& sDomSet = sh.domSet;
+	unsigned long long& sDomBase = sh.domBase;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t d = blockIdx.x * CS_THREADS + tid;
-	const bool valid = d < A.n;
-
-	uint32_t N = 0;
-	uint4 p0 = make_uint4(0, 0, 0, 0), p1 = p0;
-	uint64_t psBaseResolved = 0;
-	// the culling record does not depend on anything resolved below: requested first, so that its DRAM latency
-	// overlaps the handle walk instead of following it (one round trip less in the per-drawable chain)
-	uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, cc = ca;
-	if(valid) {
-		ca = ldg_stream_u4(A.cullData + 3ull * d); cb = ldg_stream_u4(A.cullData + 3ull * d + 1); cc = ldg_stream_u4(A.cullData + 3ull * d + 2);
-		if constexpr(!FUSED) {
-			p0 = ldg_stream_u4(A.pointers + 2ull * d);
-			p1 = ldg_stream_u4(A.pointers + 2ull * d + 1);
-		}
-	}
-	if constexpr(FUSED) {
-		if(valid) {
-			// processDrawables.comp main() :92-113 for this drawable (see process_drawables.cu)
-			const uint4* rec = reinterpret_cast<const uint4*>(A.drawableList) + size_t(d) * 3;
-			const uint4 ra = ldg_stream_u4(rec), rb = ldg_stream_u4(rec + 1), rc = ldg_stream_u4(rec + 2);
-			const uint64_t ml = lookupHandle<LEVEL>(A.root, uint64_t(rb.x) | (uint64_t(rb.y) << 32));
-			const uint64_t psb = lookupHandle<LEVEL>(A.root, uint64_t(rc.x) | (uint64_t(rc.y) << 32));
-			const uint64_t vd = lookupHandle<LEVEL>(A.root, uint64_t(ra.x) | (uint64_t(ra.y) << 32));
-			const uint64_t id = lookupHandle<LEVEL>(A.root, uint64_t(ra.z) | (uint64_t(ra.w) << 32));
-			const uint64_t dd = lookupHandle<LEVEL>(A.root, uint64_t(rb.z) | (uint64_t(rb.w) << 32));
-			N = ldg_u32(ml);
-			const uint32_t psCount = ldg_u32(psb + rc.z), psFirst = ldg_u32(psb + rc.z + 4);
-			p0 = make_uint4(uint32_t(vd), uint32_t(vd >> 32), uint32_t(id), uint32_t(id >> 32));
-			p1 = make_uint4(uint32_t(ml), uint32_t(ml >> 32), uint32_t(dd), uint32_t(dd >> 32));
-			psBaseResolved = psb;
-			st_stream_u4(const_cast<uint4*>(A.indirect) + d, make_uint4(psCount, N, psFirst, 0u));
-			st_stream_u4(const_cast<uint4*>(A.pointers) + 2ull * d, p0);
-			st_stream_u4(const_cast<uint4*>(A.pointers) + 2ull * d + 1, p1);
-		}
-	}
-	else {
-		if(valid) N = ldg_stream_u4(A.indirect + d).y;  // IndirectData.instanceCount == ml.numMatrices
-	}
 
 	// ---- per-drawable records (needed by both paths) -------------------------------------------------
 	uint32_t psOff[3] = {0, 0, 0};
@@ -170,7 +150,7 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 	if(small) {
 		const uint8_t* mats = reinterpret_cast<const uint8_t*>(matrixList) + CADR_MATRIX_LIST_HEADER_BYTES;
 		for(uint32_t j = 0; j < N; j++) {
-			Mat m = loadMat(mats + 64ull * j);
+			Mat m = (j == 0) ? firstMatrix() : loadMat(mats + 64ull * j);
 			bool nb;
 			int lod = evalInstance(m, L, A.plane, A.eye, nb);
 			nearCount += nb ? 1u : 0u;
@@ -196,11 +176,11 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 	if(tid == 0) {
 		uint32_t tot = 0;
 #pragma unroll
-		for(int w = 0; w < CS_THREADS / 32; w++) tot += sChunkTot[w];
+		for(int w = 0; w < THREADS / 32; w++) tot += sChunkTot[w];
 		sChunkBase = tot ? atomicAdd(&A.hdr->chunkCount, tot) : 0u;
 		uint32_t totM = 0;
 #pragma unroll
-		for(int w = 0; w < CS_THREADS / 32; w++) totM += sMedTot[w];
+		for(int w = 0; w < THREADS / 32; w++) totM += sMedTot[w];
 		sMedBase = totM ? atomicAdd(&A.hdr->medCount, totM) : 0u;
 	}
 
@@ -212,7 +192,7 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 	if(tid == 0) {
 		uint32_t tot = 0;
 #pragma unroll
-		for(int w = 0; w < CS_THREADS / 32; w++) tot += sGroupTot[w];
+		for(int w = 0; w < THREADS / 32; w++) tot += sGroupTot[w];
 		unsigned long long add = (unsigned long long)(tot & 0xfffu) | ((unsigned long long)(tot >> 12) << 32);
 		sDomBase = tot ? atomicAdd(A.counts + domSet, add) : 0ull;
 	}
@@ -297,6 +277,233 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 	}
 }
 
+// FUSED = true additionally does the work of processDrawablesKernel for the same drawable (handle resolve + Tier R
+// records), so the drawable list is read once per frame and the indirect / pointers records are not re-read.
+template<int LEVEL, bool FUSED>
+__global__ void __launch_bounds__(CS_THREADS)
+cullSmallKernel(const __grid_constant__ CullArgs A)
+{
+	__shared__ SmallShared sh;
+	const int tid = threadIdx.x;
+	const uint32_t d = blockIdx.x * CS_THREADS + tid;
+	const bool valid = d < A.n;
+	uint32_t N = 0;
+	uint4 p0 = make_uint4(0, 0, 0, 0), p1 = p0;
+	uint64_t psBaseResolved = 0;
+	// the culling record does not depend on anything resolved below: requested first, so that its DRAM latency
+	// overlaps the handle walk instead of following it (one round trip less in the per-drawable chain)
+	uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, cc = ca;
+	if(valid) {
+		ca = ldg_stream_u4(A.cullData + 3ull * d); cb = ldg_stream_u4(A.cullData + 3ull * d + 1); cc = ldg_stream_u4(A.cullData + 3ull * d + 2);
+		if constexpr(!FUSED) {
+			p0 = ldg_stream_u4(A.pointers + 2ull * d);
+			p1 = ldg_stream_u4(A.pointers + 2ull * d + 1);
+		}
+	}
+	if constexpr(FUSED) {
+		if(valid) {
+			// processDrawables.comp main() :92-113 for this drawable (see process_drawables.cu)
+			const uint4* rec = reinterpret_cast<const uint4*>(A.drawableList) + size_t(d) * 3;
+			const uint4 ra = ldg_stream_u4(rec), rb = ldg_stream_u4(rec + 1), rc = ldg_stream_u4(rec + 2);
+			const uint64_t ml = lookupHandle<LEVEL>(A.root, uint64_t(rb.x) | (uint64_t(rb.y) << 32));
+			const uint64_t psb = lookupHandle<LEVEL>(A.root, uint64_t(rc.x) | (uint64_t(rc.y) << 32));
+			const uint64_t vd = lookupHandle<LEVEL>(A.root, uint64_t(ra.x) | (uint64_t(ra.y) << 32));
+			const uint64_t id = lookupHandle<LEVEL>(A.root, uint64_t(ra.z) | (uint64_t(ra.w) << 32));
+			const uint64_t dd = lookupHandle<LEVEL>(A.root, uint64_t(rb.z) | (uint64_t(rb.w) << 32));
+			N = ldg_u32(ml);
+			const uint32_t psCount = ldg_u32(psb + rc.z), psFirst = ldg_u32(psb + rc.z + 4);
+			p0 = make_uint4(uint32_t(vd), uint32_t(vd >> 32), uint32_t(id), uint32_t(id >> 32));
+			p1 = make_uint4(uint32_t(ml), uint32_t(ml >> 32), uint32_t(dd), uint32_t(dd >> 32));
+			psBaseResolved = psb;
+			st_stream_u4(const_cast<uint4*>(A.indirect) + d, make_uint4(psCount, N, psFirst, 0u));
+			st_stream_u4(const_cast<uint4*>(A.pointers) + 2ull * d, p0);
+			st_stream_u4(const_cast<uint4*>(A.pointers) + 2ull * d + 1, p1);
+		}
+	}
+	else {
+		if(valid) N = ldg_stream_u4(A.indirect + d).y;  // IndirectData.instanceCount == ml.numMatrices
+	}
+
+	const uint8_t* m0 = reinterpret_cast<const uint8_t*>(uint64_t(p1.x) | (uint64_t(p1.y) << 32)) + CADR_MATRIX_LIST_HEADER_BYTES;
+	smallListsBody<LEVEL, FUSED, CS_THREADS>(A, sh, d, valid, N, ca, cb, cc, p0, p1, psBaseResolved, [m0]() { return loadMat(m0); });
+}
+
+#ifdef CADR_B200_EXPERIMENTS
+// ---------------------------------------------------------------------------------------------------
+// the fused pass (cadr_b200_process_and_cull) with the indirection staged through shared memory
+// ---------------------------------------------------------------------------------------------------
+// cullSmallKernel<FUSED> walks, per thread, a chain of three dependent DRAM round trips - the 48-byte record, the
+// handle-table leaf entry of its MatrixList, the line that holds numMatrices and the first matrix - with nothing of the
+// next drawables in flight: on BASELINE configs[1] (10 M drawables x 1 matrix) ncu showed DRAM 71 % busy, warps 48 %
+// active, long-scoreboard stalls 13.7 per issue: latency-bound, not bandwidth-bound.  Here a CTA is persistent and runs a
+// software pipeline over TILES of 256 drawables, every stage of the chain one tile further ahead, all of it staged in
+// shared memory by asynchronous copies (LDGSTS, no registers held):
+//
+//   tile k+3   records (12 KiB, contiguous) requested                               -> sRec[(k+3)&1]
+//   tile k+2   records arrived: handles read, the five table walks issued; their leaf entries (the DRAM part of a
+//              walk: one distinct entry per MatrixList) stay in flight IN REGISTERS while tile k is evaluated
+//   tile k+1   walk results consumed at the top of the iteration: Tier R pointers record written, PrimitiveSet fields
+//              requested, and the drawable's MatrixList line - header word + first matrix, 80 bytes - requested into the
+//              thread's own slot                                                     -> sMl[(k+1)&1];   culling records
+//              (12 KiB, contiguous) requested                                        -> sCull[(k+1)&1]
+//   tile k     everything is in shared memory: numMatrices and matrix 0 from sMl, culling record from sCull; evaluate,
+//              reserve block-aggregated, emit (smallListsBody: the same code as cullSmallKernel)
+//
+// so the three round trips of a drawable overlap the evaluation of the three tiles before it.  Two commit groups per
+// iteration in a fixed order (G_M: MatrixList lines; G_R: records + culling records), so the waits are constants:
+// records of k+2 = newest-but-one group when the walk starts (wait_group 1), lines and culling records of k = everything
+// but the two groups of this iteration when the evaluation starts (wait_group 2).  88 KiB of shared memory per CTA, two
+// CTAs per SM; per SM ~100 KiB of requests in flight, against ~44 KiB that Little's law asks for at 6.5 TB/s and ~1 us.
+// Lists of 2..32 matrices read matrices 1.. directly (only matrix 0 is staged); longer lists are queued as before.
+// Matrix 0 is requested together with the header word, i.e. BEFORE numMatrices is known: for an empty list these 64 bytes
+// lie behind the list's block.  They are only ever requested when they lie in the same 2 MiB page as the header (device
+// memory is mapped in granules of 2 MiB - cudaMalloc, the VMM API and IPC mappings alike - so the request cannot fault)
+// and never used when numMatrices is 0; a list whose first matrix starts a 2 MiB page reads it directly instead.
+constexpr uint32_t ST_ML_SLOT   = 80u;                           // 16 B header chunk {numMatrices, capacity, 0, 0} + matrix 0
+constexpr size_t stagedSmemBytes(int tile) { return size_t(tile) * (2 * 48 + 2 * 48 + 2 * ST_ML_SLOT); }   // 352 B per drawable: 88 KiB at 256
+// what the walk of one drawable resolves (processDrawables.comp:97-112), carried through the pipeline in registers
+struct Resolved { uint64_t ml, psb, vd, id, dd; };
+__device__ __forceinline__ bool matrixStaged(uint64_t ml) { return ((ml + CADR_MATRIX_LIST_HEADER_BYTES) & 0x1FFFFFull) != 0; }
+
+template<int LEVEL, int ST_TILE>       // ST_TILE = drawables per tile = threads per CTA: 256 (two CTAs per SM) or 128 (four)
+__global__ void __launch_bounds__(ST_TILE, 512 / ST_TILE)
+cullSmallStagedKernel(const __grid_constant__ CullArgs A)
+{
+	constexpr uint32_t ST_REC_BYTES = ST_TILE * 48u;                 // DrawableGpuData / cadr_drawable_cull_data of a tile
+	constexpr uint32_t ST_ML_BYTES  = ST_TILE * ST_ML_SLOT;
+	extern __shared__ __align__(128) uint8_t stSmem[];
+	__shared__ SmallShared sh;
+	const uint32_t tid = threadIdx.x;
+	const uint32_t sRec = smemAddr(stSmem), sCull = sRec + 2 * ST_REC_BYTES, sMl = sCull + 2 * ST_REC_BYTES;
+	const uint32_t numTiles = (A.n + ST_TILE - 1) / ST_TILE;
+	// this CTA's k-th tile; tiles past the end are empty (their stages issue nothing but still commit their groups)
+	auto tileBase = [&](uint32_t k) -> uint64_t { return (uint64_t(blockIdx.x) + uint64_t(k) * gridDim.x) * ST_TILE; };
+	auto tileCount = [&](uint32_t k) -> uint32_t { const uint64_t b = tileBase(k); return b >= A.n ? 0u : uint32_t(min(uint64_t(ST_TILE), A.n - b)); };
+
+	// 48-byte records of a tile are contiguous: thread t copies 16-byte chunks t, t + 256, t + 512
+	auto requestRecords = [&](const uint8_t* array, uint32_t dst, uint32_t k) {
+		const uint32_t chunks = tileCount(k) * 3u;
+		const uint8_t* src = array + tileBase(k) * 48ull;
+#pragma unroll
+		for(uint32_t c = 0; c < 3; c++)
+			if(c * ST_TILE + tid < chunks) cpAsync16(dst + (c * ST_TILE + tid) * 16u, src + (c * ST_TILE + tid) * 16ull);
+	};
+	// the five table walks of this thread's drawable of tile k (its record is in shared memory)
+	auto walk = [&](uint32_t k, uint32_t& psOffset) -> Resolved {
+		Resolved w = {0, 0, 0, 0, 0};
+		psOffset = 0;
+		if(tid < tileCount(k)) {
+			const uint32_t rec = sRec + (k & 1u) * ST_REC_BYTES + tid * 48u;
+			const uint4 ra = ldsU4(rec), rb = ldsU4(rec + 16u), rc = ldsU4(rec + 32u);
+			// the five walks level by level (the loads are pinned in program order: five independent loads per level, not
+			// five dependent chains one after the other)
+			const uint64_t h[5] = {uint64_t(rb.x) | (uint64_t(rb.y) << 32), uint64_t(rc.x) | (uint64_t(rc.y) << 32), uint64_t(ra.x) | (uint64_t(ra.y) << 32),
+			                       uint64_t(ra.z) | (uint64_t(ra.w) << 32), uint64_t(rb.z) | (uint64_t(rb.w) << 32)};
+			uint64_t t[5];
+#pragma unroll
+			for(int i = 0; i < 5; i++) t[i] = A.root;
+			if constexpr(LEVEL == 3) {
+#pragma unroll
+				for(int i = 0; i < 5; i++) t[i] = ldg_u64_pinned(t[i] + 8ull * uint32_t(h[i] >> 22));
+			}
+			if constexpr(LEVEL >= 2) {
+#pragma unroll
+				for(int i = 0; i < 5; i++) t[i] = ldg_u64_pinned(t[i] + 8ull * (LEVEL == 3 ? (uint32_t(h[i] >> 11) & 0x7ffu) : uint32_t(h[i] >> 11)));
+			}
+#pragma unroll
+			for(int i = 0; i < 5; i++) t[i] = ldg_u64_pinned(t[i] + 8ull * (LEVEL == 1 ? uint32_t(h[i]) : (uint32_t(h[i]) & 0x7ffu)));
+			w.ml = t[0]; w.psb = t[1]; w.vd = t[2]; w.id = t[3]; w.dd = t[4];
+			psOffset = rc.z;
+		}
+		return w;
+	};
+	// walk results of tile k are in: Tier R pointers record out, PrimitiveSet fields and the MatrixList line requested
+	auto requestLists = [&](uint32_t k, const Resolved& w, uint32_t psOffset, uint32_t& psCount, uint32_t& psFirst) {
+		psCount = psFirst = 0;
+		if(tid < tileCount(k)) {
+			const uint64_t d = tileBase(k) + tid;
+			const uint8_t* ml = reinterpret_cast<const uint8_t*>(w.ml);
+			const uint32_t slot = sMl + (k & 1u) * ST_ML_BYTES + tid * ST_ML_SLOT;
+			cpAsync16(slot, ml);                                       // {numMatrices, capacity, 0, 0}   MatrixList.h:54-59
+			if(matrixStaged(w.ml)) {
+#pragma unroll
+				for(uint32_t c = 0; c < 4; c++) cpAsync16(slot + 16u + c * 16u, ml + CADR_MATRIX_LIST_HEADER_BYTES + c * 16u);
+			}
+			st_stream_u4(const_cast<uint4*>(A.pointers) + 2ull * d, make_uint4(uint32_t(w.vd), uint32_t(w.vd >> 32), uint32_t(w.id), uint32_t(w.id >> 32)));
+			st_stream_u4(const_cast<uint4*>(A.pointers) + 2ull * d + 1, make_uint4(uint32_t(w.ml), uint32_t(w.ml >> 32), uint32_t(w.dd), uint32_t(w.dd >> 32)));
+			psCount = ldg_u32(w.psb + psOffset); psFirst = ldg_u32(w.psb + psOffset + 4);
+		}
+	};
+
+	// ---- prologue: establish what iteration 0 expects (walk of tile 1 in registers, lines + culling records of tile 0 and
+	// records of tile 2 requested)
+	requestRecords(A.drawableList, sRec, 0);
+	requestRecords(A.drawableList, sRec + ST_REC_BYTES, 1);
+	cpAsyncCommit();
+	asm volatile("cp.async.wait_group 0;" ::: "memory");
+	__syncthreads();
+	uint32_t psOffA, psOffB;
+	Resolved cur = walk(0, psOffA);            // tile k   (evaluated in this iteration)
+	Resolved nxt = walk(1, psOffB);            // tile k+1
+	uint32_t curPsCount, curPsFirst;
+	requestLists(0, cur, psOffA, curPsCount, curPsFirst);
+	cpAsyncCommit();                                                            // G_M
+	__syncthreads();                                                            // every thread has read sRec[0]
+	requestRecords(A.drawableList, sRec, 2);
+	requestRecords(reinterpret_cast<const uint8_t*>(A.cullData), sCull, 0);
+	cpAsyncCommit();                                                            // G_R
+
+	for(uint32_t k = 0; tileBase(k) < A.n; k++) {                               // uniform over the CTA
+		// ---- tile k+1: walk results (requested one iteration ago) -> lines requested ------------------------------
+		uint32_t nxtPsCount, nxtPsFirst;
+		requestLists(k + 1u, nxt, psOffB, nxtPsCount, nxtPsFirst);
+		cpAsyncCommit();                                                        // G_M of this iteration
+		// ---- tile k+2: records have arrived -> walks issued, leaf entries stay in flight in registers -------------
+		asm volatile("cp.async.wait_group 1;" ::: "memory");                    // everything but G_M above: records of k+2 are in
+		__syncthreads();
+		uint32_t psOffC;
+		const Resolved nx2 = walk(k + 2u, psOffC);
+		// ---- tile k+3 records, tile k+1 culling records requested --------------------------------------------------
+		// (slot (k+1)&1 of sRec was last read by the walk of tile k+1, one iteration ago; of sCull by the evaluation of
+		// tile k-1; barriers in between)
+		requestRecords(A.drawableList, sRec + ((k + 3u) & 1u) * ST_REC_BYTES, k + 3u);
+		requestRecords(reinterpret_cast<const uint8_t*>(A.cullData), sCull + ((k + 1u) & 1u) * ST_REC_BYTES, k + 1u);
+		cpAsyncCommit();                                                        // G_R of this iteration
+		// ---- tile k: evaluate ----------------------------------------------------------------------------------------
+		asm volatile("cp.async.wait_group 2;" ::: "memory");                    // all but this iteration's two groups
+		__syncthreads();
+		{
+			const uint32_t cnt = tileCount(k);
+			const bool valid = tid < cnt;
+			const uint32_t d = uint32_t(tileBase(k)) + tid;
+			const uint32_t slot = sMl + (k & 1u) * ST_ML_BYTES + tid * ST_ML_SLOT;
+			uint32_t N = 0;
+			uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, cc = ca;
+			uint4 p0 = ca, p1 = ca;
+			if(valid) {
+				const uint32_t rec = sCull + (k & 1u) * ST_REC_BYTES + tid * 48u;
+				ca = ldsU4(rec); cb = ldsU4(rec + 16u); cc = ldsU4(rec + 32u);
+				N = lds32(slot);                                                // ml.numMatrices   processDrawables.comp:103
+				p0 = make_uint4(uint32_t(cur.vd), uint32_t(cur.vd >> 32), uint32_t(cur.id), uint32_t(cur.id >> 32));
+				p1 = make_uint4(uint32_t(cur.ml), uint32_t(cur.ml >> 32), uint32_t(cur.dd), uint32_t(cur.dd >> 32));
+				st_stream_u4(const_cast<uint4*>(A.indirect) + d, make_uint4(curPsCount, N, curPsFirst, 0u));
+			}
+			const uint64_t ml = cur.ml;
+			smallListsBody<LEVEL, true, ST_TILE>(A, sh, d, valid, N, ca, cb, cc, p0, p1, cur.psb, [slot, ml]() {
+				if(!matrixStaged(ml)) return loadMat(reinterpret_cast<const uint8_t*>(ml) + CADR_MATRIX_LIST_HEADER_BYTES);
+				Mat m;
+				m.c0 = ldsF4(slot + 16u); m.c1 = ldsF4(slot + 32u); m.c2 = ldsF4(slot + 48u); m.c3 = ldsF4(slot + 64u);
+				return m;
+			});
+		}
+		cur = nxt; curPsCount = nxtPsCount; curPsFirst = nxtPsFirst;
+		nxt = nx2; psOffB = psOffC;
+	}
+	asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+#endif  // CADR_B200_EXPERIMENTS (cullSmallStagedKernel)
+
 // ---------------------------------------------------------------------------------------------------
 // lists longer than 32 matrices: persistent warps, one work item per warp at a time, pipelined across items
 // ---------------------------------------------------------------------------------------------------
@@ -325,24 +532,6 @@ __device__ __forceinline__ uint4 loadItemWord(const CullArgs& A, uint32_t item, 
 	uint4 w = make_uint4(0u, 0u, 0u, 0u);     // count 0 = no item
 	if(item < total && lane < 8) w = ldg_stream_u4(reinterpret_cast<const uint4*>(A.items + item) + lane);
 	return w;
-}
-
-// shared-memory accessors on 32-bit shared-window addresses (no generic-address conversion in the loops)
-__device__ __forceinline__ uint4 ldsU4(uint32_t addr)
-{
-	uint4 v;
-	asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-	return v;
-}
-__device__ __forceinline__ float4 ldsF4(uint32_t addr)
-{
-	float4 v;
-	asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-	return v;
-}
-__device__ __forceinline__ void stsU4(uint32_t addr, uint4 v)
-{
-	asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // 2-bit code per step in a lane-private 64-bit history (32 steps = one work item): 0 = culled, 1 + lod otherwise
@@ -428,36 +617,6 @@ constexpr uint32_t FL_STRIDE     = 144;                 // descriptor stride in 
                                                         // their own descriptor (emission) do not all hit the same banks
 constexpr uint32_t FL_WARP_BYTES = 32 * FL_STRIDE;      // 4.5 KiB per warp, 36 KiB per CTA
 static_assert(CADR_CULL_MEDIUM_LIST_MAX <= 64 && CADR_CULL_MEDIUM_LIST_MAX > CADR_CULL_SMALL_LIST_MAX, "one 64-bit mask per LOD; a step spans at most two items");
-
-__device__ __forceinline__ uint32_t lds32(uint32_t addr)
-{
-	uint32_t v;
-	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-	return v;
-}
-__device__ __forceinline__ uint2 ldsU2(uint32_t addr)
-{
-	uint2 v;
-	asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
-	return v;
-}
-
-__device__ __forceinline__ void stsU2(uint32_t addr, uint2 v)
-{
-	asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(addr), "r"(v.x), "r"(v.y) : "memory");
-}
-__device__ __forceinline__ unsigned long long ldsU64(uint32_t addr)
-{
-	const uint2 v = ldsU2(addr);
-	return (unsigned long long)v.x | ((unsigned long long)v.y << 32);
-}
-__device__ __forceinline__ void orMask(uint32_t addr, unsigned long long bits)
-{
-	if(bits) {
-		const uint2 v = ldsU2(addr);
-		stsU2(addr, make_uint2(v.x | uint32_t(bits), v.y | uint32_t(bits >> 32)));
-	}
-}
 
 // position of the run: the item that contains the first instance of a step, and that item's flat index range
 struct FlatPos { uint32_t item, start, end; };
@@ -785,11 +944,6 @@ constexpr int    LW_STAGE_BYTES = 32 * 64;
 constexpr size_t LW_WARP_BYTES  = LW_STAGES * LW_STAGE_BYTES + LW_DESCS * sizeof(WorkItem);   // 6.5 KiB
 constexpr size_t LW_SMEM_BYTES  = (CM_THREADS / 32) * LW_WARP_BYTES;          // 52 KiB per CTA, four CTAs per SM
 
-__device__ __forceinline__ void cpAsync16(uint32_t dstSmem, const uint8_t* src)
-{
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dstSmem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cpAsyncWaitAllBut(uint32_t pending)   // warp-uniform; the operand must be an immediate
 {
 	switch(pending) {
@@ -923,6 +1077,156 @@ cullListRingKernel(const __grid_constant__ CullArgs A)
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------
+// long lists, shared-memory ring + packed-fp32 pair evaluation (experiment variant 6)
+// ---------------------------------------------------------------------------------------------------
+// cullListRingKernel lifted the memory-side ceiling (C3 streams in 0.91 ms with the evaluation stubbed out, 0.96-0.98 ms
+// for the register kernel) but its copies and shared-memory reads made the complete kernel issue-bound (73 % of the
+// issue slots).  Here a stage holds 64 matrices (4 KiB): a lane evaluates matrices `lane` and `lane + 32` of the stage
+// TOGETHER with Blackwell's packed fp32 operations (evalInstancePair: FFMA2 / FADD2 / FMUL2 - each component the same
+// IEEE operation as the scalar code, bit-identical results), which halves the FP instruction count per instance, and
+// every per-step cost (waits, barriers, cursor bookkeeping, history update) is paid once per 64 matrices instead of 32.
+// Three stages of 4 KiB per warp, eight warps per CTA (100 KiB), two CTAs per SM: as many bytes in flight per SM as the
+// 2-KiB ring at four CTAs.  The lane's history holds 4 bits per step (two 2-bit codes); sub-step t = 2 * step + half
+// is matrix 32 t + lane of the item, so the tail (emitItem) is the one of the other kernels with twice the steps.
+constexpr int    L2_STAGES      = 3;
+constexpr int    L2_STAGE_BYTES = 64 * 64;
+constexpr size_t L2_WARP_BYTES  = L2_STAGES * L2_STAGE_BYTES + LW_DESCS * sizeof(WorkItem);   // 12.5 KiB
+constexpr size_t L2_SMEM_BYTES  = (CM_THREADS / 32) * L2_WARP_BYTES;                          // 100 KiB per CTA
+static_assert(2 * L2_SMEM_BYTES + 2048 <= 227 * 1024, "two CTAs per SM");
+static_assert(CADR_CULL_WORK_ITEM_INSTANCES <= 16 * 64, "16 steps of 4 bits in a 64-bit history");
+
+__global__ void __launch_bounds__(CM_THREADS, 2)
+cullListRingPairKernel(const __grid_constant__ CullArgs A)
+{
+	extern __shared__ __align__(128) uint8_t lwSmem[];
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t ring = smemAddr(lwSmem) + (threadIdx.x >> 5) * uint32_t(L2_WARP_BYTES);   // shared-window address of my ring
+	const uint32_t ringEnd = ring + L2_STAGES * L2_STAGE_BYTES;
+	const uint32_t descs = ringEnd;                                                         // LW_DESCS x 128 bytes
+	const unsigned FULL = 0xffffffffu;
+	// writer: chunk g = k*32 + lane -> matrix k*8 + (lane >> 2), column lane & 3, swizzle ((lane >> 3) & 3)
+	const uint32_t wrOff = (lane >> 2) * 64u + (((lane & 3u) ^ ((lane >> 3) & 3u)) << 4);
+	// reader: matrices `lane` and `lane + 32`; column c sits at slot c ^ ((lane >> 1) & 3), i.e. at (stage + rdOff) ^ (c << 4)
+	const uint32_t rdOff = lane * 64u + (((lane >> 1) & 3u) << 4);
+
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");    // cullMediumKernel may move in as soon as CTAs retire
+	uint32_t total, totalM;
+	bool overflow;
+	queueExtents(A, total, totalM, overflow);
+	if(overflow && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&A.hdr->status, CADR_CULL_STATUS_CHUNK_OVERFLOW);
+	const uint32_t numWarps = gridDim.x * (CM_THREADS / 32);
+	uint32_t batch = total / (numWarps * 16u);
+	batch = batch < 1u ? 1u : (batch > 8u ? 8u : batch);
+
+	// item indices: A (evaluated), B, C (descriptors in shared memory), D (descriptor in flight in dIn), E (being claimed)
+	uint32_t rNext = 0, rEnd = 0;      // lane 0: claimed index range
+	uint32_t iA, iB, iC, iD;
+	{
+		const uint32_t first = batch < 4u ? 4u : batch;
+		uint32_t r = 0;
+		if(lane == 0) { r = atomicAdd(&A.hdr->chunkCursor, first); rNext = r + 4u; rEnd = r + first; }
+		r = __shfl_sync(FULL, r, 0);
+		iA = r; iB = r + 1u; iC = r + 2u; iD = r + 3u;
+	}
+	uint32_t seq = 0;                  // warp-local sequence number of A; its descriptor slot is seq & 3
+	{
+		const uint4 a = loadItemWord(A, iA, total, lane), b = loadItemWord(A, iB, total, lane);
+		if(lane < 8) { stsU4(descs + lane * 16u, a); stsU4(descs + 128u + lane * 16u, b); }
+	}
+	uint4 dIn = loadItemWord(A, iC, total, lane);     // stored to the ring at the top of the first iteration
+
+	// fetch cursor: fSeq = item it reads from (seq - 1: none yet), fRemain matrices of it not fetched yet, fSrc this
+	// lane's source of the next stage, fDst / eAddr the ring slots written / read next
+	uint32_t fSeq = 0xffffffffu, fRemain = 0, inFlight = 0, fDst = ring, eAddr = ring;
+	const uint8_t* fSrc = nullptr;
+
+	while(iA < total) {
+		// ---- descriptor pipeline: C has arrived, request D, claim E ------------------------------------
+		if(lane < 8) stsU4(descs + ((seq + 2u) & 3u) * 128u + lane * 16u, dIn);
+		dIn = loadItemWord(A, iD, total, lane);
+		uint32_t iE = 0;
+		if(lane == 0) {
+			if(rNext < rEnd) iE = rNext++;
+			else { iE = atomicAdd(&A.hdr->chunkCursor, batch); rNext = iE + 1u; rEnd = iE + batch; }
+		}
+		__syncwarp();
+		const uint32_t dA = descs + (seq & 3u) * 128u;
+		const uint4 a0 = ldsU4(dA), a1 = ldsU4(dA + 16u), a2 = ldsU4(dA + 32u), a3 = ldsU4(dA + 48u);
+		const uint4 b0 = ldsU4(descs + ((seq + 1u) & 3u) * 128u), c0 = ldsU4(descs + ((seq + 2u) & 3u) * 128u);
+		const uint32_t N = a0.z;
+		LodInfo L;
+		L.lodCount = a1.z;
+		L.sphere = make_float4(__uint_as_float(a2.x), __uint_as_float(a2.y), __uint_as_float(a2.z), __uint_as_float(a2.w));
+		L.thr0 = __uint_as_float(a3.x); L.thr1 = __uint_as_float(a3.y);
+
+		unsigned long long hist = 0;       // 4 bits per step, newest at the top: two codes, 0 = culled, 1 + lod otherwise
+		uint32_t nb = 0, steps = 0;
+		for(uint32_t left = N; left != 0; left = (left > 64u) ? left - 64u : 0u) {
+			// ---- top up the ring: the fetch cursor runs ahead through A, B and C -------------------------
+			while(inFlight < uint32_t(L2_STAGES)) {
+				if(fRemain == 0) {                              // (rare) move the cursor to the next item
+					const uint32_t which = fSeq + 1u - seq;     // 0 = A, 1 = B, 2 = C
+					if(which > 2u) break;                       // beyond C: not known yet
+					const uint4 w = (which == 0u) ? a0 : (which == 1u) ? b0 : c0;
+					if(w.z == 0u) break;                        // there is no further item
+					fSeq++; fRemain = w.z;
+					fSrc = reinterpret_cast<const uint8_t*>(uint64_t(w.x) | (uint64_t(w.y) << 32)) + 16u * lane;
+				}
+				const uint32_t dst = fDst + wrOff;
+				if(fRemain >= 64u) {
+#pragma unroll
+					for(uint32_t k = 0; k < 8; k++) cpAsync16(dst + k * 512u, fSrc + k * 512u);
+					fRemain -= 64u;
+				}
+				else {
+					const uint32_t chunks = fRemain * 4u;       // 16-byte chunks of a ragged last stage
+#pragma unroll
+					for(uint32_t k = 0; k < 8; k++)
+						if(k * 32u + lane < chunks) cpAsync16(dst + k * 512u, fSrc + k * 512u);
+					fRemain = 0;
+				}
+				cpAsyncCommit();
+				fSrc += L2_STAGE_BYTES;
+				fDst += L2_STAGE_BYTES; if(fDst == ringEnd) fDst = ring;
+				inFlight++;
+			}
+			// ---- the oldest stage in flight is this step ----------------------------------------------
+			if(inFlight == 3u)      asm volatile("cp.async.wait_group 2;" ::: "memory");
+			else if(inFlight == 2u) asm volatile("cp.async.wait_group 1;" ::: "memory");
+			else                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+			__syncwarp();                      // chunks of my matrices were copied by other lanes
+			uint32_t code = 0;
+			if(lane < left) {                  // (lane + 32 < left implies lane < left)
+				const uint32_t ma = eAddr + rdOff, mb = ma + 2048u;
+				Mat m, n;
+				m.c0 = ldsF4(ma); m.c1 = ldsF4(ma ^ 16u); m.c2 = ldsF4(ma ^ 32u); m.c3 = ldsF4(ma ^ 48u);
+				n.c0 = ldsF4(mb); n.c1 = ldsF4(mb ^ 16u); n.c2 = ldsF4(mb ^ 32u); n.c3 = ldsF4(mb ^ 48u);
+				const bool second = lane + 32u < left;   // otherwise n is stale ring contents: evaluated, result dropped
+				int lodA, lodB;
+				bool nearA, nearB;
+				if(A.diagNoEval) { lodA = (m.c0.x == 12345.f && m.c2.x == 1.f) ? 0 : -1; lodB = (n.c0.x == 12345.f && n.c2.x == 1.f) ? 0 : -1; nearA = nearB = false; }
+				else evalInstancePair(m, n, L, A.plane, A.eye, lodA, lodB, nearA, nearB);
+				code = uint32_t(lodA + 1) | (second ? uint32_t(lodB + 1) << 2 : 0u);
+				nb += (nearA ? 1u : 0u) + ((second && nearB) ? 1u : 0u);
+			}
+			hist = (hist >> 4) | ((unsigned long long)code << 60);
+			steps++;
+			__syncwarp();                      // every lane has read the slot before any lane refills it
+			eAddr += L2_STAGE_BYTES; if(eAddr == ringEnd) eAddr = ring;
+			inFlight--;
+		}
+		if(steps) hist >>= (64u - 4u * steps);      // sub-step t = 2 * step + half now sits at bits [2t, 2t + 1]
+
+		emitItem(A, hist, 2u * steps, nb, dA, a0, a1, lane);
+		__syncwarp();       // A's descriptor slot is rewritten two iterations from now; keep the warp together
+
+		// ---- advance the pipeline: B becomes A ---------------------------------------------------------------
+		seq++;
+		iA = iB; iB = iC; iC = iD; iD = __shfl_sync(FULL, iE, 0);
+	}
+}
+
 #endif  // CADR_B200_EXPERIMENTS
 
 // The product library has ONE path (cullSmallKernel -> cullListWarpKernel -> cullMediumKernel) and reads no environment.
@@ -1007,10 +1311,31 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 	// cullListWarpKernel instead of cullMediumKernel); 4 = every list longer than 32 matrices in the one queue (the
 	// state before the medium path existed), for A/B measurements
 	const int variant = cullVariant();
-	A.medMax = ((variant == 2 || variant == 5) && p.chunkCapacity) ? CADR_CULL_MEDIUM_LIST_MAX : 0u;
+	A.medMax = ((variant == 2 || variant == 5 || variant == 6) && p.chunkCapacity) ? CADR_CULL_MEDIUM_LIST_MAX : 0u;
 
 	uint32_t gridS = (p.numDrawables + CS_THREADS - 1) / CS_THREADS;
 	ctx->timeBegin(KS_CULL_SMALL, s);
+#ifdef CADR_B200_EXPERIMENTS
+	// A/B: the fused pass with the indirection staged through shared memory (cullSmallStagedKernel): parity-green, but slower
+	// than the direct-load kernel on every shape measured so far (profiles/r02c_*), so it is not in the product library
+	if(const char* v = std::getenv("CADR_B200_SMALL_STAGED"); fused && v && v[0] >= '1') {
+		const bool small = v[0] == '2';            // 1: tiles of 256, two CTAs per SM; 2: tiles of 128, four CTAs per SM
+		const int tile = small ? 128 : 256;
+		const void* fn = nullptr;
+		switch(p.handleLevel * 2 + (small ? 1 : 0)) {
+		case 2: fn = (const void*)cullSmallStagedKernel<1, 256>; break;  case 3: fn = (const void*)cullSmallStagedKernel<1, 128>; break;
+		case 4: fn = (const void*)cullSmallStagedKernel<2, 256>; break;  case 5: fn = (const void*)cullSmallStagedKernel<2, 128>; break;
+		case 6: fn = (const void*)cullSmallStagedKernel<3, 256>; break;  default: fn = (const void*)cullSmallStagedKernel<3, 128>; break;
+		}
+		CADR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(stagedSmemBytes(tile))));
+		uint32_t gridP = uint32_t(ctx->smCount) * uint32_t(512 / tile);
+		const uint32_t tiles = (p.numDrawables + tile - 1) / tile;
+		if(gridP > tiles) gridP = tiles;
+		void* args[] = {(void*)&A};
+		CADR_CUDA(cudaLaunchKernel(fn, dim3(gridP), dim3(tile), args, stagedSmemBytes(tile), s));
+	}
+	else
+#endif
 	if(fused) {
 		switch(p.handleLevel) {
 		case 1: cullSmallKernel<1, true><<<gridS, CS_THREADS, 0, s>>>(A); break;
@@ -1046,6 +1371,22 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 			if(int r = launchCullVariant(ctx, A, variant, p.chunkCapacity, s)) return r;
 		}
 		else if(variant == 5) cullListWarpKernel<true><<<gridL, CM_THREADS, 0, s>>>(A);
+		else if(variant == 6) {
+			CADR_CUDA(cudaFuncSetAttribute(cullListRingPairKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L2_SMEM_BYTES)));
+			uint32_t grid2 = uint32_t(ctx->smCount) * 2u;
+			if(grid2 > need) grid2 = need;
+			cullListRingPairKernel<<<grid2, CM_THREADS, L2_SMEM_BYTES, s>>>(A);
+			if(A.medMax) {
+				cudaLaunchConfig_t cfg = {};
+				cfg.gridDim = dim3(gridL); cfg.blockDim = dim3(CM_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+				cudaLaunchAttribute attr[1];
+				attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+				attr[0].val.programmaticStreamSerializationAllowed = 1;
+				cfg.attrs = attr; cfg.numAttrs = 1;
+				CADR_CUDA(cudaLaunchKernelEx(&cfg, cullMediumKernel, A));
+				ctx->launches++;
+			}
+		}
 		else
 #endif
 		{

@@ -36,6 +36,33 @@ __global__ void waitPeersKernel(const unsigned long long* flags, uint32_t world,
 	}
 }
 
+// Renderer-side pull of the survivors' instance-index runs (the exchange that is NOT free).  One CTA column
+// per (rank, range): count from the counters that rank published, source = that rank's instance-index buffer through
+// its peer mapping, destination = the same offsets inside this GPU's gathered index buffer (so firstInstance of the
+// gathered commands stays valid against `dst + rank * instCapacity`).  128-bit loads where the run is aligned.
+__global__ void pullInstancesKernel(const __grid_constant__ cadr_exchange_pull P)
+{
+	const uint32_t r = blockIdx.y / P.numRanges, s = blockIdx.y % P.numRanges;
+	if(r == P.rank && !P.includeLocal) return;
+	const unsigned long long packed = reinterpret_cast<const unsigned long long*>(P.gatheredCounters + uint64_t(r) * P.countersBytes + sizeof(cadr_cull_header))[s];
+	const uint32_t count = uint32_t(packed >> 32);
+	if(count == 0) return;
+	const uint4 reg = reinterpret_cast<const uint4*>(P.regions[r])[s];       // cmdBase, cmdCap, instBase, instCap
+	const uint32_t n = count < reg.w ? count : reg.w;
+	const uint32_t* src = reinterpret_cast<const uint32_t*>(P.peerInst[r]) + reg.z;
+	uint32_t* dst = reinterpret_cast<uint32_t*>(P.gatheredInst) + uint64_t(r) * P.instCapacity + reg.z;
+	// head up to the first 16-byte boundary (source and destination have the same misalignment: both start at element
+	// reg.z of 256-byte-aligned buffers), body as uint4, tail
+	const uint32_t head = min(n, (4u - (reg.z & 3u)) & 3u);
+	const uint32_t vec = (n - head) / 4u, tailStart = head + vec * 4u;
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+	if(t < head) dst[t] = src[t];
+	const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+	uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+	for(uint32_t i = t; i < vec; i += stride) d4[i] = ldg_stream_u4(s4 + i);
+	if(t < n - tailStart) dst[tailStart + t] = src[tailStart + t];
+}
+
 }  // namespace cadr
 
 using namespace cadr;
@@ -140,6 +167,32 @@ int cadr_b200_exchange_wait(cadr_ctx* ctx, const cadr_exchange_sync* sync, cadr_
 	if(!sync->peerFlags[sync->rank]) return setError(CADR_E_LOGIC, "exchange_wait: local flag array missing");
 	cudaStream_t s = ctx->pick(stream);
 	waitPeersKernel<<<1, 32, 0, s>>>(reinterpret_cast<const unsigned long long*>(sync->peerFlags[sync->rank]), sync->world, sync->frameSeq);
+	ctx->launches++;
+	CADR_CUDA(cudaGetLastError());
+	return CADR_OK;
+}
+
+int cadr_b200_exchange_pull_instances(cadr_ctx* ctx, const cadr_exchange_pull* pull, cadr_stream stream)
+{
+	REQUIRE_DEVICE_X(ctx);
+	if(!pull) return setError(CADR_E_LOGIC, "exchange_pull_instances: null argument");
+	if(pull->world < 1 || pull->world > CADR_MAX_PEERS || pull->rank >= pull->world)
+		return setError(CADR_E_LOGIC, "exchange_pull_instances: bad world/rank (%u/%u)", pull->rank, pull->world);
+	if(pull->numRanges == 0) return CADR_OK;
+	if(!pull->gatheredCounters || !pull->gatheredInst || (pull->gatheredInst & 15) || (pull->countersBytes & 7))
+		return setError(CADR_E_LOGIC, "exchange_pull_instances: gathered buffers missing or misaligned");
+	for(uint32_t r = 0; r < pull->world; r++)
+		if(!pull->regions[r] || !pull->peerInst[r] || (pull->regions[r] & 15) || (pull->peerInst[r] & 15))
+			return setError(CADR_E_LOGIC, "exchange_pull_instances: buffers of rank %u missing or misaligned", r);
+	if((pull->instCapacity & 3) != 0)
+		return setError(CADR_E_LOGIC, "exchange_pull_instances: instCapacity must be a multiple of 4 elements");
+	cudaStream_t s = ctx->pick(stream);
+	// enough CTAs per (rank, range) column to keep many 16-byte requests in flight over NVLink
+	const uint32_t columns = pull->world * pull->numRanges;
+	uint32_t perColumn = (uint32_t(ctx->smCount) * 8u + columns - 1) / columns;
+	if(perColumn < 1) perColumn = 1;
+	if(perColumn > 64) perColumn = 64;
+	pullInstancesKernel<<<dim3(perColumn, columns), 256, 0, s>>>(*pull);
 	ctx->launches++;
 	CADR_CUDA(cudaGetLastError());
 	return CADR_OK;

@@ -148,8 +148,11 @@ class PeerExchange:
         """regions / inst_out / arena (optional, all or none): this rank's region table [S,4] u32, its instance-index
         buffer and the arena that holds its geometry and matrix lists.  They are exported to the peers as well, which
         makes every rank's result CONSUMABLE on any GPU (consume_params): commands and counters are local copies, instance
-        indices and matrices are read through the peer mappings on demand (mitigation iii).  first_drawable =
-        position of this rank's first drawable in the whole flattened list (the tag's drawable index is slice-relative)."""
+        indices and matrices are read through the peer mappings on demand (mitigation iii).  inst_out may be a
+        pair of buffers: begin_frame then alternates them by frame parity like the gathered arrays, so that a peer may
+        still read frame k's runs while this rank already culls frame k + 1 (it cannot get further ahead: it cannot pass
+        the wait of frame k + 1 before every peer has published it).  first_drawable = position of this rank's first
+        drawable in the whole flattened list (the tag's drawable index is slice-relative)."""
         import ctypes as C
         from . import _capi
         self.ctx, self.group = ctx, group
@@ -195,14 +198,15 @@ class PeerExchange:
                 raise ValueError("PeerExchange: regions, inst_out and arena go together")
             reg = np.zeros((self.num_ranges, 4), np.uint32)
             reg[:regions.shape[0]] = regions
+            self.inst_sets = [int(a) for a in (inst_out if isinstance(inst_out, (list, tuple)) else [inst_out])]
             mine = dict(regions=reg, first=int(first_drawable), arena=int(arena),
-                        inst=ctx.ipc_export_range(inst_out), mem=ctx.ipc_export_range(arena))
+                        inst=[ctx.ipc_export_range(a) for a in self.inst_sets], mem=ctx.ipc_export_range(arena))
             everyone = [None] * self.world
             dist.all_gather_object(everyone, mine, group=group)
             self.first_drawable = [e["first"] for e in everyone]
             self.peer_regions = [e["regions"] for e in everyone]
             self.regions_dev = []                  # [rank] -> device copy of that rank's region table
-            self.peer_inst = []                    # [rank] -> its instance-index buffer as mapped here
+            self.peer_inst = []                    # [rank] -> its instance-index buffer(s) as mapped here (one, or one per frame parity)
             self.peer_delta = []                   # [rank] -> (its arena as mapped here) - (address on the owner), mod 2^64
             opened = {}                            # one mapping per exported allocation (two buffers may share one)
 
@@ -218,9 +222,9 @@ class PeerExchange:
                 ctx.memcpy_h2d(a, np.ascontiguousarray(e["regions"]))
                 self.regions_dev.append(a)
                 if r == self.rank:
-                    self.peer_inst.append(int(inst_out)); self.peer_delta.append(0)
+                    self.peer_inst.append(list(self.inst_sets)); self.peer_delta.append(0)
                 else:
-                    self.peer_inst.append(open_(e["inst"]))
+                    self.peer_inst.append([open_(x) for x in e["inst"]])
                     self.peer_delta.append((open_(e["mem"]) - e["arena"]) & 0xFFFFFFFFFFFFFFFF)
             self.digests = ctx.arena_alloc(max(16 * self.num_ranges, 256))
             ctx.sync()
@@ -234,6 +238,13 @@ class PeerExchange:
         for r in range(self.world):
             s = self.peer[r]["sets"][k]
             params.exchangeCmd[r], params.exchangePtr[r], params.exchangeTag[r] = s["cmd"], s["ptr"], s["tag"]
+        if self.consumable and len(self.inst_sets) == 2:
+            params.instOut = self.inst_sets[k]
+
+    def inst_of(self, r: int) -> int:
+        """Rank r's instance-index buffer of the current frame as mapped on this GPU."""
+        bufs = self.peer_inst[r]
+        return bufs[self.frame & 1] if len(bufs) == 2 else bufs[0]
 
     def _sync(self, local_counters: int):
         s = self._capi.ExchangeSync()
@@ -263,10 +274,11 @@ class PeerExchange:
         cnt = out["counters"].reshape(self.world, self.counters_bytes)[:, 64:].copy().view(np.uint64)
         return dict(cmd=out["cmd"].view(np.uint32).reshape(-1, 5), ptr=out["ptr"].view(np.uint64).reshape(-1, 4),
                     tag=out["tag"].view(np.uint32).reshape(-1, 2), counts=cnt,
+                    counters_raw=out["counters"].reshape(self.world, self.counters_bytes),
                     status=out["counters"].reshape(self.world, self.counters_bytes)[:, :4].copy().view(np.uint32)[:, 0])
 
     # -- consuming any rank's result on this GPU ----------------------------------------------------------------------
-    def consume_params(self, r: int):
+    def consume_params(self, r: int, inst_override: int | None = None):
         """cadr_cull_params describing rank r's result of the current frame AS SEEN FROM THIS GPU: commands, pointers and
         tags in slot r of the local gathered arrays, the counters rank r published, rank r's region table, and its
         instance indices + geometry / matrix lists through the peer mappings (addressDelta translates the addresses the
@@ -280,14 +292,15 @@ class PeerExchange:
         p.cmdOut, p.ptrOut, p.tagOut = st["cmd"] + 20 * slot, st["ptr"] + 32 * slot, st["tag"] + 8 * slot
         p.counters = st["counters"] + r * self.counters_bytes
         p.stateSetRegions = self.regions_dev[r]
-        p.instOut = self.peer_inst[r]
+        p.instOut = self.inst_of(r) if inst_override is None else inst_override
         p.addressDelta = self.peer_delta[r]
         return p
 
-    def consume(self, r: int, stream: int = 0) -> tuple[int, int]:
+    def consume(self, r: int, stream: int = 0, pulled: bool = False) -> tuple[int, int]:
         """Walk EVERY range of rank r's result on this GPU the way the reference's vertex shader would
-        (cadr_b200_consume_check_culled; shader.vert:99-123) -> (digest, fetches), summed over the ranges."""
-        p = self.consume_params(r)
+        (cadr_b200_consume_check_culled; shader.vert:99-123) -> (digest, fetches), summed over the ranges.
+        pulled=True reads the instance indices from the local copies made by pull_instances instead of the peer mapping."""
+        p = self.consume_params(r, self.gathered_inst + 4 * r * self.inst_cap if pulled else None)
         reg = self.peer_regions[r]
         live = [s for s in range(reg.shape[0]) if reg[s, 1]]
         for s in live:
@@ -297,6 +310,71 @@ class PeerExchange:
         self.ctx.sync(stream)
         d = out.reshape(-1, 2)[live] if live else np.zeros((0, 2), np.uint64)
         return int(d[:, 0].sum(dtype=np.uint64)), int(d[:, 1].sum(dtype=np.uint64))
+
+    # -- second stage (optional): the survivors' instance indices on the renderer GPU -------------------------------
+    def enable_pull(self, inst_capacity: int) -> None:
+        """Allocate this GPU's gathered instance-index buffer [world][capacity] (capacity = the largest rank's)."""
+        caps = [None] * self.world
+        dist.all_gather_object(caps, int(inst_capacity), group=self.group)
+        self.inst_cap = (max(caps) + 3) & ~3
+        self.gathered_inst = self.ctx.arena_alloc(max(self.world * self.inst_cap * 4, 256))
+
+    def pull_instances(self, stream: int = 0, include_local: bool = False) -> None:
+        """After end_frame: copy every peer's compacted instance-index runs of the current frame into gathered_inst
+        (cadr_b200_exchange_pull_instances).  Rank r's commands then index gathered_inst + r * inst_cap * 4."""
+        p = self._capi.ExchangePull()
+        p.world, p.rank, p.numRanges, p.countersBytes = self.world, self.rank, self.num_ranges, self.counters_bytes
+        p.gatheredCounters = self.local[self.frame & 1]["counters"]
+        p.gatheredInst, p.instCapacity, p.includeLocal = self.gathered_inst, self.inst_cap, int(include_local)
+        for r in range(self.world):
+            p.regions[r], p.peerInst[r] = self.regions_dev[r], self.inst_of(r)
+        self.ctx.exchange_pull_instances(p, stream)
+
+    # -- cross-check of the fused exchange over NCCL -------------------------------------------------------------------
+    def verify(self, device) -> dict:
+        """What the peer stores of the cull kernels left in THIS rank's gathered arrays against what every rank holds
+        for itself: each rank sends its own slot (commands, pointers, tags of every range in use, its counters) through
+        an NCCL all-gather, and the received copies must equal, byte for byte, the slots the fused exchange filled here.
+        -> dict(ok, commands, bytes, problems); identical on all ranks only if every rank's view is right, so callers
+        all-reduce `ok`."""
+        g = self.read()
+        cap, cb = self.cmd_cap, self.counters_bytes
+        me = slice(self.rank * cap, (self.rank + 1) * cap)
+        payload = np.concatenate([g["cmd"][me].reshape(-1).view(np.uint8), g["ptr"][me].reshape(-1).view(np.uint8),
+                                  g["tag"][me].reshape(-1).view(np.uint8), g["counters_raw"][self.rank].reshape(-1)])
+        mine = torch.from_numpy(np.ascontiguousarray(payload)).to(device)
+        everyone = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        got = everyone.cpu().numpy().reshape(self.world, -1)
+        problems, commands, nbytes = [], 0, 0
+        for r in range(self.world):
+            o = got[r]
+            cmd = o[:cap * 20].view(np.uint32).reshape(-1, 5)
+            ptr = o[cap * 20:cap * 52].view(np.uint64).reshape(-1, 4)
+            tag = o[cap * 52:cap * 60].view(np.uint32).reshape(-1, 2)
+            ctr = o[cap * 60:cap * 60 + cb]
+            if not np.array_equal(ctr, g["counters_raw"][r]):
+                problems.append(f"counters of rank {r} differ from what it holds itself")
+                continue
+            counts = ctr[64:].view(np.uint64)
+            reg = self.peer_regions[r] if self.consumable else None
+            for s_ in range(len(counts)):
+                c = int(counts[s_] & np.uint64(0xFFFFFFFF))
+                if c == 0:
+                    continue
+                if reg is None:
+                    raise RuntimeError("PeerExchange.verify needs the region tables (create it with regions=...)")
+                b = int(reg[s_, 0])
+                if b + c > cap or c > int(reg[s_, 1]):
+                    problems.append(f"rank {r} range {s_}: {c} commands exceed the region")
+                    continue
+                lo, hi = r * cap + b, r * cap + b + c
+                if not (np.array_equal(cmd[b:b + c], g["cmd"][lo:hi]) and np.array_equal(ptr[b:b + c], g["ptr"][lo:hi])
+                        and np.array_equal(tag[b:b + c], g["tag"][lo:hi])):
+                    problems.append(f"rank {r} range {s_}: records differ from the owner's")
+                commands += c
+                nbytes += c * 60
+        return dict(ok=not problems, commands=commands, bytes=nbytes + self.world * cb, problems=problems[:8])
 
     def directory(self) -> list[dict]:
         """Host view after a sync: the draws a renderer issues for the whole scene, StateSet by StateSet - one
@@ -321,6 +399,9 @@ class PeerExchange:
                 self.ctx.arena_free(a)
             self.ctx.arena_free(self.digests)
             self.regions_dev = []
+        if getattr(self, "gathered_inst", 0):
+            self.ctx.arena_free(self.gathered_inst)
+            self.gathered_inst = 0
         for a in self._imported:
             self.ctx.ipc_close(a)
         self._imported = []

@@ -389,11 +389,48 @@ def build_scene(name: str, *, geometries: list[dict] | dict, ml_count: np.ndarra
         dd_per_drawable[np.asarray(drawable_data, dtype=bool)] = dd_off
     g = dict(gen or {})
     g["metadata_bytes"] = ml_start
+    # what slice_scene() needs to lay out a part of this scene again (references, nothing is copied)
+    g["build"] = dict(geometries=geometries, ml_count=ml_count, drawable_geom=dg, drawable_ml=dm,
+                      drawable_ps_offset=np.asarray(drawable_ps_offset, dtype=np.uint64), state_set=ss,
+                      sphere=np.ascontiguousarray(sphere, dtype=np.float32), lod_count=np.asarray(lod_count, dtype=np.uint32),
+                      lod_ps_offset=np.asarray(lod_ps_offset, dtype=np.uint32), lod_threshold=np.ascontiguousarray(lod_threshold, dtype=np.float32),
+                      drawable_data=drawable_data, first_handle=first_handle, force_level=force_level, num_state_sets=S)
     return Scene(name=name, arena_bytes=arena_bytes, handle_level=level, root_off=root_off, num_handles=num_handles,
                  tables=tables, blobs=blobs, ml_off=ml_off, ml_count=ml_count, matrices=matrices,
                  drawables=d, cull=c, drawable_ml=dm.astype(np.uint32), drawable_geom=dg,
                  geo_off=np.stack([v_off, i_off, p_off], axis=1), dd_off=dd_per_drawable,
                  regions=regions, seed=seed, gen=g)
+
+
+def slice_scene(scene: Scene, first: int, count: int) -> Scene:
+    """One rank's part of ONE scene: drawables [first, first + count) of the flattened list, the geometries
+    and matrix lists they use (shared ones once), and a handle table over these local objects only.  StateSet indices stay
+    global (StateSets without local drawables get empty regions); matrices are the global scene's; drawable index d of
+    the slice is position first + d of the whole list.  Needs host matrices (the big device-synthesised shapes use
+    config3_shard)."""
+    b = scene.gen["build"]
+    sl = slice(first, first + count)
+    dg, dm = b["drawable_geom"][sl], b["drawable_ml"][sl]
+    geoms, g_inv = np.unique(dg, return_inverse=True)
+    lists, l_inv = np.unique(dm, return_inverse=True)
+    if isinstance(b["geometries"], dict):
+        geo = dict(b["geometries"]); geo["count"] = len(geoms)
+    else:
+        geo = [b["geometries"][int(g)] for g in geoms]
+    if scene.matrices is None:
+        raise ValueError("slice_scene needs host matrices")
+    starts = np.concatenate([[0], np.cumsum(b["ml_count"].astype(np.int64))])
+    rows = np.concatenate([np.arange(starts[k], starts[k + 1]) for k in lists]) if len(lists) else np.zeros(0, np.int64)
+    dd = b["drawable_data"]
+    out = build_scene(f"{scene.name}[{first}:{first + count}]", geometries=geo, ml_count=b["ml_count"][lists],
+                      drawable_geom=g_inv.reshape(-1), drawable_ml=l_inv.reshape(-1), drawable_ps_offset=b["drawable_ps_offset"][sl],
+                      state_set=b["state_set"][sl], sphere=b["sphere"][sl], lod_count=b["lod_count"][sl],
+                      lod_ps_offset=b["lod_ps_offset"][sl], lod_threshold=b["lod_threshold"][sl],
+                      matrices=scene.matrices[rows.astype(np.int64)], drawable_data=None if dd is None else np.asarray(dd)[sl],
+                      first_handle=b["first_handle"], force_level=b["force_level"], seed=scene.seed,
+                      num_state_sets=b["num_state_sets"])
+    out.gen["first"] = int(first)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -213,6 +213,21 @@ typedef struct cadr_exchange_sync {
 	uint64_t peerFlags[CADR_MAX_PEERS];       /* rank r's flag array [world] u64 as mapped here                  */
 } cadr_exchange_sync;
 
+/* Renderer-side gather of the survivors' instance-index runs of every rank (optional second stage of the exchange:
+ * with it a renderer reads instance indices locally and only the matrices through peer mappings).  For every
+ * (rank r, range s) the run [instBase, instBase + count) of rank r's instance-index buffer - count = high half of the
+ * counter rank r published - is copied to gatheredInst + (r * instCapacity + instBase) * 4. */
+typedef struct cadr_exchange_pull {
+	uint32_t world, rank;
+	uint32_t numRanges, countersBytes;
+	uint64_t gatheredCounters;                /* local gathered counters [world][countersBytes]                 */
+	uint64_t gatheredInst;                    /* local uint32_t [world][instCapacity], 16-byte aligned          */
+	uint64_t instCapacity;                    /* elements per rank, a multiple of 4                             */
+	uint32_t includeLocal, reserved;          /* 0: skip this rank's own runs (they are local already)          */
+	uint64_t regions[CADR_MAX_PEERS];         /* device copy of rank r's cadr_stateset_region[numRanges]        */
+	uint64_t peerInst[CADR_MAX_PEERS];        /* rank r's instance-index buffer as mapped here                  */
+} cadr_exchange_pull;
+
 /* ---- upload ------------------------------------------------------------------ */
 
 /* One copy region == one vk::BufferCopy recorded by DataMemory::recordUploads
@@ -338,6 +353,10 @@ CADR_API int  cadr_b200_ipc_close(cadr_ctx* ctx, uint64_t devAddr);
 CADR_API int  cadr_b200_exchange_publish(cadr_ctx* ctx, const cadr_exchange_sync* sync, cadr_stream stream);
 /* Block the stream (not the host) until every peer's flag in the LOCAL flag array has reached frameSeq. */
 CADR_API int  cadr_b200_exchange_wait(cadr_ctx* ctx, const cadr_exchange_sync* sync, cadr_stream stream);
+
+/* Pull every peer's compacted instance-index runs into the local gathered index buffer (stream-ordered; call it after
+ * cadr_b200_exchange_wait of the frame).  Inbound NVLink traffic: 4 B x survivors of all other ranks. */
+CADR_API int  cadr_b200_exchange_pull_instances(cadr_ctx* ctx, const cadr_exchange_pull* pull, cadr_stream stream);
 
 /* ---- export to a Vulkan consumer or another process (optional in north_star) ------------------- */
 

@@ -152,3 +152,54 @@ def test_tier_r_gather_rejects_bad_slices():
             g.run(torch.zeros(16, dtype=torch.uint8), torch.zeros(96, dtype=torch.uint8))   # indirect too short
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_slices_of_one_scene_add_up_to_the_whole_scene(world):
+    """synth.slice_scene (what every rank of the one-scene multi-GPU path lays out): per-rank slices cut by
+    shard.partition, each with its own arena and handle table over local objects only, global StateSet indices.  Resolved
+    and culled by the oracle slice by slice, the results put back at their global drawable positions are exactly the
+    whole scene's: Tier R indirect records, per-(drawable, lod) survivor sets, per-StateSet totals, near-band count."""
+    from helpers import fold_by_drawable_lod, oracle_tier_r, oracle_tier_x
+    whole = synth.random_scene(4242, n=1100, num_geometries=9, num_lists=140, max_count=80, state_sets=7, big_lists=3, valid_geometry=True)
+    planes, eye = synth.orbit_camera(75, 250.0, far=500.0)
+    w_ind, _, ref = oracle_tier_x(whole, planes, eye)
+    K, S, Q = fold_by_drawable_lod(ref, whole.n)
+    slices = shard.partition(whole.ml_count[whole.drawable_ml], world)
+    inst = np.zeros(whole.num_state_sets, np.int64)
+    near = 0
+    for f, c in slices:
+        sc = synth.slice_scene(whole, f, c)
+        assert sc.n == c and sc.num_state_sets == whole.num_state_sets and sc.gen["first"] == f
+        assert sc.arena_bytes < whole.arena_bytes or world == 1
+        ind, _, r = oracle_tier_x(sc, planes, eye)
+        assert np.array_equal(ind, w_ind[f:f + c])
+        k, s, q = fold_by_drawable_lod(r, c)
+        assert np.array_equal(k, K[f:f + c]) and np.array_equal(s, S[f:f + c]) and np.array_equal(q, Q[f:f + c])
+        assert r["status"] == 0
+        absent = np.setdiff1d(np.arange(whole.num_state_sets), np.unique(sc.cull[:, 10]))
+        assert not sc.regions[absent, 1].any() and not sc.regions[absent, 3].any()        # StateSets without local drawables: empty regions
+        inst += r["inst_count"]; near += r["near_band"]
+    assert np.array_equal(inst, ref["inst_count"]) and near == ref["near_band"]
+
+
+def test_config3_shards_are_parts_of_one_config3_scene():
+    """synth.config3_shard (the big device-synthesised shape of BASELINE configs[4]): matrices, StateSets and culling
+    records of every shard are those of config3() at the same global positions, whichever way the list is cut."""
+    n, inst, S = 1900, 24, 16
+    whole = synth.config3(n, inst, state_sets=S)
+    planes, eye = synth.orbit_camera(30, 1500.0, far=3000.0)
+    from helpers import fold_by_drawable_lod, oracle_tier_x
+    _, _, ref = oracle_tier_x(whole, planes, eye)
+    K, _, Q = fold_by_drawable_lod(ref, n)
+    for world in (2, 5):
+        tot = 0
+        for f, c in shard.partition(np.full(n, inst), world):
+            sc = synth.config3_shard(n, f, c, inst, state_sets=S)
+            assert np.array_equal(sc.matrices.reshape(c, inst, 16), whole.matrices.reshape(n, inst, 16)[whole.drawable_ml[f:f + c]])
+            assert np.array_equal(sc.cull, whole.cull[f:f + c]) and sc.num_state_sets == S
+            _, _, r = oracle_tier_x(sc, planes, eye)
+            k, _, q = fold_by_drawable_lod(r, c)
+            assert np.array_equal(k, K[f:f + c]) and np.array_equal(q, Q[f:f + c])
+            tot += r["num_instances"]
+        assert tot == ref["num_instances"] and tot > 0
