@@ -706,6 +706,7 @@ def run_b200(args):
         arena.tensors.clear()
         torch.cuda.empty_cache()
         line["workloads"] = other_workloads(args)
+        line["e2e_facade"] = facade_line(local, max(20, min(args.steps, 200)))
     if rank == 0:
         print(json.dumps(line))
     if verify is not None and not verify["ok"]:
@@ -739,6 +740,23 @@ def other_workloads(args) -> dict:
             c["upload"] = {k: d["upload"][k] for k in ("bytes_per_step", "launch_ms", "achieved", "frac")}
         out[w] = c
     return out
+
+
+def facade_line(device: int, frames: int) -> dict:
+    """The same workload through the C++ facade: cadr_b200/host/bin/facade_bench builds configs[2] with CadR::Geometry /
+    MatrixList / Drawable / StateSet and runs the reference's frame loop (main.cpp:1374-1573) through CadR::Renderer."""
+    exe = os.path.join(ROOT, "cadr_b200", "host", "bin", "facade_bench")
+    if not os.path.exists(exe):
+        return {"error": "cadr_b200/host/bin/facade_bench is not built"}
+    try:
+        r = subprocess.run([exe, str(device), "c3", str(frames)], capture_output=True, text=True, timeout=300)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+    return {"value": d["e2e_queued"]["M_instances_per_s"], "unit": "M instances/s", "ms_per_step": d["e2e_queued"]["ms_per_frame"],
+            "synchronised_every_frame": d["e2e_synchronised"], "gpuDrawableProcessing_ms": d["gpuDrawableProcessing_ms"],
+            "cpu_frame_ms": d["cpu_frame_ms"], "survivor_fraction": d["survivor_fraction"], "frames": d["frames"],
+            "scene_build_seconds": d["build_seconds"], "what": d["loop"], "workload": d["workload"]}
 
 
 def main():

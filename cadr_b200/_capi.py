@@ -140,6 +140,8 @@ SYMBOLS = {
     "cadr_b200_process_and_cull": (C.c_int, [_P, C.POINTER(CullParams), _P]),
     "cadr_b200_compute_drawable_bounds": (C.c_int, [_P, C.POINTER(CullParams), C.c_uint64, C.c_uint64, C.c_uint32, _P]),
     "cadr_b200_ipc_export": (C.c_int, [_P, C.c_uint64, C.c_char_p]),
+    "cadr_b200_upload_stage": (C.c_int, [_P, C.POINTER(CopyRegion), C.c_uint32, _P, _P, C.POINTER(C.c_uint64)]),
+    "cadr_b200_upload_commit": (C.c_int, [_P, C.c_uint64, _P]),
     "cadr_b200_exchange_pull_instances": (C.c_int, [_P, C.POINTER(ExchangePull), _P]),
     "cadr_b200_ipc_export_range": (C.c_int, [_P, C.c_uint64, C.c_char_p, C.POINTER(C.c_uint64)]),
     "cadr_b200_ipc_import": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_uint64)]),
@@ -265,6 +267,18 @@ class Context:
         check(self._l.cadr_b200_memset(self._h, dst, value, nbytes, _P(stream)))
 
     # -- upload path
+    def upload_stage(self, regions, staging, copy_stream: int = 0) -> int:
+        """Phase 1 of the two-phase upload: bytes cross PCIe into a device-side slot on `copy_stream` -> ticket."""
+        arr, n = _regions(regions)
+        ptr, _ = _buf(staging, None)
+        t = C.c_uint64()
+        check(self._l.cadr_b200_upload_stage(self._h, arr, n, ptr, _P(copy_stream), C.byref(t)))
+        return t.value
+
+    def upload_commit(self, ticket: int, stream: int = 0) -> None:
+        """Phase 2: `stream` waits for the staging and one scatter launch places the bytes."""
+        check(self._l.cadr_b200_upload_commit(self._h, ticket, _P(stream)))
+
     def upload(self, regions, staging, stream: int = 0) -> None:
         arr, n = _regions(regions)
         ptr, _ = _buf(staging, None)

@@ -46,17 +46,28 @@ static int growDevice(void*& p, size_t& have, size_t need)
 	return CADR_OK;
 }
 
-int cadr_ctx::ensureDevScratch(size_t bytes) { return growDevice(devScratch, devScratchBytes, bytes); }
-int cadr_ctx::ensureDevMirror(size_t bytes)  { return growDevice(devMirror, devMirrorBytes, bytes); }
-int cadr_ctx::ensureHostScratch(size_t bytes)
+int cadr_ctx::UploadSlot::ensureDev(size_t bytes)    { return growDevice(dev, devBytes, bytes); }
+int cadr_ctx::UploadSlot::ensureMirror(size_t bytes) { return growDevice(mirror, mirrorBytes, bytes); }
+int cadr_ctx::UploadSlot::ensureHost(size_t bytes)
 {
-	if(bytes <= hostScratchBytes) return CADR_OK;
-	size_t want = hostScratchBytes ? hostScratchBytes : (1u << 20);
+	if(bytes <= hostBytes) return CADR_OK;
+	size_t want = hostBytes ? hostBytes : (1u << 20);
 	while(want < bytes) want *= 2;
-	if(hostScratch) { CADR_CUDA(cudaFreeHost(hostScratch)); hostScratch = nullptr; hostScratchBytes = 0; }
-	CADR_CUDA(cudaMallocHost(&hostScratch, want));
-	hostScratchBytes = want;
+	if(host) { CADR_CUDA(cudaFreeHost(host)); host = nullptr; hostBytes = 0; }
+	CADR_CUDA(cudaMallocHost(&host, want));
+	hostBytes = want;
 	return CADR_OK;
+}
+
+cadr_ctx::UploadSlot* cadr_ctx::acquireSlot()
+{
+	for(int tries = 0; tries < 2; tries++) {
+		UploadSlot& sl = slots[nextSlot++ & 1u];
+		if(sl.pendingUnits) continue;                    // staged, not committed yet: its buffers are in use
+		if(cudaEventSynchronize(sl.free) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+		return &sl;
+	}
+	return nullptr;
 }
 
 #define REQUIRE_CTX(ctx)      do { if(!(ctx)) return setError(CADR_E_LOGIC, "%s: null context", __func__); } while(0)
@@ -99,8 +110,11 @@ int cadr_b200_create(int device, cadr_ctx** out)
 		cudaEventCreate(&ctx->evBegin[k]);
 		cudaEventCreate(&ctx->evEnd[k]);
 	}
-	cudaEventCreateWithFlags(&ctx->hostScratchFree, cudaEventDisableTiming);
-	cudaEventRecord(ctx->hostScratchFree, ctx->stream);
+	for(auto& sl : ctx->slots) {
+		cudaEventCreateWithFlags(&sl.free, cudaEventDisableTiming);
+		cudaEventCreateWithFlags(&sl.staged, cudaEventDisableTiming);
+		cudaEventRecord(sl.free, ctx->stream);
+	}
 	*out = ctx;
 	return CADR_OK;
 }
@@ -121,11 +135,14 @@ void cadr_b200_destroy(cadr_ctx* ctx)
 		while(!ctx->externals.empty()) cadr_b200_external_free(ctx, ctx->externals.begin()->first);
 		for(auto& a : ctx->arenas) cudaFree(reinterpret_cast<void*>(a.first));
 		for(auto& h : ctx->hostBlocks) cudaFreeHost(h.first);
-		if(ctx->devScratch) cudaFree(ctx->devScratch);
-		if(ctx->devMirror) cudaFree(ctx->devMirror);
-		if(ctx->hostScratch) cudaFreeHost(ctx->hostScratch);
+		for(auto& sl : ctx->slots) {
+			if(sl.dev) cudaFree(sl.dev);
+			if(sl.mirror) cudaFree(sl.mirror);
+			if(sl.host) cudaFreeHost(sl.host);
+			cudaEventDestroy(sl.free);
+			cudaEventDestroy(sl.staged);
+		}
 		for(int k = 0; k < KS_COUNT; k++) { cudaEventDestroy(ctx->evBegin[k]); cudaEventDestroy(ctx->evEnd[k]); }
-		cudaEventDestroy(ctx->hostScratchFree);
 		cudaStreamDestroy(ctx->stream);
 	}
 	else {
@@ -271,6 +288,24 @@ int cadr_b200_upload(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n,
 	if(n == 0) return CADR_OK;
 	if(!regions) return setError(CADR_E_LOGIC, "upload: null region list");
 	return launchUpload(ctx, regions, n, stagingBase, ctx->pick(stream));
+}
+
+int cadr_b200_upload_stage(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n, const void* stagingBase, cadr_stream copyStream,
+                           uint64_t* ticket)
+{
+	REQUIRE_DEVICE(ctx);
+	if(!ticket) return setError(CADR_E_LOGIC, "upload_stage: null ticket");
+	*ticket = 0;
+	if(n == 0) return CADR_OK;
+	if(!regions) return setError(CADR_E_LOGIC, "upload_stage: null region list");
+	return stageUpload(ctx, regions, n, stagingBase, ctx->pick(copyStream), ticket);
+}
+
+int cadr_b200_upload_commit(cadr_ctx* ctx, uint64_t ticket, cadr_stream stream)
+{
+	REQUIRE_DEVICE(ctx);
+	if(ticket == 0) return CADR_OK;            // an empty upload_stage
+	return commitUpload(ctx, ticket, ctx->pick(stream));
 }
 
 int cadr_b200_scatter_copy(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n, uint64_t stagingDevAddr, cadr_stream stream)

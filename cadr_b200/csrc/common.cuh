@@ -49,16 +49,27 @@ struct cadr_ctx {
 	// pinned host blocks (ptr -> size)
 	std::map<void*, size_t> hostBlocks;
 
-	// growable scratch owned by the context
-	void*  devScratch = nullptr;   size_t devScratchBytes = 0;    // copy units / patches on device
-	void*  devMirror = nullptr;    size_t devMirrorBytes = 0;     // device mirror of small staged regions
-	void*  hostScratch = nullptr;  size_t hostScratchBytes = 0;   // pinned; descriptors + packed small regions
-	cudaEvent_t hostScratchFree = nullptr;                        // last consumer of hostScratch
+	// Growable scratch of the upload family (upload, scatter_copy, patch_handles, upload_stage / upload_commit): TWO slots
+	// used in turn, so that a call only ever waits (on the host) for the consumer of the call before the previous one -
+	// in a frame loop that work is long finished, and nothing blocks.
+	struct UploadSlot {
+		void*  dev = nullptr;     size_t devBytes = 0;       // copy units / patches on device
+		void*  mirror = nullptr;  size_t mirrorBytes = 0;    // device-side staging of the regions' bytes
+		void*  host = nullptr;    size_t hostBytes = 0;      // pinned; descriptors + packed small regions
+		cudaEvent_t free = nullptr;                          // last consumer of this slot
+		cudaEvent_t staged = nullptr;                        // two-phase upload: the staging copies on the copy stream are done
+		size_t pendingUnits = 0;                             // two-phase upload: copy units waiting for upload_commit
+		uint32_t generation = 0;                             // part of the ticket handed out by upload_stage
+		int ensureDev(size_t bytes);
+		int ensureMirror(size_t bytes);
+		int ensureHost(size_t bytes);
+	};
+	UploadSlot slots[2];
+	uint32_t nextSlot = 0;
+	// next slot that holds no staged-but-uncommitted upload, after its last consumer has finished (nullptr: both are staged)
+	UploadSlot* acquireSlot();
 
 	cudaStream_t pick(cadr_stream s) const { return s ? reinterpret_cast<cudaStream_t>(s) : stream; }
-	int ensureDevScratch(size_t bytes);
-	int ensureDevMirror(size_t bytes);
-	int ensureHostScratch(size_t bytes);
 
 	void timeBegin(cadr::KernelSlot k, cudaStream_t s) { if(profiling) { cudaEventRecord(evBegin[k], s); evUsed[k] = true; } }
 	void timeEnd(cadr::KernelSlot k, cudaStream_t s)   { if(profiling) cudaEventRecord(evEnd[k], s); }
@@ -154,5 +165,7 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 int launchComputeBounds(cadr_ctx* ctx, const cadr_cull_params& p, uint64_t boundsOut, uint64_t indices, uint32_t count, cudaStream_t s);
 int launchScatterCopy(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n, uint64_t stagingDevAddr, cudaStream_t s);
 int launchPatchHandles(cadr_ctx* ctx, uint64_t root, uint32_t level, const cadr_handle_patch* patches, uint32_t n, cudaStream_t s);
+int stageUpload(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n, const void* stagingBase, cudaStream_t copyStream, uint64_t* ticket);
+int commitUpload(cadr_ctx* ctx, uint64_t ticket, cudaStream_t s);
 
 }  // namespace cadr

@@ -8,6 +8,8 @@
 
 #include "common.cuh"
 #include <cstring>
+#include <map>
+#include <vector>
 
 namespace cadr {
 
@@ -91,18 +93,20 @@ static void fillUnits(CopyUnit* u, const cadr_copy_region* regions, uint32_t n, 
 	}
 }
 
-// units already sit at the start of the pinned scratch: ship them and launch one CTA per unit
-static int shipUnitsAndLaunch(cadr_ctx* ctx, size_t numUnits, cudaStream_t s)
+// units already sit at the start of the slot's pinned scratch: ship them and launch one CTA per unit
+static int shipUnitsAndLaunch(cadr_ctx* ctx, cadr_ctx::UploadSlot& sl, size_t numUnits, cudaStream_t s)
 {
-	CADR_CUDA(cudaMemcpyAsync(ctx->devScratch, ctx->hostScratch, numUnits * sizeof(CopyUnit), cudaMemcpyHostToDevice, s));
+	CADR_CUDA(cudaMemcpyAsync(sl.dev, sl.host, numUnits * sizeof(CopyUnit), cudaMemcpyHostToDevice, s));
 	ctx->timeBegin(KS_SCATTER, s);
-	scatterCopyKernel<<<uint32_t(numUnits), SC_THREADS, 0, s>>>(static_cast<const CopyUnit*>(ctx->devScratch));
+	scatterCopyKernel<<<uint32_t(numUnits), SC_THREADS, 0, s>>>(static_cast<const CopyUnit*>(sl.dev));
 	ctx->timeEnd(KS_SCATTER, s);
 	ctx->launches++;
 	CADR_CUDA(cudaGetLastError());
-	CADR_CUDA(cudaEventRecord(ctx->hostScratchFree, s));
+	CADR_CUDA(cudaEventRecord(sl.free, s));
 	return CADR_OK;
 }
+
+static int slotBusy() { return setError(CADR_E_LOGIC, "upload: both scratch slots hold staged uploads that were never committed (cadr_b200_upload_commit)"); }
 
 int launchScatterCopy(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n, uint64_t stagingDevAddr, cudaStream_t s)
 {
@@ -115,25 +119,35 @@ int launchScatterCopy(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n
 	if(numUnits > 0x7fffffffull)
 		return setError(CADR_E_LOGIC, "scatter_copy: too many copy units");
 	size_t unitBytes = numUnits * sizeof(CopyUnit);
-	CADR_CUDA(cudaEventSynchronize(ctx->hostScratchFree));  // previous consumer of the pinned scratch
-	if(int r = ctx->ensureHostScratch(unitBytes)) return r;
-	if(int r = ctx->ensureDevScratch(unitBytes)) return r;
-	fillUnits(static_cast<CopyUnit*>(ctx->hostScratch), regions, n, stagingDevAddr);
-	return shipUnitsAndLaunch(ctx, numUnits, s);
+	cadr_ctx::UploadSlot* sl = ctx->acquireSlot();      // waits (host) for the consumer of the call before the previous one
+	if(!sl) return slotBusy();
+	if(int r = sl->ensureHost(unitBytes)) return r;
+	if(int r = sl->ensureDev(unitBytes)) return r;
+	fillUnits(static_cast<CopyUnit*>(sl->host), regions, n, stagingDevAddr);
+	return shipUnitsAndLaunch(ctx, *sl, numUnits, s);
 }
 
 // Three ways for a region to reach the device, chosen per call:
 //   * regions of at least UPLOAD_DMA_THRESHOLD bytes go out as their own DMA (what vkCmdCopyBuffer does for every
-//     region; the reference's regions are few and large because staging mirrors the device layout);
+//     region; the reference's regions are few and large because staging mirrors the device layout) - not in the
+//     two-phase form, where nothing may touch a destination before the commit;
 //   * the remaining regions, when their sources are dense in the staging block (>= half of the span they cover),
 //     are shipped with ONE DMA of that span into the device mirror and scattered by ONE kernel launch — thousands
 //     of rewritten allocations cost one copy-engine transfer at PCIe speed plus an HBM-speed scatter;
 //   * otherwise they are packed on the host first (one DMA of the packed bytes + one scatter launch).
 constexpr uint64_t UPLOAD_DMA_THRESHOLD = 1u << 20;
 
-int launchUpload(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n, const void* stagingBase, cudaStream_t s)
+struct UploadPlan {
+	struct Span { uint64_t lo, bytes, mirrorOff; };
+	std::vector<uint32_t> direct;            // regions that go out as their own DMA
+	std::vector<Span> spans;                 // stretches of the staging block shipped whole into the mirror
+	std::vector<uint32_t> packIdx;           // regions packed on the host
+	std::vector<cadr_copy_region> small;     // everything that is scattered; srcOffset = offset inside the device mirror
+	uint64_t mirrorBytes = 0, packBase = 0, packedBytes = 0;
+};
+
+static int planUpload(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n, const uint8_t* base, bool allThroughMirror, UploadPlan& P)
 {
-	const uint8_t* base = static_cast<const uint8_t*>(stagingBase);
 	// Small regions are grouped by the host block their source lies in: a span may only be shipped whole when every byte
 	// of it is known to be readable.  With a staging base the caller's block covers all offsets by contract; with absolute
 	// addresses (base == nullptr) the blocks handed out by cadr_b200_host_alloc are known, anything else is packed.
@@ -147,10 +161,7 @@ int launchUpload(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n, con
 			return setError(CADR_E_LOGIC, "upload: region %u has a null destination", i);
 		if(base == nullptr && r.srcOffset == 0)
 			return setError(CADR_E_LOGIC, "upload: region %u has a null source", i);
-		if(r.bytes >= UPLOAD_DMA_THRESHOLD) {
-			CADR_CUDA(cudaMemcpyAsync(reinterpret_cast<void*>(r.dstAddr), base + r.srcOffset, r.bytes, cudaMemcpyHostToDevice, s));
-			continue;
-		}
+		if(r.bytes >= UPLOAD_DMA_THRESHOLD && !allThroughMirror) { P.direct.push_back(i); continue; }
 		Group* g = &loose;
 		if(base != nullptr) g = &groups[0];
 		else {
@@ -169,50 +180,105 @@ int launchUpload(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n, con
 	}
 	// dense groups (sources cover >= half of the span) go out as ONE DMA of the span each; everything else is packed on
 	// the host into the pinned scratch (16-B aligned slots keep the scatter kernel's fast path) and goes out as one DMA
-	std::vector<cadr_copy_region> small;     // srcOffset rewritten to the offset inside the device mirror
-	struct Span { uint64_t lo, bytes, mirrorOff; };
-	std::vector<Span> spans;
-	std::vector<uint32_t> packIdx = std::move(loose.idx);
-	uint64_t mirrorBytes = 0;
+	P.packIdx = std::move(loose.idx);
 	for(auto& [key, g] : groups) {
 		if(g.idx.empty()) continue;
 		const uint64_t lo = g.lo & ~uint64_t(15);                 // keep the 16-byte phase
 		if(g.sum * 2 >= g.hi - lo) {
-			spans.push_back(Span{lo, g.hi - lo, mirrorBytes});
-			for(uint32_t i : g.idx) { cadr_copy_region q = regions[i]; q.srcOffset = mirrorBytes + (q.srcOffset - lo); small.push_back(q); }
-			mirrorBytes += (g.hi - lo + 255) & ~uint64_t(255);
+			P.spans.push_back(UploadPlan::Span{lo, g.hi - lo, P.mirrorBytes});
+			for(uint32_t i : g.idx) { cadr_copy_region q = regions[i]; q.srcOffset = P.mirrorBytes + (q.srcOffset - lo); P.small.push_back(q); }
+			P.mirrorBytes += (g.hi - lo + 255) & ~uint64_t(255);
 		}
-		else packIdx.insert(packIdx.end(), g.idx.begin(), g.idx.end());
+		else P.packIdx.insert(P.packIdx.end(), g.idx.begin(), g.idx.end());
 	}
-	const uint64_t packBase = mirrorBytes;
-	uint64_t packedBytes = 0;
-	for(uint32_t i : packIdx) { cadr_copy_region q = regions[i]; q.srcOffset = packBase + packedBytes; small.push_back(q); packedBytes += (q.bytes + 15) & ~uint64_t(15); }
-	mirrorBytes += packedBytes;
-	if(small.empty())
-		return CADR_OK;
+	P.packBase = P.mirrorBytes;
+	for(uint32_t i : P.packIdx) { cadr_copy_region q = regions[i]; q.srcOffset = P.packBase + P.packedBytes; P.small.push_back(q); P.packedBytes += (q.bytes + 15) & ~uint64_t(15); }
+	P.mirrorBytes += P.packedBytes;
+	return CADR_OK;
+}
 
-	const size_t numUnits = countUnits(small.data(), uint32_t(small.size()));
-	if(numUnits > 0x7fffffffull)
-		return setError(CADR_E_LOGIC, "upload: too many copy units");
+// the host-to-device part of a plan: spans and packed bytes into the slot's mirror, copy units into its pinned scratch
+static int stagePlan(cadr_ctx::UploadSlot& sl, const UploadPlan& P, const cadr_copy_region* regions, const uint8_t* base, size_t numUnits, cudaStream_t s)
+{
 	const size_t unitBytes = (numUnits * sizeof(CopyUnit) + 255) & ~size_t(255);
-	CADR_CUDA(cudaEventSynchronize(ctx->hostScratchFree));
-	if(int r = ctx->ensureDevScratch(unitBytes)) return r;
-	if(int r = ctx->ensureHostScratch(unitBytes + packedBytes)) return r;
-	if(int r = ctx->ensureDevMirror(mirrorBytes)) return r;
-	fillUnits(static_cast<CopyUnit*>(ctx->hostScratch), small.data(), uint32_t(small.size()), reinterpret_cast<uint64_t>(ctx->devMirror));
-	uint8_t* mirror = static_cast<uint8_t*>(ctx->devMirror);
-	for(const Span& sp : spans)
+	if(int r = sl.ensureDev(unitBytes)) return r;
+	if(int r = sl.ensureHost(unitBytes + P.packedBytes)) return r;
+	if(int r = sl.ensureMirror(P.mirrorBytes)) return r;
+	fillUnits(static_cast<CopyUnit*>(sl.host), P.small.data(), uint32_t(P.small.size()), reinterpret_cast<uint64_t>(sl.mirror));
+	uint8_t* mirror = static_cast<uint8_t*>(sl.mirror);
+	for(const UploadPlan::Span& sp : P.spans)
 		CADR_CUDA(cudaMemcpyAsync(mirror + sp.mirrorOff, base + sp.lo, sp.bytes, cudaMemcpyHostToDevice, s));
-	if(packedBytes) {
-		uint8_t* pack = static_cast<uint8_t*>(ctx->hostScratch) + unitBytes;
+	if(P.packedBytes) {
+		uint8_t* pack = static_cast<uint8_t*>(sl.host) + unitBytes;
 		uint64_t off = 0;
-		for(uint32_t i : packIdx) {
+		for(uint32_t i : P.packIdx) {
 			std::memcpy(pack + off, base + regions[i].srcOffset, regions[i].bytes);
 			off += (regions[i].bytes + 15) & ~uint64_t(15);
 		}
-		CADR_CUDA(cudaMemcpyAsync(mirror + packBase, pack, packedBytes, cudaMemcpyHostToDevice, s));
+		CADR_CUDA(cudaMemcpyAsync(mirror + P.packBase, pack, P.packedBytes, cudaMemcpyHostToDevice, s));
 	}
-	return shipUnitsAndLaunch(ctx, numUnits, s);
+	return CADR_OK;
+}
+
+int launchUpload(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n, const void* stagingBase, cudaStream_t s)
+{
+	const uint8_t* base = static_cast<const uint8_t*>(stagingBase);
+	UploadPlan P;
+	if(int r = planUpload(ctx, regions, n, base, false, P)) return r;
+	for(uint32_t i : P.direct)
+		CADR_CUDA(cudaMemcpyAsync(reinterpret_cast<void*>(regions[i].dstAddr), base + regions[i].srcOffset, regions[i].bytes, cudaMemcpyHostToDevice, s));
+	if(P.small.empty())
+		return CADR_OK;
+	const size_t numUnits = countUnits(P.small.data(), uint32_t(P.small.size()));
+	if(numUnits > 0x7fffffffull)
+		return setError(CADR_E_LOGIC, "upload: too many copy units");
+	cadr_ctx::UploadSlot* sl = ctx->acquireSlot();
+	if(!sl) return slotBusy();
+	if(int r = stagePlan(*sl, P, regions, base, numUnits, s)) return r;
+	return shipUnitsAndLaunch(ctx, *sl, numUnits, s);
+}
+
+// Two-phase form (cadr_b200_upload_stage / _commit).  Stage: every region's bytes cross PCIe into the slot's device
+// mirror on the COPY stream; no destination is touched, so the frame in flight on the main stream may still read them.
+// Commit: the main stream waits for the staging (an event, not the host) and ONE scatter launch places the bytes at HBM
+// speed.  A renderer stages frame k + 1 while frame k is culled: the PCIe transfer disappears behind the GPU work.
+int stageUpload(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n, const void* stagingBase, cudaStream_t copyStream, uint64_t* ticket)
+{
+	const uint8_t* base = static_cast<const uint8_t*>(stagingBase);
+	UploadPlan P;
+	if(int r = planUpload(ctx, regions, n, base, true, P)) return r;
+	if(P.small.empty()) return CADR_OK;
+	const size_t numUnits = countUnits(P.small.data(), uint32_t(P.small.size()));
+	if(numUnits > 0x7fffffffull)
+		return setError(CADR_E_LOGIC, "upload_stage: too many copy units");
+	cadr_ctx::UploadSlot* sl = ctx->acquireSlot();
+	if(!sl) return slotBusy();
+	if(int r = stagePlan(*sl, P, regions, base, numUnits, copyStream)) return r;
+	CADR_CUDA(cudaMemcpyAsync(sl->dev, sl->host, numUnits * sizeof(CopyUnit), cudaMemcpyHostToDevice, copyStream));
+	CADR_CUDA(cudaEventRecord(sl->staged, copyStream));
+	CADR_CUDA(cudaEventRecord(sl->free, copyStream));     // until the commit records the real last consumer
+	sl->pendingUnits = numUnits;
+	sl->generation++;
+	*ticket = (uint64_t(sl->generation) << 8) | uint64_t(sl - ctx->slots) | 0x80u;
+	return CADR_OK;
+}
+
+int commitUpload(cadr_ctx* ctx, uint64_t ticket, cudaStream_t s)
+{
+	const uint32_t idx = uint32_t(ticket & 0x7f);
+	if(!(ticket & 0x80u) || idx > 1) return setError(CADR_E_LOGIC, "upload_commit: not a ticket of upload_stage");
+	cadr_ctx::UploadSlot& sl = ctx->slots[idx];
+	if(sl.pendingUnits == 0 || sl.generation != uint32_t(ticket >> 8))
+		return setError(CADR_E_LOGIC, "upload_commit: this ticket was committed already");
+	CADR_CUDA(cudaStreamWaitEvent(s, sl.staged, 0));
+	ctx->timeBegin(KS_SCATTER, s);
+	scatterCopyKernel<<<uint32_t(sl.pendingUnits), SC_THREADS, 0, s>>>(static_cast<const CopyUnit*>(sl.dev));
+	ctx->timeEnd(KS_SCATTER, s);
+	ctx->launches++;
+	CADR_CUDA(cudaGetLastError());
+	CADR_CUDA(cudaEventRecord(sl.free, s));
+	sl.pendingUnits = 0;
+	return CADR_OK;
 }
 
 int launchPatchHandles(cadr_ctx* ctx, uint64_t root, uint32_t level, const cadr_handle_patch* patches, uint32_t n, cudaStream_t s)
@@ -228,13 +294,14 @@ int launchPatchHandles(cadr_ctx* ctx, uint64_t root, uint32_t level, const cadr_
 			return setError(CADR_E_LOGIC, "patch_handles: handle %llu out of range for level %u",
 			                (unsigned long long)patches[i].handle, level);
 	size_t bytes = size_t(n) * sizeof(cadr_handle_patch);
-	CADR_CUDA(cudaEventSynchronize(ctx->hostScratchFree));
-	if(int r = ctx->ensureHostScratch(bytes)) return r;
-	if(int r = ctx->ensureDevScratch(bytes)) return r;
-	std::memcpy(ctx->hostScratch, patches, bytes);
-	CADR_CUDA(cudaMemcpyAsync(ctx->devScratch, ctx->hostScratch, bytes, cudaMemcpyHostToDevice, s));
+	cadr_ctx::UploadSlot* sl = ctx->acquireSlot();
+	if(!sl) return slotBusy();
+	if(int r = sl->ensureHost(bytes)) return r;
+	if(int r = sl->ensureDev(bytes)) return r;
+	std::memcpy(sl->host, patches, bytes);
+	CADR_CUDA(cudaMemcpyAsync(sl->dev, sl->host, bytes, cudaMemcpyHostToDevice, s));
 	uint32_t grid = (n + 255) / 256;
-	auto dp = static_cast<const cadr_handle_patch*>(ctx->devScratch);
+	auto dp = static_cast<const cadr_handle_patch*>(sl->dev);
 	ctx->timeBegin(KS_PATCH, s);
 	switch(level) {
 	case 1: patchHandlesKernel<1><<<grid, 256, 0, s>>>(root, dp, n); break;
@@ -244,7 +311,7 @@ int launchPatchHandles(cadr_ctx* ctx, uint64_t root, uint32_t level, const cadr_
 	ctx->timeEnd(KS_PATCH, s);
 	ctx->launches++;
 	CADR_CUDA(cudaGetLastError());
-	CADR_CUDA(cudaEventRecord(ctx->hostScratchFree, s));
+	CADR_CUDA(cudaEventRecord(sl->free, s));
 	return CADR_OK;
 }
 

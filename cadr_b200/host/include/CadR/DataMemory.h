@@ -44,6 +44,9 @@ public:
 
 	DataAllocationRecord* alloc(size_t numBytes);                      ///< nullptr when there is no room (DataMemory.cpp:255-397)
 	static void free(DataAllocationRecord* a) noexcept;
+	/// Present for API compatibility and, as in the reference, does nothing: the body of DataMemory::cancelAllAllocations
+	/// is compiled out there ("disabled as it is questionable what it should exactly do", DataMemory.cpp:199-201).
+	void cancelAllAllocations() noexcept {}
 
 	/// Append this buffer's copy regions; -> bytes to transfer.  The runs move into `pending` until uploadDone().
 	size_t recordUploads(std::vector<cadr_copy_region>& regions, PendingUpload& pending);

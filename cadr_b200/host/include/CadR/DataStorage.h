@@ -57,6 +57,8 @@ public:
 	DataAllocationRecord* realloc(DataAllocationRecord* allocationRecord, size_t numBytes);
 	DataAllocationRecord* zeroSizeAllocationRecord() noexcept { return &_zeroSizeAllocationRecord; }
 	void free(DataAllocationRecord* a) noexcept { if(a->size == 0) return; DataMemory::free(a); }
+	/// DataStorage.cpp:168-172: forwards to every DataMemory, where the reference's implementation is compiled out.
+	void cancelAllAllocations() noexcept { for(DataMemory* m : _dataMemoryList) m->cancelAllAllocations(); }
 
 	/// One cadr_b200_upload per call: -> {resources to release once the stream has passed the copies, bytes}.
 	std::tuple<TransferResources, size_t> recordUploads(void* stream);

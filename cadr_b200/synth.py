@@ -306,8 +306,11 @@ def build_scene(name: str, *, geometries: list[dict] | dict, ml_count: np.ndarra
         bump.top = base0 + stride * G
         rng = np.random.default_rng(seed + 17)
         one = np.zeros(stride, dtype=np.uint8)
-        one[v0 - base0:v0 - base0 + vb] = rng.integers(0, 256, vb, dtype=np.uint8)
-        one[i0 - base0:i0 - base0 + ib] = rng.integers(0, 256, ib, dtype=np.uint8)
+        # real geometry when given (the consumer-side walk dereferences indices and vertices), else opaque bytes
+        vbytes = geometries.get("vertices")
+        ibytes = geometries.get("indices")
+        one[v0 - base0:v0 - base0 + vb] = rng.integers(0, 256, vb, dtype=np.uint8) if vbytes is None else np.ascontiguousarray(vbytes).view(np.uint8).reshape(-1)
+        one[i0 - base0:i0 - base0 + ib] = rng.integers(0, 256, ib, dtype=np.uint8) if ibytes is None else np.ascontiguousarray(ibytes).view(np.uint8).reshape(-1)
         one[p0 - base0:p0 - base0 + ps.nbytes] = ps.view(np.uint8).reshape(-1)
         blobs.append((base0, np.tile(one, G)))
     else:
@@ -470,9 +473,16 @@ BOX_SPHERE_RADIUS = math.sqrt(3.0) * 2.43   # box of side 4.86 (Tests.cpp:495-50
 LOD_PRIMITIVE_SETS = np.array([[36, 0], [24, 36], [12, 60]], dtype=np.uint32)  # Appendix D cfg 3
 
 
+_BOX_TRIANGLES = np.array([0, 2, 1, 1, 2, 3, 0, 1, 4, 4, 1, 5, 0, 4, 2, 2, 4, 6, 4, 5, 6, 6, 5, 7, 2, 6, 3, 3, 6, 7, 1, 3, 5, 5, 3, 7], np.uint32)
+
+
 def _box_geometry(lods: bool) -> dict:
+    """A real box of side 4.86 (Tests.cpp:495-503): 8 corners x 12 bytes, 36 indices; with LODs 24 and 12 more (the
+    first faces again), matching LOD_PRIMITIVE_SETS.  Real so that the consumer-side walk can dereference it."""
     ps = LOD_PRIMITIVE_SETS if lods else LOD_PRIMITIVE_SETS[:1]
-    return dict(vertex_bytes=8 * 12, index_bytes=72 * 4 if lods else 36 * 4, primitive_sets=ps)
+    corners = np.array([[(2.43 if v & 1 else -2.43), (2.43 if v & 2 else -2.43), (2.43 if v & 4 else -2.43)] for v in range(8)], np.float32)
+    idx = np.concatenate([_BOX_TRIANGLES, _BOX_TRIANGLES[:24], _BOX_TRIANGLES[:12]]) if lods else _BOX_TRIANGLES
+    return dict(vertex_bytes=8 * 12, index_bytes=72 * 4 if lods else 36 * 4, primitive_sets=ps, vertices=corners, indices=idx)
 
 
 def config2(num_drawables: int = 10_000_000, seed: int = 0xC0FFEE02, host_matrices: bool = True,

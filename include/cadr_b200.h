@@ -292,6 +292,16 @@ CADR_API int  cadr_b200_memset(cadr_ctx* ctx, uint64_t dstAddr, int value, size_
 CADR_API int  cadr_b200_upload(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n,
                                const void* stagingBase, cadr_stream stream);
 
+/* The same upload in two phases, for a renderer that overlaps the PCIe transfer of frame k + 1's uploads with the GPU work
+ * of frame k (the reference blocks on a fence per executeCopyOperations, Renderer.cpp:982-993, so its PCIe and GPU phases
+ * are serial).  upload_stage moves every region's bytes into a device-side staging slot on `copyStream` and touches no
+ * destination - the frame in flight may still read them; upload_commit makes `stream` wait for the staging (an event, not
+ * the host) and places the bytes with ONE scatter launch at HBM speed.  The context has two slots: at most two staged
+ * uploads may be outstanding.  *ticket == 0 after an empty stage (commit of 0 is a no-op). */
+CADR_API int  cadr_b200_upload_stage(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n, const void* stagingBase,
+                                     cadr_stream copyStream, uint64_t* ticket);
+CADR_API int  cadr_b200_upload_commit(cadr_ctx* ctx, uint64_t ticket, cadr_stream stream);
+
 /* Device-side scatter only: staging already resident in HBM at `stagingDevAddr` (srcOffset relative to
  * it).  This is the kernel the HBM roofline is quoted on for the upload path. */
 CADR_API int  cadr_b200_scatter_copy(cadr_ctx* ctx, const cadr_copy_region* regions, uint32_t n,

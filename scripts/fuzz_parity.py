@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Randomised parity soak on a GPU: random ragged scenes x random cameras x {fused, two calls} x {bounds on, off} against
 the oracle, for a time budget.  usage: scripts/fuzz_parity.py [seconds] [first_seed]   (CADR_B200_CULL_VARIANT selects
-the list kernel).  Prints one line per failure and a summary; exit code 1 if anything differed."""
+the list kernel when FUZZ_EXPERIMENTS=1 loads the A/B library libcadr_b200_exp.so).  Prints one line per failure and a summary; exit code 1 if anything differed."""
 import os
 import sys
 import time
@@ -13,6 +13,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cadr_b200  # noqa: E402
 from cadr_b200 import synth  # noqa: E402
+if os.environ.get("FUZZ_EXPERIMENTS") == "1":      # the A/B library: CADR_B200_CULL_VARIANT / CADR_B200_SMALL_STAGED select its kernels
+    from cadr_b200 import _capi, build
+    _capi.LIB_PATH = build.build_cuda(experiments=True)
 from cadr_b200.frame import DeviceScene, canon_equal, canonicalise  # noqa: E402
 from helpers import oracle_tier_x  # noqa: E402
 
@@ -76,6 +79,8 @@ while (only or time.time() < t_end):
     if os.environ.get("FUZZ_SEEDS") and not only:
         break
     seed += 1
-print(f"fuzz: {runs} frames over {seed - seed0} scenes, {fails} failures (variant {os.environ.get('CADR_B200_CULL_VARIANT', '2')})")
+print(f"fuzz: {runs} frames over {seed - seed0} scenes, {fails} failures (list variant {os.environ.get('CADR_B200_CULL_VARIANT', '2')}, "
+      f"staged fused pass {os.environ.get('CADR_B200_SMALL_STAGED', '0')}, library {'exp' if os.environ.get('FUZZ_EXPERIMENTS') == '1' else 'product'})")
+sys.exit(1 if fails else 0)
 ctx.close()
 sys.exit(1 if fails else 0)

@@ -4,10 +4,10 @@
 tag=${1:-r02b}
 N=${2:-2}
 mkdir -p gpurun_out
-run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 "${@:2}"; }
-( timeout 600 run 29541 tests/multigpu_check.py ) > gpurun_out/${tag}_multigpu_check.log 2>&1; echo "multigpu_check rc=$?"; grep -v "^W0\|^\*\*\*\|OMP_NUM" gpurun_out/${tag}_multigpu_check.log | tail -12
-( MG_ASYNC=1 MG_FRAMES=40 timeout 600 run 29542 tests/multigpu_check.py ) > gpurun_out/${tag}_multigpu_async.log 2>&1; echo "async rc=$?"; tail -2 gpurun_out/${tag}_multigpu_async.log
-( timeout 900 run 29543 bench.py --gpus $N --steps 100 --warmup 5 ) > gpurun_out/${tag}_bench_c3_${N}gpu.json 2> gpurun_out/${tag}_bench_c3_${N}gpu.err; echo "bench rc=$?"
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port"
+( timeout 600 $TR 29541 tests/multigpu_check.py ) > gpurun_out/${tag}_multigpu_check.log 2>&1; echo "multigpu_check rc=$?"; grep -v "^W0\|^\*\*\*\|OMP_NUM" gpurun_out/${tag}_multigpu_check.log | tail -12
+# (async variant: see r02b first run)
+( timeout 900 $TR 29543 bench.py --gpus $N --steps 100 --warmup 5 ) > gpurun_out/${tag}_bench_c3_${N}gpu.json 2> gpurun_out/${tag}_bench_c3_${N}gpu.err; echo "bench rc=$?"
 tail -c 1500 gpurun_out/${tag}_bench_c3_${N}gpu.err
 python - <<PY
 import json

@@ -478,3 +478,54 @@ def test_consumer_side_walk_matches_oracle(ctx, kw):
     finally:
         ctx.arena_free(digest)
         ds.close()
+
+
+@pytest.mark.parametrize("shape", ["c3", "c3-shard", "c2", "c1"])
+def test_consumer_side_walk_on_the_baseline_shapes(ctx, shape):
+    """The BASELINE shapes carry REAL box geometry (8 corners, 36 / 24 / 12 indices per LOD), so what bench.py's
+    multi-GPU verification walks at full size is walkable: consumer walk over every range of a small instance of each
+    shape == the oracle's digest; with a non-zero addressDelta on pointers moved by the opposite amount the digest is
+    unchanged (the translation a renderer GPU applies to another rank's records)."""
+    if shape == "c3":
+        sc, cam = synth.config3(300, 40, state_sets=8), synth.orbit_camera(30, 1500.0, far=3000.0)
+    elif shape == "c3-shard":
+        sc, cam = synth.config3_shard(900, 300, 300, 40, state_sets=8), synth.orbit_camera(30, 1500.0, far=3000.0)
+    elif shape == "c2":
+        sc, cam = synth.config2(5000), synth.orbit_camera(100, 1500.0, far=1500.0)
+    else:
+        sc, cam = synth.config1(12), synth.reference_camera(1)
+    planes, eye = cam
+    ds = DeviceScene(ctx, sc)
+    digest = ctx.arena_alloc(16)
+    try:
+        ds.upload_drawable_list()
+        ds.process_and_cull(planes, eye)
+        ctx.sync(ds.stream)
+        mem = ob.Memory([(ds.arena, sc.image(ds.arena)), (ds.drawable_list, np.ascontiguousarray(sc.drawables))])
+        _, _, ref = oracle_tier_x(sc, planes, eye, arena_base=ds.arena, list_base=ds.drawable_list)
+        p = ds.cull_params(planes, eye)
+        out, total = np.zeros(2, np.uint64), 0
+        for s in range(sc.num_state_sets):
+            if not int(sc.regions[s, 1]):
+                continue
+            ctx.consume_check_culled(p, s, int(sc.regions[s, 1]), digest)
+            ctx.memcpy_d2h(out, digest); ctx.sync()
+            e = ob.consume_check_culled(mem, ref, s)
+            assert (int(out[0]), int(out[1])) == e, f"range {s}"
+            total += e[1]
+        assert total > 1000
+        # address translation: shift every forwarded pointer by -delta, walk with +delta
+        n_cmd = ds.cmd_cap
+        ptr = ds._read(ds.ptr_out, n_cmd * 32, np.uint64).copy()
+        delta = 0x10000
+        live = ptr != 0
+        ptr[live] -= np.uint64(delta)
+        ctx.memcpy_h2d(ds.ptr_out, ptr); ctx.sync()
+        p.addressDelta = delta
+        s = int(np.nonzero(sc.regions[:, 1])[0][0])
+        ctx.consume_check_culled(p, s, int(sc.regions[s, 1]), digest)
+        ctx.memcpy_d2h(out, digest); ctx.sync()
+        assert (int(out[0]), int(out[1])) == ob.consume_check_culled(mem, ref, s)
+    finally:
+        ctx.arena_free(digest)
+        ds.close()
