@@ -19,6 +19,11 @@ struct DataAllocationRecord : RingRecord {     // deviceAddress, size come from 
 	DataAllocationRecord** recordPointer = nullptr;
 	void* stagingData = nullptr;
 	size_t stagingFrameNumber = size_t(-2);
+	/// DataStorage::uploadEpoch() when the staging block was handed out.  The reference reuses a staged block for every
+	/// further write of the same frame (DataAllocation.cpp:22-28, frame number only) - also after executeCopyOperations
+	/// has transferred and RELEASED that block in the middle of the frame, when the write lands in recycled staging memory
+	/// and never reaches the device.  The facade reuses a block only while nothing has been transferred since.
+	uint64_t stagingEpoch = 0;
 };
 
 class StagingData {

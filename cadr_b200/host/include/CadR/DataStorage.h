@@ -35,6 +35,7 @@ class DataStorage {
 	DataAllocationRecord _zeroSizeAllocationRecord;
 	StagingManager* _stagingManager = nullptr;
 	size_t _stagingDataSizeHint = 0;
+	uint64_t _uploadEpoch = 1;             // bumped by every recordUploads() that transferred something
 	HandleTable _handleTable;
 	DataAllocationRecord* allocInternal(size_t numBytes);
 	std::tuple<StagingMemory&, bool> allocStagingMemory(DataMemory& m, StagingMemory* lastStagingMemory,
@@ -51,6 +52,9 @@ public:
 	Renderer& renderer() const { return *_renderer; }
 	StagingManager& stagingManager() const { return *_stagingManager; }
 	size_t stagingDataSizeHint() const { return _stagingDataSizeHint; }
+	uint64_t uploadEpoch() const { return _uploadEpoch; }
+	/// Was this record staged in the current frame AND has nothing been transferred since (its staging block is still its own)?
+	bool stagedAndNotYetTransferred(const DataAllocationRecord* a) const;
 	void setStagingDataSizeHint(size_t size) { _stagingDataSizeHint = size; }
 
 	DataAllocationRecord* alloc(size_t numBytes);

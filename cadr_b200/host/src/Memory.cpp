@@ -270,7 +270,13 @@ DataAllocationRecord* DataStorage::alloc(size_t numBytes)
 	if(numBytes == 0) return &_zeroSizeAllocationRecord;   // null-object pattern (DataStorage.cpp:121-127)
 	DataAllocationRecord* a = allocInternal(numBytes);
 	a->stagingFrameNumber = _renderer->frameNumber();
+	a->stagingEpoch = _uploadEpoch;
 	return a;
+}
+
+bool DataStorage::stagedAndNotYetTransferred(const DataAllocationRecord* a) const
+{
+	return a->stagingFrameNumber == _renderer->frameNumber() && a->stagingEpoch == _uploadEpoch;
 }
 
 DataAllocationRecord* DataStorage::realloc(DataAllocationRecord* allocationRecord, size_t numBytes)
@@ -278,6 +284,7 @@ DataAllocationRecord* DataStorage::realloc(DataAllocationRecord* allocationRecor
 	if(numBytes == 0) { free(allocationRecord); return &_zeroSizeAllocationRecord; }
 	DataAllocationRecord* a = allocInternal(numBytes);   // throws before anything is released
 	a->stagingFrameNumber = _renderer->frameNumber();
+	a->stagingEpoch = _uploadEpoch;
 	if(allocationRecord->size != 0) DataMemory::free(allocationRecord);
 	return a;
 }
@@ -319,6 +326,7 @@ std::tuple<TransferResources, size_t> DataStorage::recordUploads(void* stream)
 		bytes += b;
 	}
 	if(pending->empty()) return {TransferResources(), 0};
+	_uploadEpoch++;          // staging blocks of everything staged so far are released when this transfer completes
 	TransferResources tr([pending]() { for(auto& [dm, p] : *pending) dm->uploadDone(p); });
 	if(uploadObserver) uploadObserver(regions.data(), regions.size());
 	cadr_ctx* ctx = _stagingManager->context();
@@ -347,7 +355,7 @@ size_t HandlelessAllocation::offset() const { return size_t(_record->deviceAddre
 StagingData HandlelessAllocation::alloc(size_t size)
 {
 	// reuse what was staged earlier in this frame (DataAllocation.cpp:54-69)
-	if(_record->stagingFrameNumber == _storage->renderer().frameNumber() && size <= _record->size) {
+	if(_storage->stagedAndNotYetTransferred(_record) && size <= _record->size) {
 		_record->size = size;
 		return StagingData(_record, false);
 	}
@@ -357,7 +365,7 @@ StagingData HandlelessAllocation::alloc(size_t size)
 
 StagingData HandlelessAllocation::alloc()
 {
-	if(_record->stagingFrameNumber == _storage->renderer().frameNumber())
+	if(_storage->stagedAndNotYetTransferred(_record))
 		return StagingData(_record, false);
 	_record = _storage->realloc(_record, _record->size);
 	return StagingData(_record, true);

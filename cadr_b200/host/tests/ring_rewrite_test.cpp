@@ -88,6 +88,51 @@ int main(int argc, char** argv)
 					if(!m->ringEmpty()) throw std::runtime_error("Not all memory was released (" + std::to_string(count) + " x " + std::to_string(bytes) + ")");
 			}
 		}
+		// ---- writes after a transfer in the middle of a frame ------------------------------------------------------
+		// The reference hands the SAME staging block out again for every write of a frame (DataAllocation.cpp:22-28), also
+		// after executeCopyOperations() has transferred and released it: the second write then lands in recycled staging
+		// memory and never reaches the device (an application that builds a big scene in batches inside one frame, or the
+		// handle table's leaf that receives entries before and after the transfer).  The facade re-allocates instead.
+		{
+			Renderer r(device);
+			DataStorage& ds = r.dataStorage();
+			std::map<uint64_t, std::vector<uint8_t>> mirror;
+			ds.uploadObserver = [&](const cadr_copy_region* regs, size_t n) {
+				for(size_t i = 0; i < n; i++)
+					for(const DataMemory* m : ds.dataMemoryList())
+						if(regs[i].dstAddr >= m->deviceAddress() && regs[i].dstAddr + regs[i].bytes <= m->deviceAddress() + m->size()) {
+							auto& img = mirror[m->deviceAddress()];
+							img.resize(m->size());
+							std::memcpy(img.data() + (regs[i].dstAddr - m->deviceAddress()), reinterpret_cast<const void*>(regs[i].srcOffset), regs[i].bytes);
+						}
+			};
+			auto deviceByte = [&](uint64_t addr) -> int {
+				for(auto& [base, img] : mirror) if(addr >= base && addr < base + img.size()) return img[addr - base];
+				return -1;
+			};
+			r.beginFrame();
+			std::vector<DataAllocation> objs;
+			HandlelessAllocation a(ds);
+			std::memset(a.alloc(256).data(), 0x11, 256);
+			for(int i = 0; i < 100; i++) { objs.emplace_back(ds); std::memset(objs.back().alloc(64).data(), i, 64); }    // handle table entries 1..100
+			r.executeCopyOperations();
+			if(deviceByte(a.deviceAddress()) != 0x11) throw std::runtime_error("first write did not reach the device");
+			StagingData again = a.alloc(256);                     // same frame, after the transfer
+			if(!again.wasReallocated()) throw std::runtime_error("a block that was already transferred and released was handed out again");
+			std::memset(again.data(), 0x22, 256);
+			for(int i = 0; i < 100; i++) { objs.emplace_back(ds); std::memset(objs.back().alloc(64).data(), 100 + i, 64); }   // more entries into the same leaf table
+			r.executeCopyOperations();
+			r.endFrame();
+			if(deviceByte(a.deviceAddress()) != 0x22) throw std::runtime_error("second write of the frame did not reach the device");
+			// every handle of the (re-staged) leaf table resolves to its object's address
+			const uint64_t root = ds.handleTableDeviceAddress();
+			for(size_t i = 0; i < objs.size(); i++) {
+				uint64_t entry = 0;
+				for(int b = 7; b >= 0; b--) entry = (entry << 8) | uint64_t(deviceByte(root + 8 * objs[i].handle() + b) & 0xff);
+				if(entry != objs[i].deviceAddress()) throw std::runtime_error("handle " + std::to_string(objs[i].handle()) + " does not resolve after a mid-frame transfer");
+				if(deviceByte(objs[i].deviceAddress()) != int(i)) throw std::runtime_error("object data lost");
+			}
+		}
 		printf("ring_rewrite_test ok: %zu frames, %zu copy regions, largest %zu bytes\n", frames, regions, maxRegionBytes);
 		return 0;
 	}

@@ -529,3 +529,49 @@ def test_consumer_side_walk_on_the_baseline_shapes(ctx, shape):
     finally:
         ctx.arena_free(digest)
         ds.close()
+
+
+def test_two_phase_upload_stages_on_a_copy_stream_and_commits_in_order(ctx):
+    """cadr_b200_upload_stage / _commit against the oracle's copy regions (DataMemory::recordUploads, DataMemory.cpp:400-446):
+    nothing reaches a destination before the commit; two staged uploads may be outstanding (two slots), a third is refused;
+    commits apply in the order they are issued (the later one wins where regions overlap); regions above 1 MiB go
+    through the staging slot as well; a ticket cannot be committed twice; other calls of the upload family keep working
+    while one upload is staged."""
+    import torch
+    rng = np.random.default_rng(19)
+    size = 6 << 20
+    arena = ctx.arena_alloc(size)
+    copy_stream = torch.cuda.Stream()
+    try:
+        ctx.memset(arena, 0, size); ctx.sync()
+        host = np.zeros(size, np.uint8)
+        st_a = rng.integers(0, 256, 4 << 20, dtype=np.uint8)
+        st_b = rng.integers(0, 256, 4 << 20, dtype=np.uint8)
+        regs_a = np.array([[arena + 64 + 4096 * i, 3000 * i, 2500 + i] for i in range(300)] + [[arena + (3 << 20), 1 << 20, (1 << 20) + 777]], np.uint64)
+        regs_b = np.array([[arena + 64 + 4096 * i + 1024, 5000 * i + 16, 3000] for i in range(200)], np.uint64)     # overlaps regs_a's ranges
+        ta = ctx.upload_stage(regs_a, st_a, copy_stream.cuda_stream)
+        tb = ctx.upload_stage(regs_b, st_b, copy_stream.cuda_stream)
+        assert ta and tb and ta != tb
+        with pytest.raises(cadr_b200.LogicError):
+            ctx.upload_stage(regs_b, st_b, copy_stream.cuda_stream)          # both slots hold staged uploads
+        copy_stream.synchronize(); ctx.sync()
+        got = np.empty(size, np.uint8)
+        ctx.memcpy_d2h(got, arena); ctx.sync()
+        assert not got.any(), "staging touched a destination"
+        ctx.upload_commit(ta)
+        # one slot is free again: the single-call forms work while tb is still staged
+        small = np.array([[arena + (5 << 20), 64, 4000]], np.uint64)
+        ctx.upload(small, st_a)
+        ctx.upload_commit(tb)
+        ctx.sync()
+        ctx.memcpy_d2h(got, arena); ctx.sync()
+        mem = ob.Memory([(arena, host)])
+        ob.upload(mem, regs_a, st_a); ob.upload(mem, small, st_a); ob.upload(mem, regs_b, st_b)
+        assert np.array_equal(got, host)
+        with pytest.raises(cadr_b200.LogicError):
+            ctx.upload_commit(tb)
+        assert ctx.upload_stage(np.zeros((0, 3), np.uint64), st_a, copy_stream.cuda_stream) == 0
+        ctx.upload_commit(0)
+    finally:
+        ctx.sync()
+        ctx.arena_free(arena)
