@@ -206,7 +206,8 @@ def cpu_sample_run(args, steps: int, warmup: int, sample_drawables: int | None =
             times.append(dt)
     sec = statistics.median(times)
     desc = (f"{sc.n} of the workload's drawables ({inst} instances): oracle processDrawables + per-instance "
-            f"cull/LOD evaluation, OpenMP {threads} threads, median of {steps} frames")
+            f"cull/LOD evaluation and survivor COUNT (no emission of commands / instance indices: the part of the path that "
+            f"parallelises trivially, i.e. favourable to the CPU), OpenMP {threads} threads, median of {steps} frames")
     return inst / sec, desc, threads, sec
 
 
@@ -683,7 +684,9 @@ def run_b200(args):
                        large_name: round(k_large, 4)},
         "entry": "cadr_b200_process_drawables + cadr_b200_cull_compact" if args.unfused else "cadr_b200_process_and_cull",
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": recorded_traffic({"c4": "c3"}.get(args.workload, args.workload) if not args.drawables and args.instances == 1000 and not args.list_bounds else "", dom_name), "peak_source": peak_src,
+                     "frac": round(achieved / peak, 4), "traffic": recorded_traffic(args.workload if not args.drawables and args.instances == 1000 and not args.list_bounds else "", dom_name),
+                     "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload (not measured in this run)",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(alg_bytes), "algorithmic_bytes": alg_note, "launch_ms": round(dom_ms, 4)},
         "clocks": clocks,
         "tier_r": {"kernel": "processDrawablesKernel", "drawables": scene.n, "launch_ms": round(tier_r_ms, 4),
