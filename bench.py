@@ -354,6 +354,8 @@ def run_b200(args):
                               arena=ds.arena, first_drawable=int(scene.gen.get("first", 0)))
 
     RENDERER = 0            # the rank whose GPU plays the renderer in the "instance runs pulled" series
+    pull_t = torch.cuda.Stream(device=dev)
+    pull_state = {"pending": False, "ready": torch.cuda.Event(), "done": torch.cuda.Event()}
 
     def run_cull(k, with_exchange, pull=False):
         planes, eye = cams[k % 360]
@@ -365,9 +367,17 @@ def run_b200(args):
                 ctx.cull_compact(p, stream=stream)
             else:
                 ctx.process_and_cull(p, stream=stream)
+            if pull and rank == RENDERER and pull_state["pending"]:
+                # the pull of the previous frame runs on its own stream next to this frame's cull; it has to be over before
+                # this rank publishes, because the publish is what lets the peers go on to the frame that rewrites those runs
+                stream_t.wait_event(pull_state["done"])
             px.end_frame(ds.counters, stream=stream)
             if pull and rank == RENDERER:
-                px.pull_instances(stream=stream)
+                pull_state["ready"].record(stream_t)
+                pull_t.wait_event(pull_state["ready"])
+                px.pull_instances(stream=pull_t.cuda_stream)
+                pull_state["done"].record(pull_t)
+                pull_state["pending"] = True
             return
         if args.unfused:
             ds.process_drawables()
@@ -727,7 +737,8 @@ def run_b200(args):
                                           "ms_per_step": round(ms_pull / args.steps, 4), "survivor_fraction": round(p, 4),
                                           "inbound_bytes_per_step_on_renderer": int(4 * p * inst * (world - 1)),
                                           "what": "value's frame + cadr_b200_exchange_pull_instances on rank 0: 4 B x survivors of the other "
-                                                  "ranks cross NVLink into one renderer-visible index buffer; matrices stay sharded"}
+                                                  "ranks cross NVLink into one renderer-visible index buffer (on a second stream, next to the "
+                                                  "following frame's cull; this rank publishes that frame only when the pull is over); matrices stay sharded"}
         if verify is not None:
             line["exchange_verified"] = verify["ok"]
             line["verification"] = verify

@@ -59,7 +59,14 @@ __global__ void pullInstancesKernel(const __grid_constant__ cadr_exchange_pull P
 	if(t < head) dst[t] = src[t];
 	const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
 	uint4* d4 = reinterpret_cast<uint4*>(dst + head);
-	for(uint32_t i = t; i < vec; i += stride) d4[i] = ldg_stream_u4(s4 + i);
+	// four independent 16-byte requests in flight per thread: a peer read takes a few microseconds, only the number of
+	// outstanding requests fills the link
+	uint32_t i = t;
+	for(; i + 3u * stride < vec; i += 4u * stride) {
+		const uint4 a = ldg_stream_u4(s4 + i), b = ldg_stream_u4(s4 + i + stride), c = ldg_stream_u4(s4 + i + 2u * stride), e = ldg_stream_u4(s4 + i + 3u * stride);
+		d4[i] = a; d4[i + stride] = b; d4[i + 2u * stride] = c; d4[i + 3u * stride] = e;
+	}
+	for(; i < vec; i += stride) d4[i] = ldg_stream_u4(s4 + i);
 	if(t < n - tailStart) dst[tailStart + t] = src[tailStart + t];
 }
 
@@ -187,11 +194,10 @@ int cadr_b200_exchange_pull_instances(cadr_ctx* ctx, const cadr_exchange_pull* p
 	if((pull->instCapacity & 3) != 0)
 		return setError(CADR_E_LOGIC, "exchange_pull_instances: instCapacity must be a multiple of 4 elements");
 	cudaStream_t s = ctx->pick(stream);
-	// enough CTAs per (rank, range) column to keep many 16-byte requests in flight over NVLink
+	// enough CTAs per (rank, range) column to keep many 16-byte requests in flight over NVLink; in a partitioned scene most
+	// columns are empty (a rank holds a few of the StateSets) and leave at once, so the grid is sized for the live ones
 	const uint32_t columns = pull->world * pull->numRanges;
-	uint32_t perColumn = (uint32_t(ctx->smCount) * 8u + columns - 1) / columns;
-	if(perColumn < 1) perColumn = 1;
-	if(perColumn > 64) perColumn = 64;
+	const uint32_t perColumn = 32;
 	pullInstancesKernel<<<dim3(perColumn, columns), 256, 0, s>>>(*pull);
 	ctx->launches++;
 	CADR_CUDA(cudaGetLastError());
