@@ -10,7 +10,13 @@ namespace cadr {
 
 constexpr uint32_t SMALL_MAX  = CADR_CULL_SMALL_LIST_MAX;        // lists up to this many matrices are handled by one thread
 constexpr uint32_t CHUNK      = CADR_CULL_WORK_ITEM_INSTANCES;   // instances per work item of the list kernels
-constexpr int      CS_THREADS = 256;
+// Threads per CTA of the thread-per-drawable kernels.  64 since round 2: the kernel is latency-bound (three dependent DRAM round
+// trips per thread) and every CTA barrier makes all its warps wait for the slowest chain, with the CTA's registers held until
+// its last warp is done; two warps per CTA couple far less than eight.  Measured on B200, same box, interleaved
+// (profiles/r02i_cta_size.jsonl): C2 0.508 / 0.484 / 0.474 ms at 256 / 128 / 64 threads, C1 0.0755 / 0.0735 / 0.0721 ms; one warp
+// per CTA (one reservation atomic per warp on C2's single counter) falls to 0.795 ms.
+constexpr int      CS_THREADS = 64;
+constexpr int      CS_MAX_WARPS = 8;                                // scratch is sized for the largest CTA any variant uses (256 threads)
 
 // Self-contained work item of the list kernels: 128 bytes, written by cullSmallKernel.
 struct __align__(16) WorkItem {
@@ -51,6 +57,7 @@ struct CullArgs {
 	uint32_t  medMax;                     // lists of SMALL_MAX < n <= medMax matrices go to the medium queue (0: there is none)
 #ifdef CADR_B200_EXPERIMENTS
 	uint32_t  diagNoEval;                 // CADR_B200_DIAG_NOEVAL=1: list kernels skip the evaluation (memory-system ceiling of the access structure)
+	uint32_t  pfDistance;                 // CADR_B200_SMALL_PREFETCH=<CTAs>: the fused first kernel prefetches for the drawable this many CTAs ahead
 #endif
 	float4 plane[6];
 	float4 eye;

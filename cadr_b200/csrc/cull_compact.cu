@@ -61,9 +61,9 @@ __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_
 
 // Scratch of one CTA of the thread-per-drawable kernels (block-aggregated reservations).
 struct SmallShared {
-	uint32_t chunkTot[CS_THREADS / 32];
-	uint32_t groupTot[CS_THREADS / 32];
-	uint32_t medTot[CS_THREADS / 32];
+	uint32_t chunkTot[CS_MAX_WARPS];
+	uint32_t groupTot[CS_MAX_WARPS];
+	uint32_t medTot[CS_MAX_WARPS];
 	uint32_t chunkBase;
 	uint32_t medBase;
 	uint32_t domSet;
@@ -79,9 +79,9 @@ __device__ __forceinline__ void smallListsBody(const CullArgs& A, SmallShared& s
                                                const uint4 ca, const uint4 cb, const uint4 cc, const uint4 p0, const uint4 p1,
                                                const uint64_t psBaseResolved, FirstMatrix firstMatrix)
 {
-	uint32_t (&sChunkTot)[CS_THREADS / 32] = sh.chunkTot;
-	uint32_t (&sGroupTot)[CS_THREADS / 32] = sh.groupTot;
-	uint32_t (&sMedTot)[CS_THREADS / 32] = sh.medTot;
+	uint32_t (&sChunkTot)[CS_MAX_WARPS] = sh.chunkTot;
+	uint32_t (&sGroupTot)[CS_MAX_WARPS] = sh.groupTot;
+	uint32_t (&sMedTot)[CS_MAX_WARPS] = sh.medTot;
 	uint32_t& sChunkBase = sh.chunkBase;
 	uint32_t& sMedBase = sh.medBase;
 	uint32_t& sDomSet = sh.domSet;
@@ -279,13 +279,13 @@ __device__ __forceinline__ void smallListsBody(const CullArgs& A, SmallShared& s
 
 // FUSED = true additionally does the work of processDrawablesKernel for the same drawable (handle resolve + Tier R
 // records), so the drawable list is read once per frame and the indirect / pointers records are not re-read.
-template<int LEVEL, bool FUSED>
-__global__ void __launch_bounds__(CS_THREADS)
+template<int LEVEL, bool FUSED, int THREADS = CS_THREADS>
+__global__ void __launch_bounds__(THREADS)
 cullSmallKernel(const __grid_constant__ CullArgs A)
 {
 	__shared__ SmallShared sh;
 	const int tid = threadIdx.x;
-	const uint32_t d = blockIdx.x * CS_THREADS + tid;
+	const uint32_t d = blockIdx.x * THREADS + tid;
 	const bool valid = d < A.n;
 	uint32_t N = 0;
 	uint4 p0 = make_uint4(0, 0, 0, 0), p1 = p0;
@@ -301,6 +301,23 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 		}
 	}
 	if constexpr(FUSED) {
+#ifdef CADR_B200_EXPERIMENTS
+		// Experiment (CADR_B200_SMALL_PREFETCH): this thread also walks the MatrixList handle of the drawable `pfDistance` CTAs
+		// ahead and requests that list's line into L2, and requests the record / culling-record lines of the drawable twice
+		// as far ahead - so that the three dependent DRAM round trips of a drawable become L2 hits when its own thread runs.
+		if(A.pfDistance) {
+			const uint64_t dF = uint64_t(d) + uint64_t(A.pfDistance) * CS_THREADS, dFF = dF + uint64_t(A.pfDistance) * CS_THREADS;
+			if(dFF < A.n) {
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(A.drawableList + 48ull * dFF));
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const uint8_t*>(A.cullData) + 48ull * dFF));
+			}
+			if(dF < A.n) {
+				const uint64_t hF = ldg_u64(reinterpret_cast<uint64_t>(A.drawableList) + 48ull * dF + 16);
+				const uint64_t mlF = lookupHandle<LEVEL>(A.root, hF);
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(mlF));
+			}
+		}
+#endif
 		if(valid) {
 			// processDrawables.comp main() :92-113 for this drawable (see process_drawables.cu)
 			const uint4* rec = reinterpret_cast<const uint4*>(A.drawableList) + size_t(d) * 3;
@@ -325,7 +342,7 @@ cullSmallKernel(const __grid_constant__ CullArgs A)
 	}
 
 	const uint8_t* m0 = reinterpret_cast<const uint8_t*>(uint64_t(p1.x) | (uint64_t(p1.y) << 32)) + CADR_MATRIX_LIST_HEADER_BYTES;
-	smallListsBody<LEVEL, FUSED, CS_THREADS>(A, sh, d, valid, N, ca, cb, cc, p0, p1, psBaseResolved, [m0]() { return loadMat(m0); });
+	smallListsBody<LEVEL, FUSED, THREADS>(A, sh, d, valid, N, ca, cb, cc, p0, p1, psBaseResolved, [m0]() { return loadMat(m0); });
 }
 
 #ifdef CADR_B200_EXPERIMENTS
@@ -498,6 +515,71 @@ cullSmallStagedKernel(const __grid_constant__ CullArgs A)
 		}
 		cur = nxt; curPsCount = nxtPsCount; curPsFirst = nxtPsFirst;
 		nxt = nx2; psOffB = psOffC;
+	}
+	asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// The light version of the same idea (experiment, CADR_B200_SMALL_STAGED=3): only the FIRST of the three dependent round
+// trips is taken off the critical path.  A persistent CTA (four per SM, 48 KiB of staging each) requests the records and
+// culling records of its next tile with LDGSTS while it works on the current one; walks, the MatrixList line and the
+// evaluation are the direct-load code of cullSmallKernel, nothing is carried across iterations in registers, so the
+// register budget - and with it the number of resident warps - stays that of the direct kernel.
+template<int LEVEL>
+__global__ void __launch_bounds__(256, 4)
+cullSmallRecordsStagedKernel(const __grid_constant__ CullArgs A)
+{
+	constexpr int CS_THREADS = 256;              // (this experiment keeps the CTA size it was measured with)
+	constexpr uint32_t REC_BYTES = CS_THREADS * 48u;
+	extern __shared__ __align__(128) uint8_t stSmem[];
+	__shared__ SmallShared sh;
+	const uint32_t tid = threadIdx.x;
+	const uint32_t sRec = smemAddr(stSmem), sCull = sRec + 2 * REC_BYTES;
+	auto tileBase = [&](uint32_t k) -> uint64_t { return (uint64_t(blockIdx.x) + uint64_t(k) * gridDim.x) * CS_THREADS; };
+	auto tileCount = [&](uint32_t k) -> uint32_t { const uint64_t b = tileBase(k); return b >= A.n ? 0u : uint32_t(min(uint64_t(CS_THREADS), A.n - b)); };
+	auto request = [&](uint32_t k) {
+		const uint32_t chunks = tileCount(k) * 3u;
+		const uint8_t* r = A.drawableList + tileBase(k) * 48ull;
+		const uint8_t* c = reinterpret_cast<const uint8_t*>(A.cullData) + tileBase(k) * 48ull;
+		const uint32_t dr = sRec + (k & 1u) * REC_BYTES, dc = sCull + (k & 1u) * REC_BYTES;
+#pragma unroll
+		for(uint32_t i = 0; i < 3; i++)
+			if(i * CS_THREADS + tid < chunks) {
+				cpAsync16(dr + (i * CS_THREADS + tid) * 16u, r + (i * CS_THREADS + tid) * 16ull);
+				cpAsync16(dc + (i * CS_THREADS + tid) * 16u, c + (i * CS_THREADS + tid) * 16ull);
+			}
+		cpAsyncCommit();
+	};
+	request(0);
+	for(uint32_t k = 0; tileBase(k) < A.n; k++) {
+		request(k + 1u);        // slot (k+1)&1 was read at the top of iteration k-1; every thread has passed a barrier of that iteration's body since
+		asm volatile("cp.async.wait_group 1;" ::: "memory");
+		__syncthreads();
+		const bool valid = tid < tileCount(k);
+		const uint32_t d = uint32_t(tileBase(k)) + tid;
+		uint32_t N = 0;
+		uint4 p0 = make_uint4(0, 0, 0, 0), p1 = p0, ca = p0, cb = p0, cc = p0;
+		uint64_t psBaseResolved = 0;
+		if(valid) {
+			const uint32_t rec = sRec + (k & 1u) * REC_BYTES + tid * 48u, cul = sCull + (k & 1u) * REC_BYTES + tid * 48u;
+			const uint4 ra = ldsU4(rec), rb = ldsU4(rec + 16u), rc = ldsU4(rec + 32u);
+			ca = ldsU4(cul); cb = ldsU4(cul + 16u); cc = ldsU4(cul + 32u);
+			// processDrawables.comp main() :92-113 (as in cullSmallKernel)
+			const uint64_t ml = lookupHandle<LEVEL>(A.root, uint64_t(rb.x) | (uint64_t(rb.y) << 32));
+			const uint64_t psb = lookupHandle<LEVEL>(A.root, uint64_t(rc.x) | (uint64_t(rc.y) << 32));
+			const uint64_t vd = lookupHandle<LEVEL>(A.root, uint64_t(ra.x) | (uint64_t(ra.y) << 32));
+			const uint64_t id = lookupHandle<LEVEL>(A.root, uint64_t(ra.z) | (uint64_t(ra.w) << 32));
+			const uint64_t dd = lookupHandle<LEVEL>(A.root, uint64_t(rb.z) | (uint64_t(rb.w) << 32));
+			N = ldg_u32(ml);
+			const uint32_t psCount = ldg_u32(psb + rc.z), psFirst = ldg_u32(psb + rc.z + 4);
+			p0 = make_uint4(uint32_t(vd), uint32_t(vd >> 32), uint32_t(id), uint32_t(id >> 32));
+			p1 = make_uint4(uint32_t(ml), uint32_t(ml >> 32), uint32_t(dd), uint32_t(dd >> 32));
+			psBaseResolved = psb;
+			st_stream_u4(const_cast<uint4*>(A.indirect) + d, make_uint4(psCount, N, psFirst, 0u));
+			st_stream_u4(const_cast<uint4*>(A.pointers) + 2ull * d, p0);
+			st_stream_u4(const_cast<uint4*>(A.pointers) + 2ull * d + 1, p1);
+		}
+		const uint8_t* m0 = reinterpret_cast<const uint8_t*>(uint64_t(p1.x) | (uint64_t(p1.y) << 32)) + CADR_MATRIX_LIST_HEADER_BYTES;
+		smallListsBody<LEVEL, true, CS_THREADS>(A, sh, d, valid, N, ca, cb, cc, p0, p1, psBaseResolved, [m0]() { return loadMat(m0); });
 	}
 	asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
@@ -1298,6 +1380,7 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 	A.eye = make_float4(p.eye[0], p.eye[1], p.eye[2], 0.f);
 #ifdef CADR_B200_EXPERIMENTS
 	{ const char* dg = std::getenv("CADR_B200_DIAG_NOEVAL"); A.diagNoEval = (dg && dg[0] == '1') ? 1u : 0u; }
+	{ const char* pf = std::getenv("CADR_B200_SMALL_PREFETCH"); A.pfDistance = pf ? uint32_t(std::atoi(pf)) : 0u; }
 #endif
 	A.xWorld = exchange ? p.exchangeWorld : 0;
 	A.xSlotBase = exchange ? p.exchangeRank * p.exchangeCmdCapacity : 0;
@@ -1318,7 +1401,31 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 #ifdef CADR_B200_EXPERIMENTS
 	// A/B: the fused pass with the indirection staged through shared memory (cullSmallStagedKernel): parity-green, but slower
 	// than the direct-load kernel on every shape measured so far (profiles/r02c_*), so it is not in the product library
-	if(const char* v = std::getenv("CADR_B200_SMALL_STAGED"); fused && v && v[0] >= '1') {
+	if(const char* v = std::getenv("CADR_B200_SMALL_THREADS"); fused && v && (std::atoi(v) == 256 || std::atoi(v) == 128 || std::atoi(v) == 32)) {
+		const uint32_t t = uint32_t(std::atoi(v)), g = (p.numDrawables + t - 1) / t;      // the same kernel with other CTA sizes (product: CS_THREADS)
+		switch(p.handleLevel * 1000 + t) {
+		case 1256: cullSmallKernel<1, true, 256><<<g, 256, 0, s>>>(A); break;
+		case 2256: cullSmallKernel<2, true, 256><<<g, 256, 0, s>>>(A); break;
+		case 3256: cullSmallKernel<3, true, 256><<<g, 256, 0, s>>>(A); break;
+		case 1128: cullSmallKernel<1, true, 128><<<g, 128, 0, s>>>(A); break;
+		case 2128: cullSmallKernel<2, true, 128><<<g, 128, 0, s>>>(A); break;
+		case 3128: cullSmallKernel<3, true, 128><<<g, 128, 0, s>>>(A); break;
+		case 1032: cullSmallKernel<1, true, 32><<<g, 32, 0, s>>>(A); break;
+		case 2032: cullSmallKernel<2, true, 32><<<g, 32, 0, s>>>(A); break;
+		default:   cullSmallKernel<3, true, 32><<<g, 32, 0, s>>>(A); break;
+		}
+	}
+	else if(const char* v = std::getenv("CADR_B200_SMALL_STAGED"); fused && v && v[0] == '3') {
+		const void* fn = p.handleLevel == 1 ? (const void*)cullSmallRecordsStagedKernel<1> : p.handleLevel == 2 ? (const void*)cullSmallRecordsStagedKernel<2> : (const void*)cullSmallRecordsStagedKernel<3>;
+		const size_t smem = 4 * 256 * 48;                // two slots x (records + culling records) = 48 KiB
+		CADR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+		uint32_t gridP = uint32_t(ctx->smCount) * 4u;
+		const uint32_t tiles = (p.numDrawables + 255) / 256;
+		if(gridP > tiles) gridP = tiles;
+		void* args[] = {(void*)&A};
+		CADR_CUDA(cudaLaunchKernel(fn, dim3(gridP), dim3(256), args, smem, s));
+	}
+	else if(const char* v = std::getenv("CADR_B200_SMALL_STAGED"); fused && v && v[0] >= '1') {
 		const bool small = v[0] == '2';            // 1: tiles of 256, two CTAs per SM; 2: tiles of 128, four CTAs per SM
 		const int tile = small ? 128 : 256;
 		const void* fn = nullptr;

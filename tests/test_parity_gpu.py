@@ -575,3 +575,40 @@ def test_two_phase_upload_stages_on_a_copy_stream_and_commits_in_order(ctx):
     finally:
         ctx.sync()
         ctx.arena_free(arena)
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["two-calls", "fused"])
+def test_primitive_set_offsets_need_only_four_byte_alignment(ctx, fused):
+    """PrimitiveSetRef is declared buffer_reference_align = 4 (processDrawables.comp:29-33): a primitiveSetOffset /
+    lodPrimitiveSetOffset that is a multiple of 4 but not of 8 is legal.  Round 1 read the PrimitiveSets of QUEUED lists
+    (more than 32 matrices) with one 8-byte load and would have faulted here; short, medium and long lists all take
+    such offsets now (advisor finding)."""
+    counts = [1, 7, 32, 33, 50, 64, 65, 200, 1024, 1500]
+    sc = synth.random_scene(71, n=60, num_geometries=5, list_counts=counts, state_sets=3)
+    P = sc.gen["build"]["geometries"]
+    per_geom = np.array([g["primitive_sets"].shape[0] for g in P])
+    room = per_geom[sc.drawable_geom] * 8                              # bytes of each drawable's PrimitiveSet array
+    # odd multiples of 4 wherever 8 bytes still fit inside the array
+    off = sc.cull[:, 5:8].astype(np.int64)
+    new = np.where(off + 4 + 8 <= room[:, None], off + 4, off)
+    sc.cull[:, 5:8] = new.astype(np.uint32)
+    rec_off = (sc.drawables[:, 5] & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    rec_new = np.where(rec_off + 4 + 8 <= room, rec_off + 4, rec_off)
+    sc.drawables[:, 5] = rec_new.astype(np.uint64)
+    assert (new % 8 == 4).any() and (rec_new % 8 == 4).any()
+    ds = DeviceScene(ctx, sc)
+    try:
+        planes, eye = synth.orbit_camera(40, 250.0, far=500.0)
+        if fused:
+            ds.upload_drawable_list(); ds.process_and_cull(planes, eye)
+        else:
+            ds.record_drawable_processing(); ds.cull(planes, eye)
+        ctx.sync(ds.stream)
+        got = ds.read_tier_x()
+        ind, ptr = ds.read_tier_r()
+        e_ind, e_ptr, ref = oracle_tier_x(sc, planes, eye, arena_base=ds.arena, list_base=ds.drawable_list)
+        assert np.array_equal(ind, e_ind) and np.array_equal(ptr, e_ptr)
+        assert_tier_x_equal(got, ref)
+        assert got["inst_count"].sum() > 0
+    finally:
+        ds.close()
