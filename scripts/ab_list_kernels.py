@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """A/B of the long-list kernel variants over MatrixList lengths in ONE process: the scene of each length is built once,
-then every variant (CADR_B200_CULL_VARIANT, read by the library at each launch) is timed on it, interleaved, with CUDA
+then every variant (CADR_B200_CULL_VARIANT, read at each launch by the A/B library libcadr_b200_exp.so, which this script loads
+instead of the product library) is timed on it, interleaved, with CUDA
 events around the frames and the library's per-kernel events.  Every variant's result is compared with variant 2's
 (counters and canonicalised commands) before it is timed.
 usage: scripts/ab_list_kernels.py [--lengths 33,64,...] [--variants 2,4,5] [--total 100000000] [--steps 30] [--rounds 2]
@@ -29,6 +30,8 @@ def main():
     a = ap.parse_args()
 
     import torch
+    from cadr_b200 import _capi, build
+    _capi.LIB_PATH = build.build_cuda(experiments=True)     # the product library has one path and reads no environment
     import cadr_b200
     from cadr_b200 import synth
     from cadr_b200.frame import DeviceScene, canon_equal, canonicalise
