@@ -612,3 +612,43 @@ def test_primitive_set_offsets_need_only_four_byte_alignment(ctx, fused):
         assert got["inst_count"].sum() > 0
     finally:
         ds.close()
+
+
+def test_back_to_back_frames_read_complete_counters(ctx):
+    """Stream order across the programmatic dependent launch: cullMediumKernel is launched behind cullListWarpKernel with
+    programmatic stream serialisation and leaves at once when there are no medium lists (the C3 shape) - without
+    griddepcontrol.wait in it, its completion would not imply the list kernel's, and the counters D2H / the next frame's
+    counters memset queued behind it could overtake a list kernel that is still running (round-1 verdict and advisor).
+    400 frames queued back to back without host synchronisation, cameras alternating so that consecutive frames differ,
+    every frame's counters copied to the host right behind its kernels: each copy must hold the complete totals of its
+    frame (known from synchronised runs of the two cameras)."""
+    sc = synth.config3(3000, 1000, state_sets=16)             # long lists only: the medium kernel has nothing to do
+    ds = DeviceScene(ctx, sc)
+    try:
+        cams = [synth.orbit_camera(30, 1500.0, far=3000.0), synth.orbit_camera(200, 1500.0, far=3000.0)]
+        ds.upload_drawable_list()
+        expect = []
+        for planes, eye in cams:
+            ds.process_and_cull(planes, eye)
+            ctx.sync(ds.stream)
+            c = ds.read_counters()
+            assert c["status"] == 0 and c["medium_count"] == 0 and c["inst_count"].sum() > 0
+            expect.append(ds._read(ds.counters, ds.counters_bytes, np.uint8).copy())
+        assert not np.array_equal(expect[0][64:], expect[1][64:])
+        frames = 400
+        host = ctx.host_alloc(frames * ds.counters_bytes)
+        try:
+            for f in range(frames):
+                planes, eye = cams[f & 1]
+                ds.process_and_cull(planes, eye)
+                ctx.memcpy_d2h(host + f * ds.counters_bytes, ds.counters, ds.counters_bytes, stream=ds.stream)
+            ctx.sync(ds.stream)
+            import ctypes
+            got = np.ctypeslib.as_array((ctypes.c_uint8 * (frames * ds.counters_bytes)).from_address(host)).reshape(frames, -1)
+            keep = np.r_[0:12, 16:20, 64:ds.counters_bytes]      # status, near-band count, queued items, queued medium lists, per-range totals
+            for f in range(frames):
+                assert np.array_equal(got[f][keep], expect[f & 1][keep]), f"frame {f}: counters were read before the frame's kernels had finished"
+        finally:
+            ctx.host_free(host)
+    finally:
+        ds.close()
