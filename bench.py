@@ -779,9 +779,9 @@ def other_workloads(args) -> dict:
     """Compact lines of BASELINE configs[0], [1], [3] and [4] (c1, c2, c4, c5): the same measurement as the main line, run
     by this script in a child process per workload."""
     out = {}
-    steps = str(max(20, min(args.steps, 100)))
+    steps = "100"                       # sub-millisecond frames: 100 steps cost nothing and are steadier than the driver's 20
     for w in ("c1", "c2", "c4", "c5"):
-        cmd = [sys.executable, os.path.abspath(__file__), "--workload", w, "--steps", steps, "--warmup", str(max(args.warmup, 3)),
+        cmd = [sys.executable, os.path.abspath(__file__), "--workload", w, "--steps", steps, "--warmup", str(max(args.warmup, 10)),
                "--no-cpu-baseline", "--no-workloads"]
         try:
             r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
