@@ -42,6 +42,8 @@ def test_struct_sizes_match_header():
     assert _capi.CullParams.drawableBounds.offset == 232 + 16 + 3 * 64
     assert ctypes.sizeof(_capi.CullParams) == 232 + 16 + 3 * 64 + 16
     assert ctypes.sizeof(_capi.ExchangeSync) == 32 + 2 * 64
+    assert _capi.CullParams.addressDelta.offset == 232 + 16 + 3 * 64 + 8          # the consumer-side pointer translation (ABI 6)
+    assert ctypes.sizeof(_capi.ExchangePull) == 16 + 3 * 8 + 8 + 2 * 64 and _capi.ExchangePull.regions.offset == 48
     assert cadr_b200.lib().cadr_b200_cull_counters_bytes(64) == 64 + 64 * 8
 
 
@@ -56,6 +58,10 @@ def test_address_space_only_context_refuses_compute(address_ctx):
                  lambda: c.upload([(a, 0, 16)], np.zeros(16, np.uint8)),
                  lambda: c.scatter_copy([(a, 0, 16)], b),
                  lambda: c.patch_handles(a, 1, [(1, 2)]),
+                 lambda: c.upload_stage([(a, 0, 16)], np.zeros(16, np.uint8)),
+                 lambda: c.upload_commit(0x181),
+                 lambda: c.exchange_pull_instances(_capi.ExchangePull()),
+                 lambda: c.ipc_export_range(a),
                  lambda: c.memcpy_h2d(a, np.zeros(16, np.uint8)),
                  lambda: c.sync()):
         with pytest.raises(cadr_b200.NoDevice):
