@@ -10,7 +10,12 @@
 //   c1   IndependentBoxesScene: side^3 boxes, a Geometry + one-matrix MatrixList + Drawable each      (Tests.cpp:456-618)
 //   c2   one shared box Geometry, N drawables with a one-matrix MatrixList each, one StateSet          (configs[1])
 //   c3   G geometries with 3 LOD PrimitiveSets x M-matrix MatrixLists over 64 StateSets                (configs[2])
-// usage: facade_bench <cuda device> <c1|c2|c3> [frames = 200] [size: side | drawables | geometries] [matrices per list]
+//   c4   c3, and every frame 10 % of the MatrixLists are re-written through MatrixList::editNewContent (configs[3]):
+//        realloc-on-write hands every rewritten list a NEW device range, the handle table follows (whole 16 KiB leaves are
+//        re-staged and re-allocated, parents repointed), executeCopyOperations moves ~640 MB of staged matrices per frame.
+//        The matrices written are the ones the lists already hold, so every frame must count exactly what the static
+//        scene counts under the same camera - checked every frame: addresses move, results may not.
+// usage: facade_bench <cuda device> <c1|c2|c3|c4> [frames = 200] [size: side | drawables | geometries] [matrices per list]
 // Prints ONE JSON line.
 #include <CadR/CadR.h>
 #include "../../../include/cadr_b200.h"
@@ -23,6 +28,7 @@
 #include <deque>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace CadR;
@@ -108,6 +114,8 @@ struct Scene {
 	std::vector<MatrixList> lists;
 	std::vector<Drawable> drawables;
 	uint64_t instances = 0;
+	std::vector<mat4> hostMatrices;      // c4: what every list holds, list after list
+	size_t perList = 0;
 	explicit Scene(Renderer& r_) : r(r_), root(r_) {}
 
 	Geometry& addBox(bool lods) {
@@ -168,12 +176,14 @@ int main(int argc, char** argv)
 			sc.instances = n;
 			desc = "configs[1] " + std::to_string(n) + " drawables x 1 matrix, one shared geometry, one StateSet, orbiting camera";
 		}
-		else if(which == "c3") {
+		else if(which == "c3" || which == "c4") {
 			const size_t G = argc > 4 ? size_t(atoll(argv[4])) : 100000;
 			const size_t M = argc > 5 ? size_t(atoll(argv[5])) : 1000;
 			const uint32_t S = 64;
 			for(uint32_t s = 0; s < S; s++) { sc.sets.emplace_back(r); sc.root.childList.append(sc.sets.back()); }
 			sc.lists.reserve(G); sc.drawables.reserve(G);
+			sc.perList = M;
+			if(which == "c4") sc.hostMatrices.resize(G * M);
 			const uint32_t lodOff[3] = {0, 8, 16};
 			const float lodThr[2] = {300.f, 900.f};
 			for(size_t k = 0; k < G; k++) {
@@ -188,6 +198,7 @@ int main(int argc, char** argv)
 					const float q[4] = {a * std::sin(t2), a * std::cos(t2), b * std::sin(t3), b * std::cos(t3)};
 					m[j] = trs(p, q, 0.5f + 1.5f * u01(30, gi));
 				}
+				if(which == "c4") std::memcpy(&sc.hostMatrices[k * M], m, M * sizeof(mat4));
 				sc.drawables.emplace_back(g, 0, sc.lists.back(), sc.sets[k % S]).setCullData(BoundingSphere{{0, 0, 0}, kBoxRadius}, 3, lodOff, lodThr);
 				if((k & 0x1ff) == 0x1ff) r.executeCopyOperations();       // 512 lists = 32 MiB of staged matrices per transfer
 			}
@@ -226,6 +237,69 @@ int main(int argc, char** argv)
 		r.waitIdle();
 		countersBytes = cadr_b200_cull_counters_bytes(r.cullResult().numRanges);
 		for(void*& p : pinned) if(cadr_b200_host_alloc(ctx, countersBytes, &p) != CADR_OK) throw std::runtime_error(cadr_b200_last_error());
+
+		if(which == "c4") {
+			// reference counters of the static scene under a fixed camera
+			auto readCounters = [&]() { std::vector<uint8_t> c(countersBytes); r.readDevice(c.data(), r.cullResult().counters, countersBytes); return c; };
+			frame(30, false); r.waitIdle();
+			const std::vector<uint8_t> expect = readCounters();
+			if(*reinterpret_cast<const uint32_t*>(expect.data())) throw std::runtime_error("culling pass reported a status");
+			const size_t G = sc.lists.size(), M = sc.perList, rewrite = G / 10;
+			std::vector<mat4*> dst(rewrite);
+			std::vector<size_t> src(rewrite);
+			const unsigned nThreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+			double fillMs = 0, copyMs = 0, gpuWaitMs = 0, totalMs = 0;
+			uint64_t uploaded = 0;
+			size_t level = 0;
+			for(int f = 0; f < frames; f++) {
+				const double t0 = now();
+				r.beginFrame();
+				for(size_t t = 0; t < rewrite; t++) {                    // SURVEY Appendix D cfg 4: lists {(f*10007 + t*7919) mod n}
+					const size_t k = (size_t(f) * 10007 + t * 7919) % G;
+					dst[t] = sc.lists[k].editNewContent(M);              // new device range, staging block handed out
+					src[t] = k;
+				}
+				{   // the application's writes into staging, on all cores (the allocator calls above are single-threaded like the reference)
+					std::vector<std::thread> pool;
+					for(unsigned w = 1; w < nThreads; w++)
+						pool.emplace_back([&, w]() { for(size_t t = w; t < rewrite; t += nThreads) std::memcpy(dst[t], &sc.hostMatrices[src[t] * M], M * sizeof(mat4)); });
+					for(size_t t = 0; t < rewrite; t += nThreads) std::memcpy(dst[t], &sc.hostMatrices[src[t] * M], M * sizeof(mat4));
+					for(auto& th : pool) th.join();
+				}
+				const double t1 = now();
+				r.executeCopyOperations();                                // uploads (blocks like the reference)
+				const double t2 = now();
+				r.beginRecording();
+				const size_t n = r.prepareSceneRendering(sc.root);
+				r.recordDrawableProcessing(n);
+				r.recordSceneRendering(sc.root);
+				r.recordDrawableCulling(orbitCamera(30, radius, farPlane));
+				r.endRecording();
+				r.executeCopyOperations();
+				r.submit();
+				r.endFrame();
+				r.waitIdle();
+				const double t3 = now();
+				const std::vector<uint8_t> got = readCounters();
+				// status, near-band count and the per-range totals (not the queue cursors)
+				if(std::memcmp(got.data(), expect.data(), 8) != 0 || std::memcmp(got.data() + 64, expect.data() + 64, countersBytes - 64) != 0)
+					throw std::runtime_error("frame " + std::to_string(f) + ": the culled result changed although only addresses moved");
+				fillMs += (t1 - t0) * 1e3; copyMs += (t2 - t1) * 1e3; gpuWaitMs += (t3 - t2) * 1e3; totalMs += (t3 - t0) * 1e3;
+				uploaded = uint64_t(rewrite) * (M + 1) * sizeof(mat4);
+				level = r.dataStorage().handleLevel();
+			}
+			size_t arenas = 0, arenaBytes = 0;
+			for(const DataMemory* m : r.dataStorage().dataMemoryList()) { arenas++; arenaBytes += m->size(); }
+			for(void* p : pinned) cadr_b200_host_free(ctx, p);
+			printf("{\"bench\": \"facade_bench\", \"scene\": \"c4\", \"workload\": \"configs[3] %s; every frame %zu of the %zu MatrixLists re-written through MatrixList::editNewContent (realloc-on-write, handle table follows)\", "
+			       "\"instances\": %llu, \"frames\": %d, \"results_identical_to_static_scene_every_frame\": true, "
+			       "\"ms_per_frame\": %.3f, \"M_instances_per_s\": %.1f, \"host_fill_ms\": %.3f, \"executeCopyOperations_ms\": %.3f, \"record_submit_wait_ms\": %.3f, "
+			       "\"staged_bytes_per_frame\": %llu, \"upload_GB_per_s\": %.1f, \"data_memories\": %zu, \"data_memory_bytes\": %zu, \"handle_level\": %zu, \"fill_threads\": %u}\n",
+			       desc.c_str(), rewrite, G, (unsigned long long)sc.instances, frames, totalMs / frames, double(sc.instances) / (totalMs / frames * 1e-3) / 1e6,
+			       fillMs / frames, copyMs / frames, gpuWaitMs / frames, (unsigned long long)uploaded, double(uploaded) / (copyMs / frames * 1e-3) / 1e9,
+			       arenas, arenaBytes, level, nThreads);
+			return 0;
+		}
 
 		// (1) device interval of the drawable processing + host time per frame, frame by frame (FrameInfo)
 		r.setCollectFrameInfo(true);
