@@ -36,6 +36,8 @@ class DataStorage {
 	StagingManager* _stagingManager = nullptr;
 	size_t _stagingDataSizeHint = 0;
 	uint64_t _uploadEpoch = 1;             // bumped by every recordUploads() that transferred something
+	bool _reuseEmptyMemories = true;
+	size_t _reuseScanStart = 0;
 	HandleTable _handleTable;
 	DataAllocationRecord* allocInternal(size_t numBytes);
 	std::tuple<StagingMemory&, bool> allocStagingMemory(DataMemory& m, StagingMemory* lastStagingMemory,
@@ -53,6 +55,13 @@ public:
 	StagingManager& stagingManager() const { return *_stagingManager; }
 	size_t stagingDataSizeHint() const { return _stagingDataSizeHint; }
 	uint64_t uploadEpoch() const { return _uploadEpoch; }
+	/// Beyond the reference (on by default): when the first and second DataMemory are full, an older DataMemory that has
+	/// become completely empty is taken into service again before a new one is created.  The reference only ever moves on
+	/// to a NEW DataMemory (DataStorage.cpp:72-85) and never returns to or releases an old one, so a scene that keeps
+	/// re-writing its allocations (realloc-on-write) grows by the re-written bytes every frame without bound.  Placement
+	/// inside a DataMemory is unaffected; off = the reference's policy.
+	void setReuseEmptyDataMemories(bool on) { _reuseEmptyMemories = on; }
+	bool reuseEmptyDataMemories() const { return _reuseEmptyMemories; }
 	/// Was this record staged in the current frame AND has nothing been transferred since (its staging block is still its own)?
 	bool stagedAndNotYetTransferred(const DataAllocationRecord* a) const;
 	void setStagingDataSizeHint(size_t size) { _stagingDataSizeHint = size; }

@@ -257,7 +257,21 @@ DataAllocationRecord* DataStorage::allocInternal(size_t numBytes)
 	if(!_secondAllocMemory)
 		_secondAllocMemory = create(numBytes < R::mediumMemorySize ? R::mediumMemorySize : std::max(numBytes, R::largeMemorySize));
 	if(DataAllocationRecord* a = _secondAllocMemory->alloc(numBytes)) return a;
-	DataMemory* m = create(std::max(R::largeMemorySize, numBytes));
+	// (extension, see DataStorage::setReuseEmptyDataMemories) an old DataMemory that has emptied out completely - no live
+	// allocation, no pending upload run - serves again before a new device buffer is created; the scan resumes where the
+	// last one ended, so that a long list of full memories is not walked from its start every time
+	DataMemory* m = nullptr;
+	if(_reuseEmptyMemories) {
+		const size_t count = _dataMemoryList.size();
+		for(size_t i = 0; i < count && !m; i++) {
+			DataMemory* c = _dataMemoryList[(_reuseScanStart + i) % count];
+			if(c != _firstAllocMemory && c != _secondAllocMemory && c->size() >= std::max(R::largeMemorySize, numBytes) && c->ringEmpty()) {
+				m = c;
+				_reuseScanStart = (_reuseScanStart + i + 1) % count;
+			}
+		}
+	}
+	if(!m) m = create(std::max(R::largeMemorySize, numBytes));
 	_firstAllocMemory = _secondAllocMemory;   // the first is full, the second nearly: rotate
 	_secondAllocMemory = m;
 	DataAllocationRecord* a = m->alloc(numBytes);

@@ -133,7 +133,51 @@ int main(int argc, char** argv)
 				if(deviceByte(objs[i].deviceAddress()) != int(i)) throw std::runtime_error("object data lost");
 			}
 		}
-		printf("ring_rewrite_test ok: %zu frames, %zu copy regions, largest %zu bytes\n", frames, regions, maxRegionBytes);
+		// ---- a scene that keeps re-writing big allocations: old DataMemory objects empty out and are taken into service again
+		// (DataStorage::setReuseEmptyDataMemories, on by default); with the reference's policy the same run only ever grows
+		size_t memoriesWithReuse = 0, memoriesReference = 0;
+		for(int reuse = 1; reuse >= 0; reuse--) {
+			Renderer r(device);
+			DataStorage& ds = r.dataStorage();
+			ds.setReuseEmptyDataMemories(reuse != 0);
+			std::map<uint64_t, std::vector<uint8_t>> mirror;
+			ds.uploadObserver = [&](const cadr_copy_region* regs, size_t n) {
+				for(size_t i = 0; i < n; i++)
+					for(const DataMemory* m : ds.dataMemoryList())
+						if(regs[i].dstAddr >= m->deviceAddress() && regs[i].dstAddr + regs[i].bytes <= m->deviceAddress() + m->size()) {
+							auto& img = mirror[m->deviceAddress()];
+							img.resize(m->size());
+							std::memcpy(img.data() + (regs[i].dstAddr - m->deviceAddress()), reinterpret_cast<const void*>(regs[i].srcOffset), regs[i].bytes);
+						}
+			};
+			const size_t count = 48, bytes = 3u << 20;               // 144 MiB live in 32 MiB memories, a quarter re-written per frame
+			std::vector<HandlelessAllocation> allocs;
+			for(size_t i = 0; i < count; i++) allocs.emplace_back(ds);
+			for(size_t frame = 0; frame < 24; frame++) {
+				r.beginFrame();
+				for(size_t i = 0; i < count; i++) {
+					if(frame != 0 && (i + frame) % 4 != 0) continue;
+					StagingData sd = allocs[i].alloc(bytes);
+					uint64_t* w = sd.data<uint64_t>();
+					w[0] = (uint64_t(frame) << 32) | i; w[bytes / 8 - 1] = ~w[0];
+				}
+				r.executeCopyOperations();
+				for(size_t i = 0; i < count; i++) {
+					const uint64_t addr = allocs[i].deviceAddress();
+					const uint8_t* p = nullptr;
+					for(auto& [base, img] : mirror) if(addr >= base && addr + bytes <= base + img.size()) p = img.data() + (addr - base);
+					if(!p) throw std::runtime_error("big allocation was never uploaded");
+					const uint64_t head = *reinterpret_cast<const uint64_t*>(p), tail = *reinterpret_cast<const uint64_t*>(p + bytes - 8);
+					if((head & 0xffffffffu) != i || tail != ~head) throw std::runtime_error("big allocation " + std::to_string(i) + " holds foreign data in frame " + std::to_string(frame));
+				}
+				r.endFrame();
+			}
+			(reuse ? memoriesWithReuse : memoriesReference) = ds.dataMemoryList().size();
+		}
+		if(memoriesWithReuse >= memoriesReference || memoriesWithReuse > 16)
+			throw std::runtime_error("empty DataMemory objects are not taken into service again: " + std::to_string(memoriesWithReuse) + " vs " + std::to_string(memoriesReference));
+		printf("ring_rewrite_test ok: %zu frames, %zu copy regions, largest %zu bytes; churn of 3 MiB allocations: %zu DataMemory objects with reuse, %zu with the reference's policy\n",
+		       frames, regions, maxRegionBytes, memoriesWithReuse, memoriesReference);
 		return 0;
 	}
 	catch(std::exception& e) {
