@@ -144,7 +144,7 @@ class PeerExchange:
     of a peer (it cannot pass the wait), so set k&1 is never overwritten while a peer still reads frame k-2... k."""
 
     def __init__(self, ctx, cmd_capacity: int, num_ranges: int, group=None, *, regions: np.ndarray | None = None,
-                 inst_out: int = 0, arena: int = 0, first_drawable: int = 0):
+                 inst_out: int = 0, arena: int = 0, first_drawable: int = 0, sets: int = 2, deferred_wait: bool = False):
         """regions / inst_out / arena (optional, all or none): this rank's region table [S,4] u32, its instance-index
         buffer and the arena that holds its geometry and matrix lists.  They are exported to the peers as well, which
         makes every rank's result CONSUMABLE on any GPU (consume_params): commands and counters are local copies, instance
@@ -152,7 +152,19 @@ class PeerExchange:
         pair of buffers: begin_frame then alternates them by frame parity like the gathered arrays, so that a peer may
         still read frame k's runs while this rank already culls frame k + 1 (it cannot get further ahead: it cannot pass
         the wait of frame k + 1 before every peer has published it).  first_drawable = position of this rank's first
-        drawable in the whole flattened list (the tag's drawable index is slice-relative)."""
+        drawable in the whole flattened list (the tag's drawable index is slice-relative).
+
+        deferred_wait (needs sets >= 4): end_frame(k) makes the stream wait for the peers' frame k-1 instead of frame k, and
+        does so BEFORE it publishes frame k.  A rank then never idles for the slowest rank of the frame it has just finished
+        (the max-over-ranks skew that is the exchange's only real cost): it starts frame k+1 at once and only needs the
+        peers to be less than a whole frame behind.  The price is one frame of latency: after end_frame(k) the gathered
+        result that is complete on this GPU is frame k-1's (`complete_frame`); finish() waits for the last one.  Why four
+        sets: a consumer of frame k-1 is queued behind end_frame(k), i.e. behind publish(k); peer A may write frame k+2 as
+        soon as it has seen everybody's publish(k) - while that consumer still runs - and frame k+3 only after everybody's
+        publish(k+1), which sits behind the consumer on this stream.  So frames k-1 .. k+2 must not share a set."""
+        if deferred_wait and sets < 4:
+            raise ValueError("PeerExchange: deferred_wait needs at least four sets of gathered arrays")
+        self.nsets, self.deferred = int(sets), bool(deferred_wait)
         import ctypes as C
         from . import _capi
         self.ctx, self.group = ctx, group
@@ -165,8 +177,8 @@ class PeerExchange:
         sizes = dict(cmd=self.world * self.cmd_cap * 20, ptr=self.world * self.cmd_cap * 32, tag=self.world * self.cmd_cap * 8,
                      counters=self.world * self.counters_bytes)
         self.sizes = sizes
-        # two sets (frame parity) of gathered arrays + one flag array
-        self.local = [{k: ctx.arena_alloc(max(v, 256)) for k, v in sizes.items()} for _ in range(2)]
+        # `sets` sets of gathered arrays (two: frame parity) + one flag array
+        self.local = [{k: ctx.arena_alloc(max(v, 256)) for k, v in sizes.items()} for _ in range(self.nsets)]
         self.flags = ctx.arena_alloc(256)
         ctx.memset(self.flags, 0, 256)
         for st in self.local:
@@ -233,38 +245,56 @@ class PeerExchange:
     def begin_frame(self, params) -> None:
         """Point the cull at this frame's gathered arrays (modifies `params` in place)."""
         self.frame += 1
-        k = self.frame & 1
+        k = self.frame % self.nsets
         params.exchangeWorld, params.exchangeRank, params.exchangeCmdCapacity = self.world, self.rank, self.cmd_cap
         for r in range(self.world):
             s = self.peer[r]["sets"][k]
             params.exchangeCmd[r], params.exchangePtr[r], params.exchangeTag[r] = s["cmd"], s["ptr"], s["tag"]
-        if self.consumable and len(self.inst_sets) == 2:
-            params.instOut = self.inst_sets[k]
+        if self.consumable and len(self.inst_sets) > 1:
+            params.instOut = self.inst_sets[self.frame % len(self.inst_sets)]
 
     def inst_of(self, r: int) -> int:
         """Rank r's instance-index buffer of the current frame as mapped on this GPU."""
         bufs = self.peer_inst[r]
-        return bufs[self.frame & 1] if len(bufs) == 2 else bufs[0]
+        return bufs[self.frame % len(bufs)]
 
-    def _sync(self, local_counters: int):
+    def _sync(self, local_counters: int, frame: int | None = None):
+        frame = self.frame if frame is None else frame
         s = self._capi.ExchangeSync()
-        s.world, s.rank, s.frameSeq = self.world, self.rank, self.frame
+        s.world, s.rank, s.frameSeq = self.world, self.rank, frame
         s.localCounters, s.countersBytes = local_counters, self.counters_bytes
-        k = self.frame & 1
+        k = frame % self.nsets
         for r in range(self.world):
             s.peerCounters[r] = self.peer[r]["sets"][k]["counters"]
             s.peerFlags[r] = self.peer[r]["flags"]
         return s
 
     def end_frame(self, local_counters: int, stream: int = 0) -> None:
-        """After the cull kernels of the frame: publish counters + flag to every peer, then wait for all peers."""
+        """After the cull kernels of the frame: publish counters + flag to every peer and wait for all peers - for this
+        frame, or with deferred_wait for the previous one and before the publish (see __init__)."""
         s = self._sync(local_counters)
+        if not self.deferred:
+            self.ctx.exchange_publish(s, stream)
+            self.ctx.exchange_wait(s, stream)
+            return
+        if self.frame > 1:
+            self.ctx.exchange_wait(self._sync(local_counters, self.frame - 1), stream)
         self.ctx.exchange_publish(s, stream)
-        self.ctx.exchange_wait(s, stream)
+        self._last_counters = local_counters
 
-    def read(self) -> dict:
-        """Host view of the current frame's gathered arrays (after a sync)."""
-        k = self.frame & 1
+    @property
+    def complete_frame(self) -> int:
+        """The newest frame whose gathered result is complete on this GPU once the stream has passed end_frame()."""
+        return self.frame - 1 if self.deferred else self.frame
+
+    def finish(self, stream: int = 0) -> None:
+        """deferred_wait: wait for the peers' last frame too (end of a run, or before reading the newest result)."""
+        if self.deferred and self.frame >= 1:
+            self.ctx.exchange_wait(self._sync(self._last_counters), stream)
+
+    def read(self, frame: int | None = None) -> dict:
+        """Host view of the gathered arrays of the current frame (or of `frame`, while its set has not been reused), after a sync."""
+        k = (self.frame if frame is None else frame) % self.nsets
         out = {}
         for name, dt in (("cmd", np.uint32), ("ptr", np.uint64), ("tag", np.uint32), ("counters", np.uint8)):
             buf = np.empty(self.sizes[name], np.uint8)
@@ -286,7 +316,7 @@ class PeerExchange:
         if not self.consumable:
             raise RuntimeError("PeerExchange was created without regions / inst_out / arena")
         p = self._capi.CullParams()
-        st = self.local[self.frame & 1]
+        st = self.local[self.frame % self.nsets]
         slot = r * self.cmd_cap
         p.numStateSets = self.num_ranges
         p.cmdOut, p.ptrOut, p.tagOut = st["cmd"] + 20 * slot, st["ptr"] + 32 * slot, st["tag"] + 8 * slot
@@ -324,19 +354,19 @@ class PeerExchange:
         (cadr_b200_exchange_pull_instances).  Rank r's commands then index gathered_inst + r * inst_cap * 4."""
         p = self._capi.ExchangePull()
         p.world, p.rank, p.numRanges, p.countersBytes = self.world, self.rank, self.num_ranges, self.counters_bytes
-        p.gatheredCounters = self.local[self.frame & 1]["counters"]
+        p.gatheredCounters = self.local[self.frame % self.nsets]["counters"]
         p.gatheredInst, p.instCapacity, p.includeLocal = self.gathered_inst, self.inst_cap, int(include_local)
         for r in range(self.world):
             p.regions[r], p.peerInst[r] = self.regions_dev[r], self.inst_of(r)
         self.ctx.exchange_pull_instances(p, stream)
 
     # -- cross-check of the fused exchange over NCCL -------------------------------------------------------------------
-    def verify(self, device) -> dict:
+    def verify(self, device, regions: list | None = None) -> dict:
         """What the peer stores of the cull kernels left in THIS rank's gathered arrays against what every rank holds
         for itself: each rank sends its own slot (commands, pointers, tags of every range in use, its counters) through
         an NCCL all-gather, and the received copies must equal, byte for byte, the slots the fused exchange filled here.
         -> dict(ok, commands, bytes, problems); identical on all ranks only if every rank's view is right, so callers
-        all-reduce `ok`."""
+        all-reduce `ok`.  `regions`: every rank's region table [S,4], for an exchange created without them."""
         g = self.read()
         cap, cb = self.cmd_cap, self.counters_bytes
         me = slice(self.rank * cap, (self.rank + 1) * cap)
@@ -357,7 +387,7 @@ class PeerExchange:
                 problems.append(f"counters of rank {r} differ from what it holds itself")
                 continue
             counts = ctr[64:].view(np.uint64)
-            reg = self.peer_regions[r] if self.consumable else None
+            reg = self.peer_regions[r] if self.consumable else (regions[r] if regions is not None else None)
             for s_ in range(len(counts)):
                 c = int(counts[s_] & np.uint64(0xFFFFFFFF))
                 if c == 0:
@@ -386,7 +416,7 @@ class PeerExchange:
             for r in range(self.world):
                 c = int(g["counts"][r][s] & np.uint64(0xFFFFFFFF))
                 if c:
-                    reg = self.peer_regions[r] if self.consumable else None
+                    reg = self.peer_regions[r] if self.consumable else (regions[r] if regions is not None else None)
                     out.append(dict(state_set=s, rank=r, count=c, instances=int(g["counts"][r][s] >> np.uint64(32)),
                                     first_command=r * self.cmd_cap + (int(reg[s, 0]) if reg is not None else 0)))
         return out

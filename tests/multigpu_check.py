@@ -15,6 +15,9 @@
                              * the optional second stage (instance-index runs pulled to the renderer GPU) delivers the
                                owners' runs, and the consumer walk over the pulled copies gives the same digests;
                              * a renderer issues at most S + world - 1 indirect-count draws (directory()).
+  D  deferred wait         PeerExchange(sets=4, deferred_wait=True): a rank waits for the peers' PREVIOUS frame before it
+                           publishes its own, frames queued back to back with a different camera each; after every
+                           end_frame the gathered result of frame k-1 - and after finish() the last frame's - equals the oracle.
   C  Tier R gather (NCCL)  the fixed-size records of the processing pass, every rank's slice broadcast into whole-list
                            arrays (shard.TierRGather): equal to the oracle's records of the slices, in list order.
 """
@@ -207,6 +210,41 @@ def part_b_and_c(ctx, rank, world, local):
     return len(directory)
 
 
+def part_d(ctx, rank, world, local):
+    scenes = [synth.random_scene(1300 + r, n=400 + 29 * r, num_lists=70, max_count=60, state_sets=3 + r % 3, big_lists=1) for r in range(world)]
+    sc = scenes[rank]
+    ds = DeviceScene(ctx, sc)
+    bases = [None] * world
+    dist.all_gather_object(bases, (ds.arena, ds.drawable_list))
+    px = shard.PeerExchange(ctx, ds.cmd_cap, sc.num_state_sets, sets=4, deferred_wait=True)
+    cams = [synth.orbit_camera(37 * f, 250.0, far=500.0) for f in range(9)]
+
+    def check(frame_no):          # frame numbers start at 1
+        planes, eye = cams[frame_no - 1]
+        g = px.read(frame=frame_no)
+        refs = [oracle_tier_x(scenes[r], planes, eye, arena_base=bases[r][0], list_base=bases[r][1])[2] for r in range(world)]
+        check_gathered_commands(rank, g, px, scenes, refs, f"D{frame_no}")
+
+    ds.upload_drawable_list()
+    for f, (planes, eye) in enumerate(cams, start=1):
+        p = ds.cull_params(planes, eye)
+        px.begin_frame(p)
+        ctx.process_and_cull(p, stream=ds.stream)
+        px.end_frame(ds.counters, stream=ds.stream)
+        if f % 3 == 0:            # every third frame: look at what is complete now (frame f-1); otherwise keep queueing
+            ctx.sync(ds.stream)
+            if px.complete_frame != f - 1:
+                fail("D: complete_frame")
+            check(f - 1)
+    px.finish(ds.stream)
+    ctx.sync(ds.stream)
+    check(len(cams))
+    dist.barrier()
+    px.close()
+    ds.close()
+    return len(cams)
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -214,6 +252,7 @@ def main():
     ctx = cadr_b200.Context(local)
     frames = part_a(ctx, rank, world, local)
     draws = part_b_and_c(ctx, rank, world, local)
+    deferred_frames = part_d(ctx, rank, world, local)
     t = torch.tensor([0 if problems else 1], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     ctx.close()
@@ -223,7 +262,7 @@ def main():
         print("multigpu_check", "ok" if ok else "FAILED",
               f"({world} ranks; A: {frames} frames of independent scenes{', queued without host sync' if os.environ.get('MG_ASYNC') == '1' else ''}; "
               f"B: one scene partitioned, merged == whole-scene oracle, consumer walk through peer mappings == oracle, NCCL cross-check, "
-              f"pulled instance runs, {draws} draws; C: Tier R gather over NCCL)")
+              f"pulled instance runs, {draws} draws; C: Tier R gather over NCCL; D: {deferred_frames} frames with the deferred wait)")
     sys.exit(0 if ok else 1)
 
 
