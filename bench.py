@@ -66,6 +66,9 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="drawables in the CPU sample (0: auto)")
     ap.add_argument("--independent-scenes", action="store_true",
                     help="multi-GPU: every rank builds a scene of its own (round-1 behaviour) instead of culling its slice of ONE scene")
+    ap.add_argument("--deferred-wait", action="store_true",
+                    help="multi-GPU: also time the exchange with the wait deferred by one frame (PeerExchange(sets=4, deferred_wait=True)); "
+                         "measured at 2 and 8 GPUs: no gain, the exchange tail is launch + system-fence overhead, not skew (DESIGN.md 4)")
     ap.add_argument("--no-verify", action="store_true", help="multi-GPU: skip the cross-checks of the exchange after the timed loops")
     ap.add_argument("--no-workloads", action="store_true",
                     help="single GPU, default workload: do not append the compact lines of the other BASELINE configs (c1, c2, c4, c5)")
@@ -496,7 +499,7 @@ def run_b200(args):
         # the same exchange with the wait deferred by one frame (PeerExchange(sets=4, deferred_wait=True)): a rank never idles
         # for the slowest rank of the frame it has just finished; the gathered result lags one frame behind
         ms_deferred = None
-        if px is not None:
+        if px is not None and args.deferred_wait:
             pxd = PeerExchange(ctx, ds.cmd_cap, scene.num_state_sets, sets=4, deferred_wait=True)
 
             def run_deferred(k):

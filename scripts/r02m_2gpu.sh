@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, 2-GPU session with the final code: the bench line at N=2 as the driver runs it, the other workloads at N=2
 # (c2 / c1 run one scene per rank: their shapes are not partitioned), multigpu_check queued without host sync.
-tag=r02m
+tag=${1:-r02m}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port"
 show() { python - "$1" "$2" <<'PY'
