@@ -152,6 +152,7 @@ SYMBOLS = {
     "cadr_b200_external_free": (C.c_int, [_P, C.c_uint64]),
     "cadr_b200_exchange_publish": (C.c_int, [_P, C.POINTER(ExchangeSync), _P]),
     "cadr_b200_exchange_wait": (C.c_int, [_P, C.POINTER(ExchangeSync), _P]),
+    "cadr_b200_exchange_publish_and_wait": (C.c_int, [_P, C.POINTER(ExchangeSync), _P]),
     "cadr_b200_consume_check": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
     "cadr_b200_consume_check_culled": (C.c_int, [_P, C.POINTER(CullParams), C.c_uint32, C.c_uint32, C.c_uint64, _P]),
     "cadr_b200_cull_counters_bytes": (C.c_size_t, [C.c_uint32]),
@@ -368,6 +369,9 @@ class Context:
 
     def exchange_publish(self, sync: "ExchangeSync", stream: int = 0) -> None:
         check(self._l.cadr_b200_exchange_publish(self._h, C.byref(sync), _P(stream)))
+
+    def exchange_publish_and_wait(self, sync: "ExchangeSync", stream: int = 0) -> None:
+        check(self._l.cadr_b200_exchange_publish_and_wait(self._h, C.byref(sync), _P(stream)))
 
     def exchange_wait(self, sync: "ExchangeSync", stream: int = 0) -> None:
         check(self._l.cadr_b200_exchange_wait(self._h, C.byref(sync), _P(stream)))

@@ -26,6 +26,30 @@ __global__ void publishKernel(const __grid_constant__ cadr_exchange_sync S)
 	}
 }
 
+// publish + wait in ONE launch (one kernel boundary less at the end of every frame): the CTA publishes, then its first
+// `world` threads spin on the local flag array.  Only for ranks that run concurrently (one process per GPU): a peer that
+// has not started its frame yet is simply waited for.
+__global__ void publishAndWaitKernel(const __grid_constant__ cadr_exchange_sync S)
+{
+	const uint32_t words = S.countersBytes / 4;
+	const uint32_t* src = reinterpret_cast<const uint32_t*>(S.localCounters);
+	for(uint32_t r = 0; r < S.world; r++) {
+		uint32_t* dst = reinterpret_cast<uint32_t*>(S.peerCounters[r] + uint64_t(S.rank) * S.countersBytes);
+		for(uint32_t i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+	}
+	__threadfence_system();
+	__syncthreads();
+	if(threadIdx.x < S.world) {
+		unsigned long long* flag = reinterpret_cast<unsigned long long*>(S.peerFlags[threadIdx.x]) + S.rank;
+		asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(flag), "l"((unsigned long long)S.frameSeq) : "memory");
+		const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(S.peerFlags[S.rank]) + threadIdx.x;
+		unsigned long long v;
+		do {
+			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+		} while(v < S.frameSeq);
+	}
+}
+
 __global__ void waitPeersKernel(const unsigned long long* flags, uint32_t world, unsigned long long frameSeq)
 {
 	if(threadIdx.x < world) {
@@ -162,6 +186,22 @@ int cadr_b200_exchange_publish(cadr_ctx* ctx, const cadr_exchange_sync* sync, ca
 			return setError(CADR_E_LOGIC, "exchange_publish: buffers of rank %u missing", r);
 	cudaStream_t s = ctx->pick(stream);
 	publishKernel<<<1, 256, 0, s>>>(*sync);
+	ctx->launches++;
+	CADR_CUDA(cudaGetLastError());
+	return CADR_OK;
+}
+
+int cadr_b200_exchange_publish_and_wait(cadr_ctx* ctx, const cadr_exchange_sync* sync, cadr_stream stream)
+{
+	REQUIRE_DEVICE_X(ctx);
+	if(int r = checkSync(sync, "exchange_publish_and_wait")) return r;
+	if(!sync->localCounters || (sync->countersBytes & 3))
+		return setError(CADR_E_LOGIC, "exchange_publish_and_wait: counters missing or not a multiple of 4 bytes");
+	for(uint32_t r = 0; r < sync->world; r++)
+		if(!sync->peerCounters[r] || !sync->peerFlags[r])
+			return setError(CADR_E_LOGIC, "exchange_publish_and_wait: buffers of rank %u missing", r);
+	cudaStream_t s = ctx->pick(stream);
+	publishAndWaitKernel<<<1, 256, 0, s>>>(*sync);
 	ctx->launches++;
 	CADR_CUDA(cudaGetLastError());
 	return CADR_OK;

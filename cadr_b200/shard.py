@@ -165,6 +165,7 @@ class PeerExchange:
         if deferred_wait and sets < 4:
             raise ValueError("PeerExchange: deferred_wait needs at least four sets of gathered arrays")
         self.nsets, self.deferred = int(sets), bool(deferred_wait)
+        self.fused_sync = True             # publish + wait as one kernel (False: two launches, as in round 1)
         import ctypes as C
         from . import _capi
         self.ctx, self.group = ctx, group
@@ -274,8 +275,11 @@ class PeerExchange:
         frame, or with deferred_wait for the previous one and before the publish (see __init__)."""
         s = self._sync(local_counters)
         if not self.deferred:
-            self.ctx.exchange_publish(s, stream)
-            self.ctx.exchange_wait(s, stream)
+            if self.fused_sync:
+                self.ctx.exchange_publish_and_wait(s, stream)      # one launch: publish, then spin on the local flags
+            else:
+                self.ctx.exchange_publish(s, stream)
+                self.ctx.exchange_wait(s, stream)
             return
         if self.frame > 1:
             self.ctx.exchange_wait(self._sync(local_counters, self.frame - 1), stream)

@@ -361,6 +361,9 @@ CADR_API int  cadr_b200_ipc_close(cadr_ctx* ctx, uint64_t devAddr);
 /* Copy this rank's counters into slot `rank` of every peer's gathered counters, then raise flag[rank] = frameSeq
  * on every peer (release at system scope). */
 CADR_API int  cadr_b200_exchange_publish(cadr_ctx* ctx, const cadr_exchange_sync* sync, cadr_stream stream);
+/* Both in one launch (one kernel boundary less per frame).  Only where all ranks run concurrently: the kernel spins until
+ * every peer has published frameSeq. */
+CADR_API int  cadr_b200_exchange_publish_and_wait(cadr_ctx* ctx, const cadr_exchange_sync* sync, cadr_stream stream);
 /* Block the stream (not the host) until every peer's flag in the LOCAL flag array has reached frameSeq. */
 CADR_API int  cadr_b200_exchange_wait(cadr_ctx* ctx, const cadr_exchange_sync* sync, cadr_stream stream);
 
