@@ -69,6 +69,9 @@ def parse_args():
     ap.add_argument("--deferred-wait", action="store_true",
                     help="multi-GPU: also time the exchange with the wait deferred by one frame (PeerExchange(sets=4, deferred_wait=True)); "
                          "measured at 2 and 8 GPUs: no gain, the exchange tail is launch + system-fence overhead, not skew (DESIGN.md 4)")
+    ap.add_argument("--split-sync", action="store_true",
+                    help="multi-GPU: also time the exchange with publish and wait as two launches (round 1's form; the default is one "
+                         "launch, cadr_b200_exchange_publish_and_wait)")
     ap.add_argument("--no-verify", action="store_true", help="multi-GPU: skip the cross-checks of the exchange after the timed loops")
     ap.add_argument("--no-workloads", action="store_true",
                     help="single GPU, default workload: do not append the compact lines of the other BASELINE configs (c1, c2, c4, c5)")
@@ -409,6 +412,24 @@ def run_b200(args):
     frame_done = [torch.cuda.Event(), torch.cuda.Event()]
     counters_host = [torch.empty(ds.counters_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
     consumed = [0]
+    # The counters go back to the host on their OWN stream, from one of two device-side counter blocks used in turn: a DMA
+    # queued on the compute stream between two frames costs a drain + copy-engine round trip per frame (~20 us of a 1 ms
+    # frame); this way frame k + 1 starts right behind frame k while the 576 bytes of frame k cross PCIe.
+    d2h_t = torch.cuda.Stream(device=dev)
+    counters_blocks = [ds.counters, arena.alloc(ds.counters_bytes)]
+    counters_block_t = [arena.tensor(a) for a in counters_blocks]
+    cull_done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def read_back(k):
+        cull_done[k % 2].record(stream_t)
+        d2h_t.wait_event(cull_done[k % 2])
+        with torch.cuda.stream(d2h_t):
+            counters_host[k % 2].copy_(counters_block_t[k % 2], non_blocking=True)
+        frame_done[k % 2].record(d2h_t)         # "frame k is done" = its counters are on the host
+
+    def read_backs_done():                      # end of a timed loop: the last read-backs belong to the timed region
+        for ev in frame_done:
+            stream_t.wait_event(ev)
 
     def upload_list(k):
         copy_t.wait_event(frame_done[k % 2])      # frame k-2 was the last reader of this buffer
@@ -439,9 +460,9 @@ def run_b200(args):
         ds.drawable_list = lists[k % 2]
         if rewrite is not None:        # Renderer::executeCopyOperations: pinned host staging -> device ranges (PCIe)
             commit_rewrite(k)
+        ds.counters = counters_blocks[k % 2]     # frame k - 2, its last user, was consumed by the host before frame k - 1 was queued
         run_cull(k, True)
-        counters_host[k % 2].copy_(counters_dev, non_blocking=True)
-        frame_done[k % 2].record(stream_t)
+        read_back(k)
         upload_list(k + 1)
         if rewrite is not None:
             stage_rewrite(k + 1)
@@ -456,7 +477,7 @@ def run_b200(args):
 
     sampler = ClockSampler(local) if rank == 0 else None     # started early: nvidia-smi needs ~0.1 s to deliver its first sample
 
-    def timed(fn, steps):
+    def timed(fn, steps, tail=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t_begin = time.monotonic()
@@ -464,6 +485,8 @@ def run_b200(args):
         e0.record(stream_t)
         for k in range(steps):
             fn(args.warmup + k)
+        if tail is not None:
+            tail()
         e1.record(stream_t)
         barrier()
         torch.cuda.nvtx.range_pop()
@@ -495,6 +518,18 @@ def run_b200(args):
         launches = ctx.launch_count - l0
 
         ms_cull_only = timed(lambda k: step_device(k, with_exchange=False), args.steps) if world > 1 else ms_total
+
+        # the same exchange with publish and wait as two kernel launches (round 1's form), interleaved with the default in one run
+        ms_split = ms_again = None
+        if px is not None and args.split_sync:
+            px.fused_sync = False
+            for k in range(3):
+                step_device(k)
+            ms_split = timed(step_device, args.steps)
+            px.fused_sync = True
+            for k in range(3):
+                step_device(k)
+            ms_again = timed(step_device, args.steps)                    # the default again, after the split form: same box state
 
         # the same exchange with the wait deferred by one frame (PeerExchange(sets=4, deferred_wait=True)): a rank never idles
         # for the slowest rank of the frame it has just finished; the gathered result lags one frame behind
@@ -533,7 +568,7 @@ def run_b200(args):
         copy_t.synchronize()
         flush_staged()
         upload_list(args.warmup)       # timed() numbers its steps from args.warmup
-        ms_e2e = timed(step_e2e, e2e_steps)
+        ms_e2e = timed(step_e2e, e2e_steps, tail=read_backs_done)
         copy_t.synchronize()
         flush_staged()
         ds.drawable_list = lists[0]    # lists[0] is the buffer DeviceScene owns (and the one the kernel profile below reads)
@@ -543,15 +578,16 @@ def run_b200(args):
         def step_resident(k):
             if rewrite is not None:
                 commit_rewrite(k)
+            ds.counters = counters_blocks[k % 2]
             run_cull(k, True)
-            counters_host[k % 2].copy_(counters_dev, non_blocking=True)
-            frame_done[k % 2].record(stream_t)
+            read_back(k)
             if rewrite is not None:
                 stage_rewrite(k + 1)
             frame_done[(k + 1) % 2].synchronize()
-        ms_resident = timed(step_resident, e2e_steps)
+        ms_resident = timed(step_resident, e2e_steps, tail=read_backs_done)
         copy_t.synchronize()
         flush_staged()
+        ds.counters = counters_blocks[0]
 
         # the single-call form for comparison (what round 1 timed): PCIe and GPU phases serial on one stream
         ms_e2e_serial = None
@@ -709,7 +745,10 @@ def run_b200(args):
         "survivor_fraction": round(p, 4),
         "e2e": {"value": round(e2e_value / 1e6, 1), "unit": "M instances/s",
                 "h2d_bytes_per_step": scene.n * 48 + 232 + (rewrite["bytes"] + rewrite["lists"] * 24 if rewrite else 0),
-                "d2h_bytes_per_step": ds.counters_bytes, "ms_per_step": round(ms_e2e / e2e_steps, 4), "steps": e2e_steps},
+                "d2h_bytes_per_step": ds.counters_bytes, "ms_per_step": round(ms_e2e / e2e_steps, 4), "steps": e2e_steps,
+                "how": "every frame: the pinned host drawable list is DMA'd to the device on a copy stream (frame k + 1's while frame k is "
+                       "culled), cadr_b200_process_and_cull, the counters DMA'd to pinned host memory on a read-back stream (two counter "
+                       "blocks in turn) and consumed by the host one frame later; the last read-backs are inside the timed region"},
         "e2e_resident_list": {"value": round(total_inst * e2e_steps / (ms_resident * 1e-3) / 1e6, 1), "unit": "M instances/s",
                               "ms_per_step": round(ms_resident / e2e_steps, 4),
                               "note": "same loop with the drawable list kept on the device (incremental list upload of the facade; static scene: "
@@ -768,6 +807,12 @@ def run_b200(args):
                                           "what": "value's frame + cadr_b200_exchange_pull_instances on rank 0: 4 B x survivors of the other "
                                                   "ranks cross NVLink into one renderer-visible index buffer (on a second stream, next to the "
                                                   "following frame's cull; this rank publishes that frame only when the pull is over); matrices stay sharded"}
+        if ms_split is not None:
+            line["with_split_sync"] = {"value": round(total_inst * args.steps / (ms_split * 1e-3) / 1e6, 1), "unit": "M instances/s",
+                                       "ms_per_step": round(ms_split / args.steps, 4),
+                                       "default_measured_again_ms_per_step": round(ms_again / args.steps, 4),
+                                       "what": "value's frame with cadr_b200_exchange_publish and cadr_b200_exchange_wait as two launches "
+                                               "(`value` closes the frame with ONE launch, cadr_b200_exchange_publish_and_wait)"}
         if ms_deferred is not None:
             line["with_deferred_wait"] = {"value": round(total_inst * args.steps / (ms_deferred * 1e-3) / 1e6, 1), "unit": "M instances/s",
                                           "ms_per_step": round(ms_deferred / args.steps, 4), "last_frame_cross_checked_over_nccl": bool(deferred_ok),
