@@ -51,6 +51,8 @@ def build_cuda(force: bool = False, verbose: bool = False, experiments: bool = F
     out = os.path.join(LIBDIR, "libcadr_b200_exp.so" if experiments else "libcadr_b200.so")
     srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES + (EXPERIMENT_SOURCES if experiments else [])]
     deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "cull_common.cuh"), os.path.join(ROOT, "include", "cadr_b200.h")]
+    if experiments:
+        deps += [os.path.join(CSRC, "experiments", h) for h in ("small_staged.cuh", "list_kernels.cuh")]
     if force or _stale(out, deps):
         flags = NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DCADR_B200_EXPERIMENTS"] if experiments else [])
         log = _run([nvcc()] + flags + ["-o", out] + srcs)

@@ -152,3 +152,39 @@ def test_pull_rejects_bad_arguments(ctx):
     pull.rank = 0
     with pytest.raises(cadr_b200.LogicError):
         ctx.exchange_pull_instances(pull)          # buffers missing
+
+
+def test_publish_and_wait_as_one_launch(ctx):
+    """cadr_b200_exchange_publish_and_wait (the one-launch frame close PeerExchange uses with one process per GPU): with a
+    world of one the kernel publishes to its own gathered slot and its wait passes on its own flag, so a one-GPU box can
+    check the launch, the copy and the flag without a second process.  (With more ranks the kernel spins until every peer
+    has published - exercised over real peer mappings by tests/multigpu_check.py and bench.py --gpus N.)"""
+    sc = synth.random_scene(77, n=300, num_lists=40, max_count=70, state_sets=3, big_lists=1)
+    ds = DeviceScene(ctx, sc)
+    cb = ctx.cull_counters_bytes(sc.num_state_sets)
+    gathered, flags = ctx.arena_alloc(max(cb, 256)), ctx.arena_alloc(256)
+    try:
+        ctx.memset(flags, 0, 256); ctx.memset(gathered, 0xEE, cb); ctx.sync()
+        ds.upload_drawable_list()
+        for seq in (1, 2):
+            planes, eye = synth.orbit_camera(40 * seq, 250.0, far=500.0)
+            ds.process_and_cull(planes, eye)
+            s = _capi.ExchangeSync()
+            s.world, s.rank, s.frameSeq, s.localCounters, s.countersBytes = 1, 0, seq, ds.counters, cb
+            s.peerCounters[0], s.peerFlags[0] = gathered, flags
+            ctx.exchange_publish_and_wait(s, ds.stream)
+            ctx.sync(ds.stream)
+            local, got, flag = np.empty(cb, np.uint8), np.empty(cb, np.uint8), np.zeros(1, np.uint64)
+            ctx.memcpy_d2h(local, ds.counters); ctx.memcpy_d2h(got, gathered); ctx.memcpy_d2h(flag, flags); ctx.sync()
+            assert np.array_equal(local, got) and int(flag[0]) == seq
+            _, _, ref = oracle_tier_x(sc, planes, eye, arena_base=ds.arena, list_base=ds.drawable_list)
+            assert np.array_equal((got[64:].view(np.uint64) >> np.uint64(32)).astype(np.int64), ref["inst_count"])
+        bad = _capi.ExchangeSync()
+        bad.world, bad.rank, bad.frameSeq, bad.localCounters, bad.countersBytes = 1, 0, 3, 0, cb
+        bad.peerCounters[0], bad.peerFlags[0] = gathered, flags
+        with pytest.raises(cadr_b200.LogicError):
+            ctx.exchange_publish_and_wait(bad, ds.stream)
+    finally:
+        ctx.sync()
+        ds.close()
+        ctx.arena_free(gathered); ctx.arena_free(flags)
