@@ -666,8 +666,8 @@ constexpr int LW_DESCS = 4;     // descriptor ring per warp: items A, B, C and t
 
 // FLAT (CADR_B200_CULL_VARIANT=5): after the queue of long items has run dry, the warp goes on with the medium items
 // itself instead of leaving them to cullMediumKernel.
-template<bool FLAT>
-__global__ void __launch_bounds__(CM_THREADS, 4)
+template<bool FLAT, int CTAS_PER_SM = 4>        // CTAS_PER_SM: 4 in the product (64 registers); 5 / 6 are A/B variants (48 / 40 registers)
+__global__ void __launch_bounds__(CM_THREADS, CTAS_PER_SM)
 cullListWarpKernel(const __grid_constant__ CullArgs A)
 {
 	// per warp: the descriptor ring of the long items (LW_DESCS x 128 B) and, afterwards, the 32 descriptors of a batch of
@@ -852,7 +852,7 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 	// cullListWarpKernel instead of cullMediumKernel); 4 = every list longer than 32 matrices in the one queue (the
 	// state before the medium path existed), for A/B measurements
 	const int variant = cullVariant();
-	A.medMax = ((variant == 2 || variant == 5 || variant == 6 || variant == 7 || variant == 8) && p.chunkCapacity) ? CADR_CULL_MEDIUM_LIST_MAX : 0u;
+	A.medMax = ((variant == 2 || (variant >= 5 && variant <= 10)) && p.chunkCapacity) ? CADR_CULL_MEDIUM_LIST_MAX : 0u;
 
 	uint32_t gridS = (p.numDrawables + CS_THREADS - 1) / CS_THREADS;
 	ctx->timeBegin(KS_CULL_SMALL, s);

@@ -614,6 +614,14 @@ static int launchListExperiment(cadr_ctx* ctx, const CullArgs& A, int variant, c
 		CADR_CUDA(cudaLaunchKernel(fn, dim3(gridL), dim3(CM_THREADS), args, smem, s));
 		return A.medMax ? launchMediumBehind(ctx, A, gridL, s) : CADR_OK;
 	}
+	if(variant == 9 || variant == 10) {             // the product kernel at 5 / 6 CTAs per SM (40 / 48 warps, 48 / 40 registers)
+		const uint32_t ctas = variant == 9 ? 5u : 6u;
+		uint32_t g = uint32_t(ctx->smCount) * ctas;
+		if(g > need) g = need;
+		if(variant == 9) cullListWarpKernel<false, 5><<<g, CM_THREADS, 0, s>>>(A);
+		else             cullListWarpKernel<false, 6><<<g, CM_THREADS, 0, s>>>(A);
+		return A.medMax ? launchMediumBehind(ctx, A, gridL, s) : CADR_OK;
+	}
 	if(variant == 6) {
 		CADR_CUDA(cudaFuncSetAttribute(cullListRingPairKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L2_SMEM_BYTES)));
 		uint32_t grid2 = uint32_t(ctx->smCount) * 2u;
