@@ -22,6 +22,8 @@ E_OVERFLOW = -6
 
 CULL_STATUS_REGION_OVERFLOW = 1
 CULL_STATUS_CHUNK_OVERFLOW = 2
+CULL_STATUS_BAD_RANGE_INDEX = 4
+CULL_STATUS_EXCHANGE_TIMEOUT = 8
 CULL_HEADER_BYTES = 64
 
 
@@ -106,7 +108,7 @@ class ExchangeSync(C.Structure):
         ("world", C.c_uint32), ("rank", C.c_uint32),
         ("frameSeq", C.c_uint64),
         ("localCounters", C.c_uint64),
-        ("countersBytes", C.c_uint32), ("reserved", C.c_uint32),
+        ("countersBytes", C.c_uint32), ("timeoutMs", C.c_uint32),
         ("peerCounters", C.c_uint64 * 8),
         ("peerFlags", C.c_uint64 * 8),
     ]

@@ -7,6 +7,30 @@
 
 namespace cadr {
 
+// Spin until the flag reaches frameSeq - or, when the caller gave a time budget (cadr_exchange_sync::timeoutMs), until it is
+// spent: a peer that died or never queued its frame must not leave this GPU spinning for ever.  The reference bounds its
+// only wait the same way (fence wait with a timeout, then CadR::Timeout: Renderer.cpp:982-993); here the wait is on the
+// device, so the expiry is reported where the host looks anyway: bit CADR_CULL_STATUS_EXCHANGE_TIMEOUT of the status word
+// of this rank's counters.
+__device__ __forceinline__ void waitForFlag(const unsigned long long* flag, unsigned long long frameSeq, uint32_t timeoutMs, uint64_t localCounters)
+{
+	unsigned long long t0 = 0, now = 0;
+	if(timeoutMs) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+	const unsigned long long budget = (unsigned long long)timeoutMs * 1000000ull;
+	for(;;) {
+		unsigned long long v;
+		asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+		if(v >= frameSeq) return;
+		if(timeoutMs) {
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+			if(now - t0 > budget) {
+				if(localCounters) atomicOr(&reinterpret_cast<cadr_cull_header*>(localCounters)->status, CADR_CULL_STATUS_EXCHANGE_TIMEOUT);
+				return;
+			}
+		}
+	}
+}
+
 __global__ void publishKernel(const __grid_constant__ cadr_exchange_sync S)
 {
 	// 1. this rank's counters -> slot `rank` of every peer's gathered counters
@@ -42,22 +66,13 @@ __global__ void publishAndWaitKernel(const __grid_constant__ cadr_exchange_sync 
 	if(threadIdx.x < S.world) {
 		unsigned long long* flag = reinterpret_cast<unsigned long long*>(S.peerFlags[threadIdx.x]) + S.rank;
 		asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(flag), "l"((unsigned long long)S.frameSeq) : "memory");
-		const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(S.peerFlags[S.rank]) + threadIdx.x;
-		unsigned long long v;
-		do {
-			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
-		} while(v < S.frameSeq);
+		waitForFlag(reinterpret_cast<const unsigned long long*>(S.peerFlags[S.rank]) + threadIdx.x, S.frameSeq, S.timeoutMs, S.localCounters);
 	}
 }
 
-__global__ void waitPeersKernel(const unsigned long long* flags, uint32_t world, unsigned long long frameSeq)
+__global__ void waitPeersKernel(const unsigned long long* flags, uint32_t world, unsigned long long frameSeq, uint32_t timeoutMs, uint64_t localCounters)
 {
-	if(threadIdx.x < world) {
-		unsigned long long v;
-		do {
-			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
-		} while(v < frameSeq);
-	}
+	if(threadIdx.x < world) waitForFlag(flags + threadIdx.x, frameSeq, timeoutMs, localCounters);
 }
 
 // Renderer-side pull of the survivors' instance-index runs (the exchange that is NOT free).  One CTA column
@@ -213,7 +228,8 @@ int cadr_b200_exchange_wait(cadr_ctx* ctx, const cadr_exchange_sync* sync, cadr_
 	if(int r = checkSync(sync, "exchange_wait")) return r;
 	if(!sync->peerFlags[sync->rank]) return setError(CADR_E_LOGIC, "exchange_wait: local flag array missing");
 	cudaStream_t s = ctx->pick(stream);
-	waitPeersKernel<<<1, 32, 0, s>>>(reinterpret_cast<const unsigned long long*>(sync->peerFlags[sync->rank]), sync->world, sync->frameSeq);
+	waitPeersKernel<<<1, 32, 0, s>>>(reinterpret_cast<const unsigned long long*>(sync->peerFlags[sync->rank]), sync->world, sync->frameSeq,
+	                                sync->timeoutMs, sync->localCounters);
 	ctx->launches++;
 	CADR_CUDA(cudaGetLastError());
 	return CADR_OK;

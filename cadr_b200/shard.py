@@ -166,6 +166,7 @@ class PeerExchange:
             raise ValueError("PeerExchange: deferred_wait needs at least four sets of gathered arrays")
         self.nsets, self.deferred = int(sets), bool(deferred_wait)
         self.fused_sync = True             # publish + wait as one kernel (False: two launches, as in round 1)
+        self.timeout_ms = 0                # > 0: budget of a stream-side wait for the peers (cadr_exchange_sync.timeoutMs); 0: wait for ever
         import ctypes as C
         from . import _capi
         self.ctx, self.group = ctx, group
@@ -263,7 +264,7 @@ class PeerExchange:
         frame = self.frame if frame is None else frame
         s = self._capi.ExchangeSync()
         s.world, s.rank, s.frameSeq = self.world, self.rank, frame
-        s.localCounters, s.countersBytes = local_counters, self.counters_bytes
+        s.localCounters, s.countersBytes, s.timeoutMs = local_counters, self.counters_bytes, int(self.timeout_ms)
         k = frame % self.nsets
         for r in range(self.world):
             s.peerCounters[r] = self.peer[r]["sets"][k]["counters"]

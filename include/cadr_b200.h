@@ -137,6 +137,7 @@ typedef struct cadr_cull_header {
 #define CADR_CULL_STATUS_REGION_OVERFLOW 1u
 #define CADR_CULL_STATUS_CHUNK_OVERFLOW  2u
 #define CADR_CULL_STATUS_BAD_RANGE_INDEX 4u     /* a culling record's stateSetIndex >= numStateSets: drawable skipped */
+#define CADR_CULL_STATUS_EXCHANGE_TIMEOUT 8u    /* multi-GPU: a peer did not publish its frame within cadr_exchange_sync::timeoutMs */
 #define CADR_CULL_WORK_ITEM_BYTES        128u   /* one self-contained descriptor per <= 1024 matrices */
 #define CADR_CULL_SMALL_LIST_MAX         32u    /* lists up to this size are evaluated by one thread; longer ones become work items */
 #define CADR_CULL_WORK_ITEM_INSTANCES    1024u
@@ -208,7 +209,11 @@ typedef struct cadr_exchange_sync {
 	uint32_t world, rank;
 	uint64_t frameSeq;                        /* > 0, strictly increasing per call pair                      */
 	uint64_t localCounters;                   /* this rank's counters buffer (header + packed counts)         */
-	uint32_t countersBytes, reserved;
+	uint32_t countersBytes;
+	uint32_t timeoutMs;                       /* 0: the waits spin until every peer has published (default); else the budget of a wait
+	                                           * in ms - when it is spent the wait ends and CADR_CULL_STATUS_EXCHANGE_TIMEOUT is set in
+	                                           * the status word of localCounters (the device-side form of the reference's bounded
+	                                           * fence wait -> CadR::Timeout, Renderer.cpp:982-993)                                   */
 	uint64_t peerCounters[CADR_MAX_PEERS];    /* rank r's gathered counters [world][countersBytes] as mapped here */
 	uint64_t peerFlags[CADR_MAX_PEERS];       /* rank r's flag array [world] u64 as mapped here                  */
 } cadr_exchange_sync;
@@ -364,7 +369,8 @@ CADR_API int  cadr_b200_exchange_publish(cadr_ctx* ctx, const cadr_exchange_sync
 /* Both in one launch (one kernel boundary less per frame).  Only where all ranks run concurrently: the kernel spins until
  * every peer has published frameSeq. */
 CADR_API int  cadr_b200_exchange_publish_and_wait(cadr_ctx* ctx, const cadr_exchange_sync* sync, cadr_stream stream);
-/* Block the stream (not the host) until every peer's flag in the LOCAL flag array has reached frameSeq. */
+/* Block the stream (not the host) until every peer's flag in the LOCAL flag array has reached frameSeq - or, with
+ * sync->timeoutMs > 0, until that budget is spent (both waits; see cadr_exchange_sync). */
 CADR_API int  cadr_b200_exchange_wait(cadr_ctx* ctx, const cadr_exchange_sync* sync, cadr_stream stream);
 
 /* Pull every peer's compacted instance-index runs into the local gathered index buffer (stream-ordered; call it after

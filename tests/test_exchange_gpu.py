@@ -188,3 +188,48 @@ def test_publish_and_wait_as_one_launch(ctx):
         ctx.sync()
         ds.close()
         ctx.arena_free(gathered); ctx.arena_free(flags)
+
+
+def test_a_peer_that_never_publishes_ends_a_bounded_wait(ctx):
+    """cadr_exchange_sync.timeoutMs: the stream-side waits give up when their budget is spent and report it in the status
+    word of the rank's own counters (the device-side form of the reference's fence wait with a timeout -> CadR::Timeout,
+    Renderer.cpp:982-993).  World of two on one device; "rank 1" never runs."""
+    import time
+    cb = ctx.cull_counters_bytes(2)
+    local, gathered0, gathered1, flags0, flags1 = (ctx.arena_alloc(256) for _ in range(5))
+    try:
+        for a in (local, gathered0, gathered1, flags0, flags1):
+            ctx.memset(a, 0, 256)
+        ctx.sync()
+        for seq, call in ((1, ctx.exchange_publish_and_wait), (2, ctx.exchange_wait)):
+            s = _capi.ExchangeSync()
+            s.world, s.rank, s.frameSeq, s.localCounters, s.countersBytes, s.timeoutMs = 2, 0, seq, local, cb, 40
+            s.peerCounters[0], s.peerCounters[1], s.peerFlags[0], s.peerFlags[1] = gathered0, gathered1, flags0, flags1
+            ctx.memset(local, 0, 256); ctx.sync()
+            t0 = time.monotonic()
+            call(s)
+            ctx.sync()
+            dt = time.monotonic() - t0
+            status = np.zeros(1, np.uint32)
+            ctx.memcpy_d2h(status, local); ctx.sync()
+            assert int(status[0]) & _capi.CULL_STATUS_EXCHANGE_TIMEOUT, "the expiry is reported in the status word"
+            assert 0.03 < dt < 5.0, f"waited {dt:.3f} s for a 40 ms budget"
+        # the peer's slot of rank 0's flags was published by the first call (rank 0 -> every rank), its own wait is what expired
+        f = np.zeros(2, np.uint64)
+        ctx.memcpy_d2h(f, flags1); ctx.sync()
+        assert int(f[0]) == 1
+        # a wait that is satisfied does not touch the status
+        ctx.memset(local, 0, 256)
+        one = np.array([5, 5], np.uint64)
+        ctx.memcpy_h2d(flags0, one); ctx.sync()
+        s = _capi.ExchangeSync()
+        s.world, s.rank, s.frameSeq, s.localCounters, s.countersBytes, s.timeoutMs = 2, 0, 5, local, cb, 40
+        s.peerCounters[0], s.peerCounters[1], s.peerFlags[0], s.peerFlags[1] = gathered0, gathered1, flags0, flags1
+        ctx.exchange_wait(s); ctx.sync()
+        status = np.zeros(1, np.uint32)
+        ctx.memcpy_d2h(status, local); ctx.sync()
+        assert int(status[0]) == 0
+    finally:
+        ctx.sync()
+        for a in (local, gathered0, gathered1, flags0, flags1):
+            ctx.arena_free(a)
