@@ -170,16 +170,21 @@ cullListRingKernel(const __grid_constant__ CullArgs A)
 // Three stages of 4 KiB per warp, eight warps per CTA (100 KiB), two CTAs per SM: as many bytes in flight per SM as the
 // 2-KiB ring at four CTAs.  The lane's history holds 4 bits per step (two 2-bit codes); sub-step t = 2 * step + half
 // is matrix 32 t + lane of the item, so the tail (emitItem) is the one of the other kernels with twice the steps.
-constexpr int    L2_STAGES      = 3;
+// Variant 11 (round 2, late): TWO stages per warp, so that THREE CTAs fit on an SM - 24 warps instead of 16 with the same 192 KiB
+// in flight per SM.
 constexpr int    L2_STAGE_BYTES = 64 * 64;
-constexpr size_t L2_WARP_BYTES  = L2_STAGES * L2_STAGE_BYTES + LW_DESCS * sizeof(WorkItem);   // 12.5 KiB
-constexpr size_t L2_SMEM_BYTES  = (CM_THREADS / 32) * L2_WARP_BYTES;                          // 100 KiB per CTA
-static_assert(2 * L2_SMEM_BYTES + 2048 <= 227 * 1024, "two CTAs per SM");
+template<int L2_STAGES> struct L2Geom {
+	static constexpr size_t WARP_BYTES = L2_STAGES * L2_STAGE_BYTES + LW_DESCS * sizeof(WorkItem);   // 12.5 KiB / 8.5 KiB
+	static constexpr size_t SMEM_BYTES = (CM_THREADS / 32) * WARP_BYTES;                              // 100 KiB / 68 KiB per CTA
+};
+static_assert(2 * (L2Geom<3>::SMEM_BYTES + 1024) <= 228 * 1024 && 3 * (L2Geom<2>::SMEM_BYTES + 1024) <= 228 * 1024, "two / three CTAs per SM");
 static_assert(CADR_CULL_WORK_ITEM_INSTANCES <= 16 * 64, "16 steps of 4 bits in a 64-bit history");
 
-__global__ void __launch_bounds__(CM_THREADS, 2)
+template<int L2_STAGES, int CTAS_PER_SM>
+__global__ void __launch_bounds__(CM_THREADS, CTAS_PER_SM)
 cullListRingPairKernel(const __grid_constant__ CullArgs A)
 {
+	constexpr size_t L2_WARP_BYTES = L2Geom<L2_STAGES>::WARP_BYTES;
 	extern __shared__ __align__(128) uint8_t lwSmem[];
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t ring = smemAddr(lwSmem) + (threadIdx.x >> 5) * uint32_t(L2_WARP_BYTES);   // shared-window address of my ring
@@ -622,11 +627,14 @@ static int launchListExperiment(cadr_ctx* ctx, const CullArgs& A, int variant, c
 		else             cullListWarpKernel<false, 6><<<g, CM_THREADS, 0, s>>>(A);
 		return A.medMax ? launchMediumBehind(ctx, A, gridL, s) : CADR_OK;
 	}
-	if(variant == 6) {
-		CADR_CUDA(cudaFuncSetAttribute(cullListRingPairKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L2_SMEM_BYTES)));
-		uint32_t grid2 = uint32_t(ctx->smCount) * 2u;
+	if(variant == 6 || variant == 11) {              // 6: three stages, two CTAs per SM; 11: two stages, three CTAs per SM
+		const void* fn = variant == 6 ? (const void*)cullListRingPairKernel<3, 2> : (const void*)cullListRingPairKernel<2, 3>;
+		const size_t smem = variant == 6 ? L2Geom<3>::SMEM_BYTES : L2Geom<2>::SMEM_BYTES;
+		CADR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+		uint32_t grid2 = uint32_t(ctx->smCount) * (variant == 6 ? 2u : 3u);
 		if(grid2 > need) grid2 = need;
-		cullListRingPairKernel<<<grid2, CM_THREADS, L2_SMEM_BYTES, s>>>(A);
+		void* args[] = {(void*)&A};
+		CADR_CUDA(cudaLaunchKernel(fn, dim3(grid2), dim3(CM_THREADS), args, smem, s));
 		return A.medMax ? launchMediumBehind(ctx, A, gridL, s) : CADR_OK;
 	}
 	return 1;
