@@ -389,6 +389,7 @@ __device__ __forceinline__ uint32_t histCount(unsigned long long h, uint32_t cod
 // Shared tail of the warp-per-item kernels: per-LOD totals from the lanes' histories, ONE 64-bit atomic to reserve the
 // item's command and index ranges, <= 3 command records (lanes 0..2), then the compacted indices, step by step, from
 // the histories (the matrices are not read again).  `desc` = shared-window address of the item's 128-byte descriptor.
+template<bool LANE_RUNS = false>
 __device__ __forceinline__ void emitItem(const CullArgs& A, unsigned long long hist, uint32_t steps, uint32_t nb,
                                          uint32_t desc, const uint4& a0, const uint4& a1, uint32_t lane, uint32_t laneMatrix)
 {
@@ -429,6 +430,22 @@ __device__ __forceinline__ void emitItem(const CullArgs& A, unsigned long long h
 			writeCommandRecord(A, ci, psCount, tl, psFirst, (lane == 0) ? i0 : (lane == 1) ? i1 : i2,
 			                   a1.x, lane, ldsU4(desc + 96u), ldsU4(desc + 112u));
 		}
+	}
+	if constexpr(LANE_RUNS) {
+		// A/B (variant 12): the order of the indices inside a run is free (comparisons sort them), so every lane writes ITS survivors
+		// of a LOD as one contiguous piece of the run - two warp scans of the lanes' counts instead of three votes per step, and a
+		// loop over the lane's set bits instead of over the item's steps (~130 instead of ~640 instructions per 1000-matrix item, a
+		// shorter pause in the warp's matrix stream), at the price of uncoalesced 4-byte stores.
+		const unsigned long long lo = hist & 0x5555555555555555ull, hi = (hist >> 1) & 0x5555555555555555ull;
+		unsigned long long m0 = lo & ~hi, m1 = hi & ~lo, m2 = lo & hi;       // bit 2s: step s has code 1 / 2 / 3
+		const uint32_t p01 = uint32_t(__popcll(m0)) | (uint32_t(__popcll(m1)) << 16), p2 = uint32_t(__popcll(m2));   // sums <= 1024 each
+		const uint32_t e01 = warpInclusiveScan(p01, int(lane)) - p01, e2 = warpInclusiveScan(p2, int(lane)) - p2;
+		const uint32_t first = a0.w + laneMatrix;
+		uint32_t o0 = i0 + (e01 & 0xffffu), o1 = i1 + (e01 >> 16), o2 = i2 + e2;
+		for(; m0; m0 &= m0 - 1) A.instOut[o0++] = first + (uint32_t(__ffsll((long long)m0) - 1) << 4);     // bit 2s -> instance 32 s
+		for(; m1; m1 &= m1 - 1) A.instOut[o1++] = first + (uint32_t(__ffsll((long long)m1) - 1) << 4);
+		for(; m2; m2 &= m2 - 1) A.instOut[o2++] = first + (uint32_t(__ffsll((long long)m2) - 1) << 4);
+		return;
 	}
 	uint32_t idx = a0.w + laneMatrix;     // firstInstance + the matrix of each step this lane evaluated (`lane` except in cullListTmaKernel)
 	for(uint32_t s = 0; s < steps; s++, idx += 32u, hist >>= 2) {
@@ -666,7 +683,8 @@ constexpr int LW_DESCS = 4;     // descriptor ring per warp: items A, B, C and t
 
 // FLAT (CADR_B200_CULL_VARIANT=5): after the queue of long items has run dry, the warp goes on with the medium items
 // itself instead of leaving them to cullMediumKernel.
-template<bool FLAT, int CTAS_PER_SM = 4>        // CTAS_PER_SM: 4 in the product (64 registers); 5 / 6 are A/B variants (48 / 40 registers)
+template<bool FLAT, int CTAS_PER_SM = 4, bool LANE_RUNS = false>   // CTAS_PER_SM: 4 in the product (64 registers), 5 / 6 are A/B variants (48 / 40
+                                                                  // registers); LANE_RUNS: A/B variant 12 of the index write-out (emitItem)
 __global__ void __launch_bounds__(CM_THREADS, CTAS_PER_SM)
 cullListWarpKernel(const __grid_constant__ CullArgs A)
 {
@@ -752,7 +770,7 @@ cullListWarpKernel(const __grid_constant__ CullArgs A)
 		}
 		hist >>= (64u - 2u * steps);       // step s now sits at bits [2s, 2s + 1]
 
-		emitItem(A, hist, steps, nb, dA, a0, a1, lane, lane);
+		emitItem<LANE_RUNS>(A, hist, steps, nb, dA, a0, a1, lane, lane);
 		__syncwarp();       // A's descriptor slot is rewritten three iterations from now; keep the warp together
 
 		// ---- advance the pipeline: B becomes A ---------------------------------------------------------------
@@ -852,7 +870,7 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 	// cullListWarpKernel instead of cullMediumKernel); 4 = every list longer than 32 matrices in the one queue (the
 	// state before the medium path existed), for A/B measurements
 	const int variant = cullVariant();
-	A.medMax = ((variant == 2 || (variant >= 5 && variant <= 11)) && p.chunkCapacity) ? CADR_CULL_MEDIUM_LIST_MAX : 0u;
+	A.medMax = ((variant == 2 || (variant >= 5 && variant <= 12)) && p.chunkCapacity) ? CADR_CULL_MEDIUM_LIST_MAX : 0u;
 
 	uint32_t gridS = (p.numDrawables + CS_THREADS - 1) / CS_THREADS;
 	ctx->timeBegin(KS_CULL_SMALL, s);

@@ -619,6 +619,10 @@ static int launchListExperiment(cadr_ctx* ctx, const CullArgs& A, int variant, c
 		CADR_CUDA(cudaLaunchKernel(fn, dim3(gridL), dim3(CM_THREADS), args, smem, s));
 		return A.medMax ? launchMediumBehind(ctx, A, gridL, s) : CADR_OK;
 	}
+	if(variant == 12) {                             // the product kernel with the lane-run write-out (emitItem<true>)
+		cullListWarpKernel<false, 4, true><<<gridL, CM_THREADS, 0, s>>>(A);
+		return A.medMax ? launchMediumBehind(ctx, A, gridL, s) : CADR_OK;
+	}
 	if(variant == 9 || variant == 10) {             // the product kernel at 5 / 6 CTAs per SM (40 / 48 warps, 48 / 40 registers)
 		const uint32_t ctas = variant == 9 ? 5u : 6u;
 		uint32_t g = uint32_t(ctx->smCount) * ctas;
