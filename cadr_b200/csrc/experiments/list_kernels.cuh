@@ -180,7 +180,7 @@ template<int L2_STAGES> struct L2Geom {
 static_assert(2 * (L2Geom<3>::SMEM_BYTES + 1024) <= 228 * 1024 && 3 * (L2Geom<2>::SMEM_BYTES + 1024) <= 228 * 1024, "two / three CTAs per SM");
 static_assert(CADR_CULL_WORK_ITEM_INSTANCES <= 16 * 64, "16 steps of 4 bits in a 64-bit history");
 
-template<int L2_STAGES, int CTAS_PER_SM>
+template<int L2_STAGES, int CTAS_PER_SM, bool LANE_RUNS = false>
 __global__ void __launch_bounds__(CM_THREADS, CTAS_PER_SM)
 cullListRingPairKernel(const __grid_constant__ CullArgs A)
 {
@@ -304,7 +304,7 @@ cullListRingPairKernel(const __grid_constant__ CullArgs A)
 		}
 		if(steps) hist >>= (64u - 4u * steps);      // sub-step t = 2 * step + half now sits at bits [2t, 2t + 1]
 
-		emitItem(A, hist, 2u * steps, nb, dA, a0, a1, lane, lane);
+		emitItem<LANE_RUNS>(A, hist, 2u * steps, nb, dA, a0, a1, lane, lane);
 		__syncwarp();       // A's descriptor slot is rewritten two iterations from now; keep the warp together
 
 		// ---- advance the pipeline: B becomes A ---------------------------------------------------------------
@@ -619,6 +619,12 @@ static int launchListExperiment(cadr_ctx* ctx, const CullArgs& A, int variant, c
 		CADR_CUDA(cudaLaunchKernel(fn, dim3(gridL), dim3(CM_THREADS), args, smem, s));
 		return A.medMax ? launchMediumBehind(ctx, A, gridL, s) : CADR_OK;
 	}
+	if(variant == 13 || variant == 14) {            // the product kernel with only 3 / 2 CTAs launched per SM (24 / 16 warps): how the time follows
+		uint32_t g = uint32_t(ctx->smCount) * (variant == 13 ? 3u : 2u);      // the number of 2-KiB steps in flight
+		if(g > need) g = need;
+		cullListWarpKernel<false><<<g, CM_THREADS, 0, s>>>(A);
+		return A.medMax ? launchMediumBehind(ctx, A, gridL, s) : CADR_OK;
+	}
 	if(variant == 12) {                             // the product kernel with the lane-run write-out (emitItem<true>)
 		cullListWarpKernel<false, 4, true><<<gridL, CM_THREADS, 0, s>>>(A);
 		return A.medMax ? launchMediumBehind(ctx, A, gridL, s) : CADR_OK;
@@ -631,11 +637,11 @@ static int launchListExperiment(cadr_ctx* ctx, const CullArgs& A, int variant, c
 		else             cullListWarpKernel<false, 6><<<g, CM_THREADS, 0, s>>>(A);
 		return A.medMax ? launchMediumBehind(ctx, A, gridL, s) : CADR_OK;
 	}
-	if(variant == 6 || variant == 11) {              // 6: three stages, two CTAs per SM; 11: two stages, three CTAs per SM
-		const void* fn = variant == 6 ? (const void*)cullListRingPairKernel<3, 2> : (const void*)cullListRingPairKernel<2, 3>;
-		const size_t smem = variant == 6 ? L2Geom<3>::SMEM_BYTES : L2Geom<2>::SMEM_BYTES;
+	if(variant == 6 || variant == 11 || variant == 15) {   // 6: three stages, two CTAs per SM; 11: two stages, three CTAs; 15: 6 with the lane-run write-out
+		const void* fn = variant == 6 ? (const void*)cullListRingPairKernel<3, 2> : variant == 15 ? (const void*)cullListRingPairKernel<3, 2, true> : (const void*)cullListRingPairKernel<2, 3>;
+		const size_t smem = variant != 11 ? L2Geom<3>::SMEM_BYTES : L2Geom<2>::SMEM_BYTES;
 		CADR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-		uint32_t grid2 = uint32_t(ctx->smCount) * (variant == 6 ? 2u : 3u);
+		uint32_t grid2 = uint32_t(ctx->smCount) * (variant != 11 ? 2u : 3u);
 		if(grid2 > need) grid2 = need;
 		void* args[] = {(void*)&A};
 		CADR_CUDA(cudaLaunchKernel(fn, dim3(grid2), dim3(CM_THREADS), args, smem, s));

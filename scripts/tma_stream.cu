@@ -9,6 +9,8 @@
 //   3  plain bulk copy (cp.async.bulk), 1 x 2048 B per stage
 //   4  plain bulk copy, 4 x 512 B per stage (destinations 528 B apart: the skew that would make unswizzled reads conflict-free)
 //   5  no TMA: 2 x LDG.256 per lane per step, next step prefetched in registers (the access structure of cullListWarpKernel)
+//   6, 7  mode 5 with the L2 prefetch-size hint .L2::128B / .L2::256B on the loads
+//   8  mode 5 with every LDG.256 instruction covering 1 KiB contiguous (a lane then holds halves of two rows)
 // build + run:  nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/tma_stream scripts/tma_stream.cu -lcuda && /tmp/tma_stream
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -33,7 +35,7 @@ streamKernel(const __grid_constant__ CUtensorMap map, const uint8_t* buf, uint32
 	constexpr uint32_t PITCH = MODE == 4 ? 2176u : 2048u;
 	const uint32_t ring = smem0 + warp * (STAGES * PITCH);
 	const uint32_t bars = smem0 + WARPS * STAGES * PITCH + warp * 32u;
-	if(MODE != 5 && lane == 0) {
+	if(MODE < 5 && lane == 0) {
 		for(int s = 0; s < STAGES; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bars + 8u * s) : "memory");
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
@@ -47,12 +49,26 @@ streamKernel(const __grid_constant__ CUtensorMap map, const uint8_t* buf, uint32
 		if(item >= items) break;
 		const uint64_t src0 = reinterpret_cast<uint64_t>(buf) + uint64_t(item) * ITEM_ROWS * 64ull;
 		constexpr uint32_t STEPS = ITEM_ROWS / 32;
-		if constexpr(MODE == 5) {
-			const uint8_t* p = reinterpret_cast<const uint8_t*>(src0) + 64u * lane;
+		if constexpr(MODE >= 5) {
+			// 5: lane i reads its own 64-byte row as two LDG.256 (each instruction touches sectors 0+2 / 1+3 of 16 lines: cullListWarpKernel)
+			// 6 / 7: the same with the L2 prefetch-size hint .L2::128B / .L2::256B
+			// 8: every LDG.256 instruction covers 1 KiB CONTIGUOUS (lane i: bytes 32 i, then 1024 + 32 i) - halves of two rows per lane
+			const uint32_t SECOND = MODE == 8 ? 1024u : 32u;
+			const uint8_t* p = reinterpret_cast<const uint8_t*>(src0) + (MODE == 8 ? 32u : 64u) * lane;
 			uint32_t c[16], n[16];
-			auto ld = [](uint32_t (&r)[16], const uint8_t* q) {
+			auto ld = [&](uint32_t (&r)[16], const uint8_t* q) {
+				if constexpr(MODE == 6) {
+					asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(q));
+					asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "l"(q + SECOND));
+				}
+				else if constexpr(MODE == 7) {
+					asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(q));
+					asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "l"(q + SECOND));
+				}
+				else {
 				asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(q));
-				asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "l"(q + 32));
+				asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "l"(q + SECOND));
+				}
 			};
 			ld(c, p);
 			for(uint32_t s = 0; s < STEPS; s++) {
@@ -124,7 +140,7 @@ static CUtensorMap makeMap(void* base, uint32_t rowBytes, CUtensorMapSwizzle sw,
 template<int MODE>
 static void run(const char* name, const CUtensorMap& map, const uint8_t* buf, uint32_t items, unsigned int* cursor, unsigned long long* sink, int sms)
 {
-	const size_t smem = MODE == 5 ? 0 : 1024 + WARPS * STAGES * (MODE == 4 ? 2176 : 2048) + WARPS * 32;
+	const size_t smem = MODE >= 5 ? 0 : 1024 + WARPS * STAGES * (MODE == 4 ? 2176 : 2048) + WARPS * 32;
 	cudaFuncSetAttribute(streamKernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
 	int occ = 0;
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, streamKernel<MODE>, 256, smem);
@@ -164,6 +180,9 @@ int main(int argc, char** argv)
 	                  m64p = makeMap(buf, 64, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 	switch(mode) {
 	case 5: run<5>("LDG.256 x2 per lane, register prefetch", m64, buf, items, cursor, sink, sms); break;
+	case 6: run<6>("LDG.256 x2 per lane + .L2::128B", m64, buf, items, cursor, sink, sms); break;
+	case 7: run<7>("LDG.256 x2 per lane + .L2::256B", m64, buf, items, cursor, sink, sms); break;
+	case 8: run<8>("LDG.256 x2, each instruction 1 KiB contiguous", m64, buf, items, cursor, sink, sms); break;
 	case 0: run<0>("tensor copy, 32 rows x 64 B, SWIZZLE_64B", m64, buf, items, cursor, sink, sms); break;
 	case 1: run<1>("tensor copy, 16 rows x 128 B, SWIZZLE_128B", m128, buf, items, cursor, sink, sms); break;
 	case 10: run<0>("tensor copy, 32 rows x 64 B, SWIZZLE_64B, L2 promotion 256 B", m64p, buf, items, cursor, sink, sms); break;
