@@ -870,7 +870,7 @@ int launchCullCompact(cadr_ctx* ctx, const cadr_cull_params& p, cudaStream_t s, 
 	// cullListWarpKernel instead of cullMediumKernel); 4 = every list longer than 32 matrices in the one queue (the
 	// state before the medium path existed), for A/B measurements
 	const int variant = cullVariant();
-	A.medMax = ((variant == 2 || (variant >= 5 && variant <= 15)) && p.chunkCapacity) ? CADR_CULL_MEDIUM_LIST_MAX : 0u;
+	A.medMax = ((variant == 2 || (variant >= 5 && variant <= 16)) && p.chunkCapacity) ? CADR_CULL_MEDIUM_LIST_MAX : 0u;
 
 	uint32_t gridS = (p.numDrawables + CS_THREADS - 1) / CS_THREADS;
 	ctx->timeBegin(KS_CULL_SMALL, s);

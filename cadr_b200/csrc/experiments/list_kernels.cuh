@@ -580,6 +580,131 @@ cullListTmaKernel(const __grid_constant__ CullArgs A)
 }
 
 
+// ---------------------------------------------------------------------------------------------------
+// cullListWarpKernel with load instructions that cover contiguous memory (experiment variant 16)
+// ---------------------------------------------------------------------------------------------------
+// In cullListWarpKernel a lane reads its own 64-byte matrix as two LDG.256: each load INSTRUCTION of the warp then touches
+// every other 32-byte sector of 2 KiB (sectors 0 + 2 of 16 lines, then 1 + 3).  In isolation an instruction that covers
+// 1 KiB contiguous streams 2.5 % faster (scripts/tma_stream.cu modes 5 / 8: 6 500 -> 6 660 GB/s).  Here the first load of
+// a step reads sector `lane` of the step's first KiB, the second sector `lane ^ 1` of its second KiB; a lane pair (2j, 2j+1)
+// then holds the four halves of matrices j and 16 + j, and one round of eight shuffles gives the even lane matrix j and
+// the odd lane matrix 16 + j (24 instructions per step: 8 SEL + 8 SHFL + 8 SEL).  The raw halves stay in flight in
+// registers exactly like `nxt` in the product kernel; the exchange happens when the step is evaluated.
+struct RawStep { float4 a0, a1, b0, b1; };
+
+__device__ __forceinline__ void ldg256(float4& x, float4& y, const uint8_t* p)
+{
+	asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w), "=f"(y.x), "=f"(y.y), "=f"(y.z), "=f"(y.w) : "l"(p));
+}
+// the halves this lane fetches of a step of `rows` matrices starting at `base` (rows >= 32: a full step)
+__device__ __forceinline__ void loadRaw(RawStep& r, const uint8_t* base, uint32_t rows, uint32_t lane)
+{
+	if((lane >> 1) < rows) ldg256(r.a0, r.a1, base + 32u * lane);                       // matrix lane >> 1, half lane & 1
+	if(16u + (lane >> 1) < rows) ldg256(r.b0, r.b1, base + 1024u + 32u * (lane ^ 1u));   // matrix 16 + (lane >> 1), half (lane & 1) ^ 1
+}
+// even lane: matrix lane >> 1 = {own a, partner's a}; odd lane: matrix 16 + (lane >> 1) = {own b, partner's b}.  All lanes call it.
+__device__ __forceinline__ Mat exchangeHalves(const RawStep& r, uint32_t lane)
+{
+	const bool odd = lane & 1u;
+	Mat m;
+	m.c0 = odd ? r.b0 : r.a0; m.c1 = odd ? r.b1 : r.a1;
+	const float4 s0 = odd ? r.a0 : r.b0, s1 = odd ? r.a1 : r.b1;
+	m.c2 = make_float4(__shfl_xor_sync(0xffffffffu, s0.x, 1), __shfl_xor_sync(0xffffffffu, s0.y, 1), __shfl_xor_sync(0xffffffffu, s0.z, 1), __shfl_xor_sync(0xffffffffu, s0.w, 1));
+	m.c3 = make_float4(__shfl_xor_sync(0xffffffffu, s1.x, 1), __shfl_xor_sync(0xffffffffu, s1.y, 1), __shfl_xor_sync(0xffffffffu, s1.z, 1), __shfl_xor_sync(0xffffffffu, s1.w, 1));
+	return m;
+}
+
+__global__ void __launch_bounds__(CM_THREADS, 4)
+cullListWarpContigKernel(const __grid_constant__ CullArgs A)
+{
+	__shared__ __align__(16) uint8_t sDescs[CM_THREADS / 32][LW_DESCS * sizeof(WorkItem)];
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t myMatrix = (lane & 1u) ? 16u + (lane >> 1) : (lane >> 1);        // the matrix of each step this lane evaluates
+	const uint32_t descs = smemAddr(sDescs[threadIdx.x >> 5]);
+	const unsigned FULL = 0xffffffffu;
+
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+	uint32_t total, totalM;
+	bool overflow;
+	queueExtents(A, total, totalM, overflow);
+	if(overflow && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&A.hdr->status, CADR_CULL_STATUS_CHUNK_OVERFLOW);
+	const uint32_t numWarps = gridDim.x * (CM_THREADS / 32);
+	uint32_t batch = total / (numWarps * 16u);
+	batch = batch < 1u ? 1u : (batch > 8u ? 8u : batch);
+
+	uint32_t rNext = 0, rEnd = 0;
+	uint32_t iA, iB, iC;
+	{
+		const uint32_t first = batch < 3u ? 3u : batch;
+		uint32_t r = 0;
+		if(lane == 0) { r = atomicAdd(&A.hdr->chunkCursor, first); rNext = r + 3u; rEnd = r + first; }
+		r = __shfl_sync(FULL, r, 0);
+		iA = r; iB = r + 1u; iC = r + 2u;
+	}
+	uint32_t seq = 0;
+	uint4 dIn;
+	RawStep cur, nxt;
+	{
+		const uint4 a = loadItemWord(A, iA, total, lane);
+		dIn = loadItemWord(A, iB, total, lane);
+		if(lane < 8) stsU4(descs + lane * 16u, a);
+		const uint64_t m = uint64_t(__shfl_sync(FULL, a.x, 0)) | (uint64_t(__shfl_sync(FULL, a.y, 0)) << 32);
+		loadRaw(cur, reinterpret_cast<const uint8_t*>(m), __shfl_sync(FULL, a.z, 0), lane);
+	}
+
+	while(iA < total) {
+		if(lane < 8) stsU4(descs + ((seq + 1u) & 3u) * 128u + lane * 16u, dIn);
+		dIn = loadItemWord(A, iC, total, lane);
+		uint32_t iD = 0;
+		if(lane == 0) {
+			if(rNext < rEnd) iD = rNext++;
+			else { iD = atomicAdd(&A.hdr->chunkCursor, batch); rNext = iD + 1u; rEnd = iD + batch; }
+		}
+		__syncwarp();
+		const uint32_t dA = descs + (seq & 3u) * 128u;
+		const uint4 a0 = ldsU4(dA), a1 = ldsU4(dA + 16u), a2 = ldsU4(dA + 32u), a3 = ldsU4(dA + 48u);
+		const uint4 b0 = ldsU4(descs + ((seq + 1u) & 3u) * 128u);
+		LodInfo L;
+		L.lodCount = a1.z;
+		L.sphere = make_float4(__uint_as_float(a2.x), __uint_as_float(a2.y), __uint_as_float(a2.z), __uint_as_float(a2.w));
+		L.thr0 = __uint_as_float(a3.x); L.thr1 = __uint_as_float(a3.y);
+
+		unsigned long long hist = 0;
+		uint32_t nb = 0, steps = 1, left = a0.z;
+		const uint8_t* p = reinterpret_cast<const uint8_t*>(uint64_t(a0.x) | (uint64_t(a0.y) << 32));     // base of the step being evaluated
+		while(left > 32u) {
+			loadRaw(nxt, p + 2048, left - 32u, lane);
+			const Mat m = exchangeHalves(cur, lane);
+			bool nbi = false;
+			const int lod = CADR_DIAG_NOEVAL(A, m) evalInstance(m, L, A.plane, A.eye, nbi);
+			nb += nbi ? 1u : 0u;
+			hist = (hist >> 2) | ((unsigned long long)uint32_t(lod + 1) << 62);
+			steps++;
+			cur = nxt; p += 2048; left -= 32u;
+		}
+		{
+			loadRaw(nxt, reinterpret_cast<const uint8_t*>(uint64_t(b0.x) | (uint64_t(b0.y) << 32)), b0.z, lane);
+			const Mat m = exchangeHalves(cur, lane);
+			uint32_t code = 0;
+			if(myMatrix < left) {
+				bool nbi = false;
+				const int lod = CADR_DIAG_NOEVAL(A, m) evalInstance(m, L, A.plane, A.eye, nbi);
+				nb += nbi ? 1u : 0u;
+				code = uint32_t(lod + 1);
+			}
+			hist = (hist >> 2) | ((unsigned long long)code << 62);
+			cur = nxt;
+		}
+		hist >>= (64u - 2u * steps);
+
+		emitItem(A, hist, steps, nb, dA, a0, a1, lane, myMatrix);
+		__syncwarp();
+		seq++;
+		iA = iB; iB = iC; iC = __shfl_sync(FULL, iD, 0);
+	}
+}
+
 // cullMediumKernel behind a list kernel of this file, as the product launches it behind cullListWarpKernel
 static int launchMediumBehind(cadr_ctx* ctx, const CullArgs& A, uint32_t gridL, cudaStream_t s)
 {
@@ -623,6 +748,10 @@ static int launchListExperiment(cadr_ctx* ctx, const CullArgs& A, int variant, c
 		uint32_t g = uint32_t(ctx->smCount) * (variant == 13 ? 3u : 2u);      // the number of 2-KiB steps in flight
 		if(g > need) g = need;
 		cullListWarpKernel<false><<<g, CM_THREADS, 0, s>>>(A);
+		return A.medMax ? launchMediumBehind(ctx, A, gridL, s) : CADR_OK;
+	}
+	if(variant == 16) {                             // the product kernel's structure with contiguous load instructions
+		cullListWarpContigKernel<<<gridL, CM_THREADS, 0, s>>>(A);
 		return A.medMax ? launchMediumBehind(ctx, A, gridL, s) : CADR_OK;
 	}
 	if(variant == 12) {                             // the product kernel with the lane-run write-out (emitItem<true>)
