@@ -278,8 +278,11 @@ __device__ __forceinline__ void smallListsBody(const CullArgs& A, SmallShared& s
 
 // FUSED = true additionally does the work of processDrawablesKernel for the same drawable (handle resolve + Tier R
 // records), so the drawable list is read once per frame and the indirect / pointers records are not re-read.
-template<int LEVEL, bool FUSED, int THREADS = CS_THREADS>
-__global__ void __launch_bounds__(THREADS)
+// MIN_CTAS = 0: no minimum named - the compiler then settles on 64 registers without a spill (32 warps per SM), which is also what
+// measures best.  Naming one changes its choice: `__launch_bounds__(64, 1)` makes it take 89 registers and C2 falls from 0.482 to
+// 0.577 ms; 56 / 48 registers (18 / 20 CTAs per SM, a few spills; A/B variants) give 0.484 / 0.526 ms (profiles/r03l_ab_small_minctas.jsonl).
+template<int LEVEL, bool FUSED, int THREADS = CS_THREADS, int MIN_CTAS = 0>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
 cullSmallKernel(const __grid_constant__ CullArgs A)
 {
 	__shared__ SmallShared sh;

@@ -246,6 +246,19 @@ cullSmallRecordsStagedKernel(const __grid_constant__ CullArgs A)
 static int launchSmallExperiment(cadr_ctx* ctx, const CullArgs& A, const cadr_cull_params& p, bool fused, cudaStream_t s)
 {
 	if(!fused) return 1;
+	if(const char* v = std::getenv("CADR_B200_SMALL_MINCTAS"); v && (std::atoi(v) == 18 || std::atoi(v) == 20)) {
+		// the product kernel (64-thread CTAs) with a register cap: 18 / 20 CTAs per SM = 56 / 48 registers, 36 / 40 warps instead of 32
+		const uint32_t g = (p.numDrawables + 63) / 64;
+		switch(p.handleLevel * 100 + std::atoi(v)) {
+		case 118: cullSmallKernel<1, true, 64, 18><<<g, 64, 0, s>>>(A); break;
+		case 218: cullSmallKernel<2, true, 64, 18><<<g, 64, 0, s>>>(A); break;
+		case 318: cullSmallKernel<3, true, 64, 18><<<g, 64, 0, s>>>(A); break;
+		case 120: cullSmallKernel<1, true, 64, 20><<<g, 64, 0, s>>>(A); break;
+		case 220: cullSmallKernel<2, true, 64, 20><<<g, 64, 0, s>>>(A); break;
+		default:  cullSmallKernel<3, true, 64, 20><<<g, 64, 0, s>>>(A); break;
+		}
+		return CADR_OK;
+	}
 	if(const char* v = std::getenv("CADR_B200_SMALL_THREADS"); v && (std::atoi(v) == 256 || std::atoi(v) == 128 || std::atoi(v) == 32)) {
 		const uint32_t t = uint32_t(std::atoi(v)), g = (p.numDrawables + t - 1) / t;      // the same kernel with other CTA sizes (product: CS_THREADS)
 		switch(p.handleLevel * 1000 + t) {
